@@ -1,0 +1,100 @@
+"""Pin the numpy oracle against fixtures produced by the reference itself
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden_ctor, golden_state, load_golden
+from oracle import nsd_oracle as O
+
+SMALL = ["small_uni", "small_bi"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("tag,tol", [("f64", 1e-11), ("f32", 2e-5)])
+def test_stages_match_reference(name, tag, tol):
+    g = load_golden(f"{name}_{tag}")
+    kw = golden_ctor(g)
+    sd = golden_state(g)
+    dt = np.float64
+    X = g["X"].astype(dt)
+    taps = g["taps"].astype(dt)
+    np.testing.assert_allclose(O.gaussian_taps(kw["gaussianSmoothWidth"]), g["taps"].astype(np.float32), rtol=2e-6, atol=1e-9)
+    ys = O.smooth(X, taps)
+    np.testing.assert_allclose(ys, g["smoothed"], rtol=tol, atol=tol)
+    z = O.softsign(O.day_affine(ys, sd["dayWeights"].astype(dt), sd["dayBias"].astype(dt), g["dayIdx"]))
+    np.testing.assert_allclose(z, g["z"], rtol=tol, atol=tol)
+    p = O.unfold(z, kw["kernelLen"], kw["strideLen"])
+    np.testing.assert_allclose(p, g["patches"], rtol=tol, atol=tol)
+    # unfold is pure data movement: exact on the reference's own z
+    assert np.array_equal(O.unfold(g["z"], kw["kernelLen"], kw["strideLen"]), g["patches"])
+    ws = [{k: v.astype(dt) for k, v in d.items()} for d in O.split_gru_state(sd, kw["layer_dim"], kw["bidirectional"])]
+    hid, _ = O.gru_fwd(g["patches"].astype(dt), ws, kw["bidirectional"])
+    np.testing.assert_allclose(hid, g["hid"], rtol=tol * 10, atol=tol * 10)
+    logits = O.linear(hid, sd["fc_decoder_out.weight"].astype(dt), sd["fc_decoder_out.bias"].astype(dt))
+    np.testing.assert_allclose(logits, g["logits"], rtol=tol * 10, atol=tol * 10)
+    lp = O.log_softmax(g["logits"].astype(dt), axis=2)
+    np.testing.assert_allclose(np.transpose(lp, (1, 0, 2)), g["log_probs_tbc"], rtol=tol, atol=tol)
+    assert np.array_equal(O.out_lens(g["X_len"], kw["kernelLen"], kw["strideLen"]), g["out_lens"])
+
+
+@pytest.mark.parametrize("name", SMALL + ["comp_uni", "comp_bi"])
+def test_ctc_and_decode_match_reference(name):
+    g = load_golden(f"{name}_f32")
+    loss, nll, grad = O.ctc_loss(g["log_probs_tbc"], g["y"], g["out_lens"], g["y_len"])
+    np.testing.assert_allclose(loss, g["loss"], rtol=2e-6)
+    np.testing.assert_allclose(nll, g["nll"], rtol=2e-6, atol=1e-5)
+    np.testing.assert_allclose(grad, g["dlog_probs_tbc"], rtol=1e-4, atol=2e-7)
+    dec = O.greedy_decode(g["log_probs_tbc"], g["out_lens"])
+    for b, seq in enumerate(dec):
+        assert seq == g["decoded"][b, : g["decoded_len"][b]].tolist()
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_full_backward_matches_reference(name):
+    g = load_golden(f"{name}_f64")
+    kw = golden_ctor(g)
+    sd = golden_state(g)
+    loss, logits, grads = O.train_loss_and_grads(
+        sd, g["X"], g["dayIdx"], g["y"], g["X_len"], g["y_len"], kernel_len=kw["kernelLen"],
+        stride_len=kw["strideLen"], n_layers=kw["layer_dim"], bidirectional=kw["bidirectional"])
+    np.testing.assert_allclose(loss, g["loss"], rtol=1e-10)
+    np.testing.assert_allclose(logits, g["logits"], rtol=1e-9, atol=1e-11)
+    names = [str(n) for n in g["live_grad_names"]]
+    assert sorted(grads.keys()) == names
+    for n in names:
+        np.testing.assert_allclose(grads[n], g["grad." + n], rtol=1e-7, atol=1e-11, err_msg=n)
+
+
+def test_ctc_edge_cases_against_torch():
+    """empty target, repeated labels, infeasible (zero_infinity), input shorter than T."""
+    import torch
+    rng = np.random.default_rng(3)
+    T, B, C = 12, 5, 6
+    lp = O.log_softmax(rng.standard_normal((T, B, C)), axis=2)
+    y = np.array([[1, 1, 2, 0, 0, 0], [3, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [2, 2, 2, 2, 2, 2], [5, 4, 5, 4, 0, 0]], dtype=np.int32)
+    yl = np.array([3, 1, 0, 6, 4], dtype=np.int32)
+    il = np.array([12, 7, 5, 9, 12], dtype=np.int32)       # utt 3 infeasible: needs 11 frames, has 9
+    loss, nll, grad = O.ctc_loss(lp, y, il, yl)
+    t = torch.tensor(lp, requires_grad=True)
+    ref = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(t, torch.tensor(y), torch.tensor(il), torch.tensor(yl))
+    ref.backward()
+    np.testing.assert_allclose(loss, ref.item(), rtol=1e-12)
+    np.testing.assert_allclose(grad, t.grad.numpy(), rtol=1e-9, atol=1e-14)
+    assert nll[3] == 0.0 and np.all(grad[:, 3] == 0)
+
+
+def test_edit_distance():
+    assert O.edit_distance([1, 2, 3], [1, 2, 3]) == 0
+    assert O.edit_distance([], [4, 5]) == 2
+    assert O.edit_distance([1, 2, 3, 4], [2, 3, 5]) == 2
+    assert O.edit_distance([7], []) == 1
+    assert O.phoneme_error_rate([[1, 2], [3]], np.array([[1, 2, 0], [4, 5, 6]]), [2, 3]) == (3, 5)
+
+
+def test_frontend_errors():
+    with pytest.raises(ZeroDivisionError):
+        O.gaussian_taps(0)
+    with pytest.raises(RuntimeError):
+        O.unfold(np.zeros((1, 5, 2)), 8, 2)
+    with pytest.raises(IndexError):
+        O.day_affine(np.zeros((1, 4, 2)), np.zeros((2, 2, 2)), np.zeros((2, 1, 2)), np.array([2]))
