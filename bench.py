@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Headline benchmark: train utterances/sec of the GRUDecoder + CTC step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+One "step" = forward -> out_lens -> log-softmax + CTC -> backward -> (gradient all-reduce) -> Adam step on one
+synthetic batch of the competition shape (256 features, 24 days, 41 classes; B=64 per GPU, T=500), i.e.
+neural_decoder_trainer.py:208-218, 242, 251-260.  Workload = BASELINE.json configs[1]: bidirectional 5x1024
+GRUDecoder, dropout 0.4, batch-sharded data parallel (weak scaling: 64 utterances per GPU).
+
+Our arm prints one JSON line with
+  value         utt/s, inputs resident in HBM, CUDA events, max over ranks
+  e2e           utt/s through the public API with HOST (pinned) inputs: H2D copies + a D2H read of the loss per step
+  roofline      the dominant kernel (K2 GEMM, tensor-bound): algorithmic FLOP / CUDA-event time measured in the timed region
+  cpu_baseline  the torch-operator port of the reference (oracle/torch_port.py) on this box's host cores (rank 0, N=1)
+``--impl reference`` times that CPU port alone (the reference has no GPU-independent build to ship: it is
+pure Python over third-party torch, and /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train utterances/sec (GRUDecoder, B=64, T=500)"
+UNIT = "utterances/s"
+MODEL_KW = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, dropout=0.4, strideLen=4,
+                kernelLen=32, gaussianSmoothWidth=2.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NSD_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--T", type=int, default=500)
+    ap.add_argument("--uni", action="store_true", help="unidirectional GRU (class default) instead of the training default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
+    return ap.parse_args()
+
+
+def config_dict(a, n_gpus, impl_note=""):
+    bi = not a.uni
+    return {"workload": f"GRUDecoder {'bi' if bi else 'uni'}directional 5x1024, 256 feats, 24 days, k32/s4, 41 classes, "
+                        f"dropout 0.4; train step fwd+CTC+bwd+Adam; B={a.batch}/GPU T={a.T} (BASELINE configs[1])",
+            "global_batch": a.batch * n_gpus, "T": a.T, "frames": (a.T - 32) // 4 + 1,
+            "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
+            "l2": "working set (0.54 GB weights + >1 GB activations per step) far exceeds the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU baseline: the torch-operator port of the reference on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_port_run(a, sample_b, steps, warmup):
+    import torch
+    from oracle import torch_port as P
+    from neural_speech_decoder_b200.synthetic import make_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = P.PortGRUDecoder(bidirectional=not a.uni, **MODEL_KW)
+    m.train()
+    opt = P.make_adam(m)
+    batch = make_batch(sample_b, a.T, seed=1)
+    for _ in range(warmup):
+        P.train_step(m, opt, *batch)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        P.train_step(m, opt, *batch)
+        times.append(time.perf_counter() - t0)
+    return sample_b * len(times) / sum(times), cores, sum(times) / len(times)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: a probe step at B=4 sizes the per-step sample so that K+W steps stay near 150 s
+    probe, cores, t_probe = cpu_port_run(a, 4, 1, 1)
+    per_utt = t_probe / 4
+    budget = 150.0 / max(1, a.steps + a.warmup)
+    sb = 64
+    while sb > 4 and sb * per_utt > budget:
+        sb //= 2
+    sb = min(sb, a.batch)
+    val, cores, t_step = cpu_port_run(a, sb, a.steps, a.warmup)
+    sample = f"{sb} utterances/step of the B={a.batch} T={a.T} workload, {a.steps} timed steps, torch {cores} threads"
+    line = {"metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(t_step * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config_dict(a, a.gpus),
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        hot = [v for v in sm if v >= 0.5 * (mx or 1)] or sm
+        return {"sm_mhz": hot[len(hot) // 2] if hot else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def gemm_flops_per_step(a, frames):
+    """Algorithmic FLOPs of the K2 launches of one train step (fwd + dgrad + wgrad of the time-batched W_ih
+    projections and the output layer, plus the time-batched W_hh wgrad); DESIGN.md section 'K2'."""
+    D = 1 if a.uni else 2
+    H, L, C, F0 = 1024, 5, 41, 256 * 32
+    M = a.batch * frames
+    fl = 0
+    for l in range(L):
+        in_l = F0 if l == 0 else H * D
+        fl += 3 * 2 * M * (3 * H) * in_l * D                  # fwd, dgrad, wgrad of W_ih (both directions)
+        fl += 2 * (M - a.batch) * (3 * H) * H * D             # W_hh wgrad (time-batched)
+    fl += 3 * 2 * M * C * H * D                               # output layer fwd, dgrad, wgrad
+    return fl
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours): no CUDA device -- this package has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import neural_speech_decoder_b200 as nsd
+    from neural_speech_decoder_b200 import _lib
+    from neural_speech_decoder_b200.parallel import GradSync
+    from neural_speech_decoder_b200.synthetic import make_batch
+
+    nsd.set_default_precision(a.precision)
+    torch.manual_seed(0)
+    model = nsd.GRUDecoder(device="cuda", bidirectional=not a.uni, **MODEL_KW).to(dev)
+    model.train()
+    gs = GradSync(world) if world > 1 else None
+    opt, sched = nsd.make_optimizer(model, dict(lrStart=0.02, lrEnd=0.02, nBatch=10000, l2_decay=1e-5))
+    if gs is not None:
+        opt.grad_scale = gs.grad_scale
+        for p in model.parameters():                       # identical start on every rank
+            dist.broadcast(p.data, 0)
+    host = [t.pin_memory() for t in make_batch(a.batch, a.T, seed=1 + rank)]
+    devb = [t.to(dev) for t in host]
+    frames = (a.T - 32) // 4 + 1
+
+    def step_resident():
+        return nsd.train_step(model, opt, *devb, scheduler=sched, grad_sync=gs)
+
+    def step_e2e():
+        b = [t.to(dev, non_blocking=True) for t in host]
+        return nsd.train_step(model, opt, *b, scheduler=sched, grad_sync=gs).item()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    barrier()
+    # ---- timed region 1: device-resident inputs
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_begin({"nsd_gemm_bf16", "nsd_gemm_f32"})
+    l0 = _lib.lib().nsd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        loss = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = (_lib.lib().nsd_launch_count() - l0) // a.steps
+    prof = _lib.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- timed region 2: host inputs through the public API
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        lv = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = tt.tolist()
+    if a.breakdown and rank == 0:
+        _lib.profile_begin(None)
+        step_resident()
+        torch.cuda.synchronize()
+        for k, (n, t) in sorted(_lib.profile_end().items(), key=lambda kv: -kv[1][1]):
+            print(f"  {k:28s} calls {n:5d}  {t:9.3f} ms", file=sys.stderr)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = a.batch * world * a.steps / (ms * 1e-3)
+    e2e = a.batch * world * a.steps / (e2e_ms * 1e-3)
+    gemm_calls = sum(n for n, _ in prof.values())
+    gemm_ms = sum(t for _, t in prof.values())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    ach = gemm_flops_per_step(a, frames) * a.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    roofline = {"kernel": "K2 time-batched GEMMs (nsd_gemm_%s)" % a.precision, "bound": "tensor",
+                "achieved": round(ach, 2) if ach else None, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(ach / peak_tf, 4) if ach else None, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained",
+                "launches_per_step": gemm_calls // max(1, a.steps), "share_of_step": round(gemm_ms / ms, 4)}
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.precision, "data": "synthetic", "config": config_dict(a, world), "clocks": clocks,
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "roofline": roofline, "loss": float(lv)}
+    if world == 1 and not a.no_cpu_baseline:
+        val, cores, t_step = cpu_port_run(a, 16, 1, 1)
+        line["cpu_baseline"] = {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"1 timed step (after 1 warm-up) on 16 of the {a.batch} utterances, T={a.T}, torch {cores} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -1,0 +1,46 @@
+"""Adam with the reference's semantics (torch.optim.Adam: L2 folded into the gradient, bias-corrected,
+``eps`` added to sqrt(v_hat); neural_decoder_trainer.py:163-169, 259) as one multi-tensor CUDA launch."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.grad_scale = grad_scale          # data parallel: 1/world_size folds the gradient average in
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps, gs, ms, vs = [], [], [], []
+            step = None
+            for p in group["params"]:
+                if p.grad is None:            # the reference's dead inpLayer* parameters never get one
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32:
+                    raise RuntimeError("FusedAdam (B200) handles CUDA float32 parameters only")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                step = st["step"] if step is None else step
+                if st["step"] != step:        # parameters that joined later: separate launch group
+                    ops.adam_step([p], [p.grad.contiguous()], [st["exp_avg"]], [st["exp_avg_sq"]], group["lr"],
+                                  *group["betas"], group["eps"], group["weight_decay"], st["step"], self.grad_scale)
+                    continue
+                ps.append(p); gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
+                ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
+            if ps:
+                ops.adam_step(ps, gs, ms, vs, group["lr"], *group["betas"], group["eps"], group["weight_decay"], step,
+                              self.grad_scale)
+        return loss

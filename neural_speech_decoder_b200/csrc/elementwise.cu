@@ -1,0 +1,132 @@
+// Element-wise kernels of the path: inter-layer dropout (nn.GRU dropout=p, reference model.py:55).
+#include "common.cuh"
+
+namespace nsd {
+
+// Philox4x32-10 counter-based generator: 4 uniform 32-bit words per (key, counter).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, size_t n, float p, float inv_keep, uint64_t seed) {
+    // one Philox call covers 4 consecutive elements; the mask depends only on (seed, element index)
+    const size_t nq = (n + 3) / 4;
+    const uint32_t thresh = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t e = q * 4 + i;
+            if (e < n) out[e] = from_f32<T>(rr[i] >= thresh ? to_f32<T>(x[e]) * inv_keep : 0.f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-tensor Adam (torch.optim.Adam semantics: g += wd*p; m,v EMA; bias correction; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)).
+// Replaces the foreach Adam step of the reference trainer (neural_decoder_trainer.py:163-169, 259).
+// HBM-bound: 16 B read + 12 B written per element; every thread moves float4s.
+constexpr int ADAM_MAX_TENSORS = 48;
+constexpr int ADAM_CHUNK = 16384;       // elements per CTA
+
+struct AdamTable {
+    float* p[ADAM_MAX_TENSORS]; const float* g[ADAM_MAX_TENSORS]; float* m[ADAM_MAX_TENSORS]; float* v[ADAM_MAX_TENSORS];
+    long long n[ADAM_MAX_TENSORS];
+    int chunk_start[ADAM_MAX_TENSORS + 1];   // first CTA of each tensor
+    int count;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float wd,
+                                         float gs, float step_size, float inv_sqrt_bc2, float eps) {
+    g = fmaf(wd, p, g * gs);
+    m = fmaf(b1, m, (1.0f - b1) * g);
+    v = fmaf(b2, v, (1.0f - b2) * g * g);
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    p -= step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tab, float b1, float b2, float wd, float gs,
+                                                   float step_size, float inv_sqrt_bc2, float eps) {
+    // locate this CTA's tensor (count <= 48: linear scan by one thread is cheap, but all threads can do it)
+    int ti = 0;
+    while (ti + 1 < tab.count && (int)blockIdx.x >= tab.chunk_start[ti + 1]) ++ti;
+    const long long n = tab.n[ti];
+    const long long base = (long long)(blockIdx.x - tab.chunk_start[ti]) * ADAM_CHUNK;
+    const long long end = min(n, base + ADAM_CHUNK);
+    float* __restrict__ P = tab.p[ti]; const float* __restrict__ G = tab.g[ti];
+    float* __restrict__ M = tab.m[ti]; float* __restrict__ V = tab.v[ti];
+    const bool vec = (((uintptr_t)P | (uintptr_t)G | (uintptr_t)M | (uintptr_t)V) & 15) == 0;
+    if (vec) {
+        const long long e4 = base + ((end - base) & ~3LL);
+        for (long long i = base + 4LL * threadIdx.x; i < e4; i += 4LL * blockDim.x) {
+            float4 p = *reinterpret_cast<float4*>(P + i), m = *reinterpret_cast<float4*>(M + i), v = *reinterpret_cast<float4*>(V + i);
+            const float4 g = __ldcs(reinterpret_cast<const float4*>(G + i));
+            adam_one(p.x, g.x, m.x, v.x, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            adam_one(p.y, g.y, m.y, v.y, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            adam_one(p.z, g.z, m.z, v.z, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            adam_one(p.w, g.w, m.w, v.w, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            *reinterpret_cast<float4*>(P + i) = p; *reinterpret_cast<float4*>(M + i) = m; *reinterpret_cast<float4*>(V + i) = v;
+        }
+        for (long long i = e4 + threadIdx.x; i < end; i += blockDim.x) adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+    } else {
+        for (long long i = base + threadIdx.x; i < end; i += blockDim.x) adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+    }
+}
+
+}  // namespace nsd
+
+extern "C" {
+
+int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                  void* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float grad_scale, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(n_tensors >= 0 && step >= 1, "adam_step: bad n_tensors=%d step=%d", n_tensors, step);
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    for (int t0 = 0; t0 < n_tensors; t0 += ADAM_MAX_TENSORS) {
+        AdamTable tab;
+        tab.count = std::min(ADAM_MAX_TENSORS, n_tensors - t0);
+        int chunks = 0;
+        for (int i = 0; i < tab.count; ++i) {
+            NSD_CHECK_ARG(params[t0 + i] && grads[t0 + i] && exp_avg[t0 + i] && exp_avg_sq[t0 + i] && numel[t0 + i] >= 0, "adam_step: null tensor %d", t0 + i);
+            tab.p[i] = (float*)params[t0 + i]; tab.g[i] = (const float*)grads[t0 + i];
+            tab.m[i] = (float*)exp_avg[t0 + i]; tab.v[i] = (float*)exp_avg_sq[t0 + i];
+            tab.n[i] = numel[t0 + i];
+            tab.chunk_start[i] = chunks;
+            chunks += (int)cdivz((size_t)numel[t0 + i], ADAM_CHUNK);
+        }
+        tab.chunk_start[tab.count] = chunks;
+        if (chunks == 0) continue;
+        adam_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(tab, beta1, beta2, weight_decay, grad_scale, step_size, inv_sqrt_bc2, eps);
+        NSD_LAUNCH_CHECK();
+    }
+    return NSD_OK;
+}
+
+int nsd_dropout(const void* x, void* out, int dtype, size_t n, float p, uint64_t seed, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p=%f not in [0,1)", (double)p);
+    if (n == 0) return NSD_OK;
+    const int blocks = (int)std::min<size_t>(cdivz(cdivz(n, 4), 256), (size_t)sm_count() * 16);
+    const float inv_keep = 1.0f / (1.0f - p);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NSD_F32) dropout_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, (float*)out, n, p, inv_keep, seed);
+    else if (dtype == NSD_BF16) dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n, p, inv_keep, seed);
+    else { set_error("dropout: bad dtype"); return NSD_ERR_INVALID; }
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+}  // extern "C"

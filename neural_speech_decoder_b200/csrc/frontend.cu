@@ -1,0 +1,382 @@
+// K1: fused Gaussian smoothing + per-day affine + softsign + unfold, and its backward.
+//
+// Replaces F.conv1d(groups=N, padding="same") + index_select + einsum + Softsign + nn.Unfold
+// (reference augmentations.py:91, model.py:84-101).  One pass over X: a CTA owns one utterance
+// and a contiguous range of output frames, walks along time in blocks of TT rows, keeps the
+// last K+TT rows of z in a shared-memory ring and emits every frame whose window is complete.
+// X is read once (plus a (ntaps-1)-row halo per block), ys/z are written once for the backward,
+// patches are written once with 16-byte stores in time-major row order (m = j*B + b).
+#include "common.cuh"
+
+namespace nsd {
+
+constexpr int FE_THREADS = 256;
+constexpr int FE_TT = 32;       // z rows computed per block
+constexpr int FE_TTP = 36;      // padded row length of the transposed ys tile (float4-aligned, conflict-free)
+
+struct FrontendFwdParams {
+    const float* x; const int64_t* day_idx; const float* day_w; const float* day_b; const float* taps;
+    float* ys; float* z; void* patches; int* err_flag;
+    int ntaps, B, T, N, n_days, K, S, Tp, frames_per_seg, ring;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int N = p.N, K = p.K, S = p.S, T = p.T, ntaps = p.ntaps;
+    const int left = (ntaps - 1) / 2;
+    const int xrows = FE_TT + ntaps - 1;
+    const int NP = N + 1;
+    float* taps_s = smem;                                   // [64]
+    float* xs = smem + 64;                                  // [xrows][N]
+    float* ysT = xs + (size_t)xrows * N;                    // [N][FE_TTP]
+    float* zring = ysT + (size_t)N * FE_TTP;                // [ring][N+1]
+
+    const int b = blockIdx.x;
+    const int j0 = blockIdx.y * p.frames_per_seg;
+    const int j1 = min(p.Tp, j0 + p.frames_per_seg);
+    if (j0 >= j1) return;
+    const int tid = threadIdx.x;
+
+    long long day = p.day_idx[b];
+    if (day < 0 || day >= p.n_days) {          // reference: index_select raises IndexError (model.py:89)
+        if (tid == 0 && p.err_flag) *p.err_flag = 1;
+        day = 0;
+    }
+    const float* W = p.day_w + (size_t)day * N * N;
+    const float* bias = p.day_b + (size_t)day * N;
+    if (tid < ntaps) taps_s[tid] = p.taps[tid];
+
+    const int R0 = j0 * S, R1 = (j1 - 1) * S + K;   // z rows this CTA needs
+    const float* xb = p.x + (size_t)b * T * N;
+    float* ysb = p.ys + (size_t)b * T * N;
+    float* zb = p.z + (size_t)b * T * N;
+    int jnext = j0;
+
+    for (int rb = R0; rb < R1; rb += FE_TT) {
+        const int rows = min(FE_TT, R1 - rb);
+        // 1. stage x rows [rb-left, rb-left+xrows) (zero outside [0,T))
+        if ((N & 3) == 0) {
+            const int n4 = N >> 2;
+            for (int i = tid; i < xrows * n4; i += FE_THREADS) {
+                int rr = i / n4, c4 = i - rr * n4;
+                int t = rb - left + rr;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t >= 0 && t < T && rr < rows + ntaps - 1) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)t * N) + c4);
+                reinterpret_cast<float4*>(xs + (size_t)rr * N)[c4] = v;
+            }
+        } else {
+            for (int i = tid; i < xrows * N; i += FE_THREADS) {
+                int rr = i / N, c = i - rr * N;
+                int t = rb - left + rr;
+                xs[i] = (t >= 0 && t < T) ? __ldg(xb + (size_t)t * N + c) : 0.f;
+            }
+        }
+        __syncthreads();
+        // 2. depthwise FIR: ys[t][c] = sum_k taps[k] * x[t-left+k][c]
+        for (int c = tid; c < N; c += FE_THREADS) {
+            for (int tt = 0; tt < FE_TT; ++tt) {
+                float acc = 0.f;
+                if (tt < rows) {
+                    for (int k = 0; k < ntaps; ++k) acc = fmaf(taps_s[k], xs[(size_t)(tt + k) * N + c], acc);
+                    ysb[(size_t)(rb + tt) * N + c] = acc;
+                }
+                ysT[(size_t)c * FE_TTP + tt] = acc;
+            }
+        }
+        __syncthreads();
+        // 3. day affine + softsign: pre[t][k] = sum_d ys[t][d] W[d][k] + bias[k]
+        for (int kc = tid; kc < N; kc += FE_THREADS) {
+            float acc[FE_TT];
+            const float bv = __ldg(bias + kc);
+#pragma unroll
+            for (int i = 0; i < FE_TT; ++i) acc[i] = bv;
+            for (int d = 0; d < N; ++d) {
+                const float w = __ldg(W + (size_t)d * N + kc);
+                const float4* yr = reinterpret_cast<const float4*>(ysT + (size_t)d * FE_TTP);
+#pragma unroll
+                for (int q = 0; q < FE_TT / 4; ++q) {
+                    float4 y = yr[q];
+                    acc[4 * q + 0] = fmaf(y.x, w, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(y.y, w, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(y.z, w, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(y.w, w, acc[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < FE_TT; ++i) {
+                if (i < rows) {
+                    float v = acc[i] / (1.0f + fabsf(acc[i]));
+                    zring[(size_t)((rb + i) % p.ring) * NP + kc] = v;
+                    zb[(size_t)(rb + i) * N + kc] = v;
+                }
+            }
+        }
+        __syncthreads();
+        // 4. emit every frame whose window [j*S, j*S+K) is now complete
+        const int rend = rb + rows;
+        int jend = jnext;
+        while (jend < j1 && jend * S + K <= rend) ++jend;
+        const int F = N * K;
+        if ((K & 3) == 0) {
+            const int f4n = F >> 2;
+            for (int j = jnext; j < jend; ++j) {
+                OutT* orow = reinterpret_cast<OutT*>(p.patches) + ((size_t)j * p.B + b) * F;
+                for (int q = tid; q < f4n; q += FE_THREADS) {
+                    int f = q << 2;
+                    int c = f / K, kk = f - c * K;
+                    int r = j * S + kk;
+                    float v0 = zring[(size_t)((r + 0) % p.ring) * NP + c];
+                    float v1 = zring[(size_t)((r + 1) % p.ring) * NP + c];
+                    float v2 = zring[(size_t)((r + 2) % p.ring) * NP + c];
+                    float v3 = zring[(size_t)((r + 3) % p.ring) * NP + c];
+                    if constexpr (sizeof(OutT) == 4) {
+                        reinterpret_cast<float4*>(orow)[q] = make_float4(v0, v1, v2, v3);
+                    } else {
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+                        uint2 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&lo);
+                        u.y = *reinterpret_cast<uint32_t*>(&hi);
+                        reinterpret_cast<uint2*>(orow)[q] = u;
+                    }
+                }
+            }
+        } else {
+            for (int j = jnext; j < jend; ++j) {
+                OutT* orow = reinterpret_cast<OutT*>(p.patches) + ((size_t)j * p.B + b) * F;
+                for (int f = tid; f < F; f += FE_THREADS) {
+                    int c = f / K, kk = f - c * K;
+                    orow[f] = from_f32<OutT>(zring[(size_t)((j * S + kk) % p.ring) * NP + c]);
+                }
+            }
+        }
+        jnext = jend;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: col2im (deterministic, thread-owned ring cells) -> softsign' -> ys^T dpre per utterance
+// ---------------------------------------------------------------------------------------------
+constexpr int FB_THREADS = 256;
+constexpr int FB_CN = 128;     // channels (columns of dW) per CTA
+constexpr int FB_G = 4;        // frames staged per group
+constexpr int FB_RCH = 16;     // rows finalised per chunk
+
+struct FrontendBwdParams {
+    const void* dp; const float* ys; const float* z; float* partial_w; float* partial_b;
+    int B, T, N, K, S, Tp, KP, ring;
+};
+
+template <typename InT>
+__global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_kernel(FrontendBwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int N = p.N, K = p.K, S = p.S, T = p.T, KP = p.KP, B = p.B;
+    const int b = blockIdx.x;
+    const int c0 = blockIdx.y * FB_CN;
+    const int cn = min(FB_CN, N - c0);
+    const int tid = threadIdx.x;
+    const int kl = tid & (FB_CN - 1);   // column within the chunk
+    const int dh = tid >> 7;            // which 128-row half of d this thread accumulates
+    const int RP = FB_CN + 1;
+    float* ring = smem;                                     // [ring][FB_CN+1]
+    float* ys_s = ring + (size_t)p.ring * RP;               // [FB_RCH][N]
+    float* stage = ys_s + (size_t)FB_RCH * N;               // [FB_G][FB_CN][KP]
+
+    for (int i = tid; i < p.ring * RP; i += FB_THREADS) ring[i] = 0.f;
+
+    const int nd_chunks = (N + 255) / 256;                  // d handled in chunks of 256 (2 halves x 128)
+    const float* ysb = p.ys + (size_t)b * T * N;
+    const float* zb = p.z + (size_t)b * T * N;
+    const InT* dp = reinterpret_cast<const InT*>(p.dp);
+    const int F = N * K;
+
+    for (int dc = 0; dc < nd_chunks; ++dc) {
+        const int d0 = dc * 256 + dh * 128;
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+        float bacc = 0.f;
+        __syncthreads();
+
+        auto finalize = [&](int r_begin, int r_end) {
+            for (int rc = r_begin; rc < r_end; rc += FB_RCH) {
+                const int nr = min(FB_RCH, r_end - rc);
+                for (int i = tid; i < nr * N; i += FB_THREADS) ys_s[i] = __ldg(ysb + (size_t)rc * N + i);
+                __syncthreads();
+                if (kl < cn) {
+                    for (int rr = 0; rr < nr; ++rr) {
+                        const int t = rc + rr;
+                        float dz = ring[(size_t)(t % p.ring) * RP + kl];
+                        float zz = __ldg(zb + (size_t)t * N + c0 + kl);
+                        float s = 1.0f - fabsf(zz);
+                        float dpre = dz * s * s;
+                        if (dh == 0) bacc += dpre;
+                        const float* yr = ys_s + (size_t)rr * N + d0;
+                        if (d0 + 128 <= N) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {
+                                float4 y = reinterpret_cast<const float4*>(yr)[q];
+                                acc[4 * q + 0] = fmaf(y.x, dpre, acc[4 * q + 0]);
+                                acc[4 * q + 1] = fmaf(y.y, dpre, acc[4 * q + 1]);
+                                acc[4 * q + 2] = fmaf(y.z, dpre, acc[4 * q + 2]);
+                                acc[4 * q + 3] = fmaf(y.w, dpre, acc[4 * q + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 128; ++i)
+                                if (d0 + i < N) acc[i] = fmaf(yr[i], dpre, acc[i]);
+                        }
+                    }
+                }
+                __syncthreads();
+                // consumed rows go back to zero for their next use
+                for (int i = tid; i < nr * FB_CN; i += FB_THREADS)
+                    ring[(size_t)((rc + i / FB_CN) % p.ring) * RP + (i % FB_CN)] = 0.f;
+                __syncthreads();
+            }
+        };
+
+        for (int jg = 0; jg < p.Tp; jg += FB_G) {
+            const int ng = min(FB_G, p.Tp - jg);
+            // a. stage this CTA's slice of ng gradient rows (coalesced)
+            for (int g = 0; g < ng; ++g) {
+                const InT* row = dp + ((size_t)(jg + g) * B + b) * F + (size_t)c0 * K;
+                float* st = stage + (size_t)g * FB_CN * KP;
+                for (int i = tid; i < cn * K; i += FB_THREADS) {
+                    int cl = i / K, kk = i - cl * K;
+                    st[cl * KP + kk] = to_f32<InT>(row[i]);
+                }
+            }
+            __syncthreads();
+            // b. scatter-add into the ring; a thread owns (cl, phase) so no two threads touch one cell
+            for (int pi = tid; pi < cn * S; pi += FB_THREADS) {
+                const int cl = pi / S, ph = pi - cl * S;
+                for (int g = 0; g < ng; ++g) {
+                    const float* st = stage + (size_t)g * FB_CN * KP + cl * KP;
+                    const int rbase = (jg + g) * S;
+                    for (int kk = ph; kk < K; kk += S) ring[(size_t)((rbase + kk) % p.ring) * RP + cl] += st[kk];
+                }
+            }
+            __syncthreads();
+            // c. rows below the next group's first row are complete
+            const bool last = (jg + ng >= p.Tp);
+            finalize(jg * S, last ? (p.Tp - 1) * S + K : (jg + ng) * S);
+        }
+        // write this utterance's partial dW rows / db
+        if (kl < cn) {
+            float* pw = p.partial_w + (size_t)b * N * N;
+#pragma unroll
+            for (int i = 0; i < 128; ++i)
+                if (d0 + i < N) pw[(size_t)(d0 + i) * N + c0 + kl] = acc[i];
+            if (dh == 0 && dc == 0) p.partial_b[(size_t)b * N + c0 + kl] = bacc;
+        }
+    }
+}
+
+// out[d][e] = sum_{b : day[b]==d} partial[b][e], utterances visited in index order (deterministic).
+__global__ void day_segment_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
+                                          const int64_t* __restrict__ day_idx, int B, int NN, int N, int n_days,
+                                          float* __restrict__ dw, float* __restrict__ db) {
+    const int d = blockIdx.y;
+    const int per = NN + N;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) {
+            if (day_idx[b] == d) s += (e < NN) ? pw[(size_t)b * NN + e] : pb[(size_t)b * N + (e - NN)];
+        }
+        if (e < NN) dw[(size_t)d * NN + e] = s;
+        else db[(size_t)d * N + (e - NN)] = s;
+    }
+}
+
+static int pick_segments(int B, int Tp, int sms, int S, int K) {
+    // minimise waves/segments: time ~ ceil(B*nseg/sms)/nseg, halo recompute grows with nseg
+    int best = 1;
+    double best_cost = 1e30;
+    for (int n = 1; n <= 16 && n <= Tp; ++n) {
+        int fps = (Tp + n - 1) / n;
+        double waves = (double)((B * n + sms - 1) / sms);
+        double cost = waves * (fps * S + K - S);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = n; }
+    }
+    return best;
+}
+
+}  // namespace nsd
+
+extern "C" {
+
+int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w, const float* day_b,
+                     const float* taps, int ntaps, int B, int T, int N, int n_days, int kernel_len,
+                     int stride_len, float* ys, float* z, void* patches, int patches_dtype, int* err_flag,
+                     void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(B > 0 && T > 0 && N > 0 && n_days > 0, "frontend_fwd: bad sizes B=%d T=%d N=%d", B, T, N);
+    NSD_CHECK_ARG(ntaps >= 1 && ntaps <= 64, "frontend_fwd: ntaps=%d not in [1,64]", ntaps);
+    NSD_CHECK_ARG(kernel_len >= 1 && stride_len >= 1, "frontend_fwd: bad kernel/stride");
+    NSD_CHECK_ARG(T >= kernel_len, "frontend_fwd: T=%d shorter than kernelLen=%d", T, kernel_len);
+    NSD_CHECK_ARG(patches_dtype == NSD_F32 || patches_dtype == NSD_BF16, "frontend_fwd: bad dtype");
+    FrontendFwdParams p;
+    p.x = x; p.day_idx = day_idx; p.day_w = day_w; p.day_b = day_b; p.taps = taps;
+    p.ys = ys; p.z = z; p.patches = patches; p.err_flag = err_flag;
+    p.ntaps = ntaps; p.B = B; p.T = T; p.N = N; p.n_days = n_days; p.K = kernel_len; p.S = stride_len;
+    p.Tp = (T - kernel_len) / stride_len + 1;
+    const int nseg = pick_segments(B, p.Tp, sm_count(), stride_len, kernel_len);
+    p.frames_per_seg = cdiv(p.Tp, nseg);
+    p.ring = kernel_len + FE_TT;
+    size_t smem = sizeof(float) * (64 + (size_t)(FE_TT + ntaps - 1) * N + (size_t)N * FE_TTP + (size_t)p.ring * (N + 1));
+    NSD_CHECK_ARG(smem <= 227 * 1024, "frontend_fwd: N=%d kernelLen=%d need %zu B shared memory", N, kernel_len, smem);
+    dim3 grid(B, cdiv(p.Tp, p.frames_per_seg));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (patches_dtype == NSD_F32) {
+        NSD_CUDA(cudaFuncSetAttribute(frontend_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_fwd_kernel<float><<<grid, FE_THREADS, smem, s>>>(p);
+    } else {
+        NSD_CUDA(cudaFuncSetAttribute(frontend_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_fwd_kernel<__nv_bfloat16><<<grid, FE_THREADS, smem, s>>>(p);
+    }
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+size_t nsd_frontend_bwd_workspace(int B, int N) { return sizeof(float) * (size_t)B * N * (N + 1); }
+
+int nsd_frontend_bwd(const void* dpatches, int dpatches_dtype, const float* ys, const float* z,
+                     const int64_t* day_idx, int B, int T, int N, int n_days, int kernel_len, int stride_len,
+                     float* d_day_w, float* d_day_b, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(B > 0 && T >= kernel_len && N > 0 && n_days > 0, "frontend_bwd: bad sizes");
+    NSD_CHECK_ARG(dpatches_dtype == NSD_F32 || dpatches_dtype == NSD_BF16, "frontend_bwd: bad dtype");
+    if (workspace_bytes < nsd_frontend_bwd_workspace(B, N)) {
+        set_error("frontend_bwd: workspace %zu < %zu", workspace_bytes, nsd_frontend_bwd_workspace(B, N));
+        return NSD_ERR_WORKSPACE;
+    }
+    FrontendBwdParams p;
+    p.dp = dpatches; p.ys = ys; p.z = z;
+    p.partial_w = reinterpret_cast<float*>(workspace);
+    p.partial_b = p.partial_w + (size_t)B * N * N;
+    p.B = B; p.T = T; p.N = N; p.K = kernel_len; p.S = stride_len;
+    p.Tp = (T - kernel_len) / stride_len + 1;
+    p.KP = ((kernel_len + 3) / 4) * 4 + 4;
+    p.ring = (FB_G - 1) * stride_len + kernel_len;
+    size_t smem = sizeof(float) * ((size_t)p.ring * (FB_CN + 1) + (size_t)FB_RCH * N + (size_t)FB_G * FB_CN * p.KP);
+    NSD_CHECK_ARG(smem <= 227 * 1024, "frontend_bwd: N=%d kernelLen=%d need %zu B shared memory", N, kernel_len, smem);
+    dim3 grid(B, cdiv(N, FB_CN));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dpatches_dtype == NSD_F32) {
+        NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_bwd_kernel<float><<<grid, FB_THREADS, smem, s>>>(p);
+    } else {
+        NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_bwd_kernel<__nv_bfloat16><<<grid, FB_THREADS, smem, s>>>(p);
+    }
+    NSD_LAUNCH_CHECK();
+    const int per = N * N + N;
+    dim3 g2(min(cdiv(per, 256), 64), n_days);
+    day_segment_reduce_kernel<<<g2, 256, 0, s>>>(p.partial_w, p.partial_b, day_idx, B, N * N, N, n_days, d_day_w, d_day_b);
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+}  // extern "C"

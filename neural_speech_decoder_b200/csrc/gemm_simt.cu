@@ -1,0 +1,225 @@
+// fp32 CUDA-core GEMM (the fp32 parity path of K2) plus small helpers (column sums, casts, [T,B,C]<->[B,T,C]).
+//
+// C[M,N] = op(A)[M,K] * op(B)[K,N] (+bias) (+beta*C), row-major, fp32 FFMA with a 128x128x16 CTA tile,
+// 8x8 register tile per thread and a double-buffered shared-memory pipeline.  It backs the time-batched
+// W_ih projections, their dgrad/wgrad and the output layer in fp32 mode (nn.GRU / nn.Linear in the
+// reference, model.py:50-57, 76-81, 119, 122); the tensor-core path lives in gemm_tc.cu.
+#include "common.cuh"
+
+namespace nsd {
+
+constexpr int GS_BM = 128, GS_BN = 128, GS_BK = 16, GS_THREADS = 256;
+
+// Loads a [rows=GS_BK (k)] x [cols=128 (m or n)] tile into registers.  `kcontig` selects which logical
+// dimension is contiguous in memory.
+//   kcontig:   element (mn, k) at base[mn*ld + k]
+//   !kcontig:  element (mn, k) at base[k*ld + mn]
+template <bool KCONTIG>
+struct TileLoader {
+    const float* base; int ld, mn0, mn_lim, k_lim; bool vec;
+    // each thread owns 8 elements of the 128x16 tile
+    __device__ __forceinline__ void load(int k0, int tid, float (&r)[8]) const {
+        if constexpr (KCONTIG) {
+            // 128 rows(mn) x 16 k: thread -> row = tid/2, k-half = (tid&1)*8
+            const int mn = mn0 + (tid >> 1), kk = k0 + ((tid & 1) << 3);
+            if (mn < mn_lim && vec && kk + 8 <= k_lim) {
+                const float4* p = reinterpret_cast<const float4*>(base + (size_t)mn * ld + kk);
+                float4 a = __ldg(p), b = __ldg(p + 1);
+                r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = (mn < mn_lim && kk + i < k_lim) ? __ldg(base + (size_t)mn * ld + kk + i) : 0.f;
+            }
+        } else {
+            // 16 k-rows x 128 mn: thread -> k = tid/16, mn group = (tid&15)*8
+            const int kk = k0 + (tid >> 4), mn = mn0 + ((tid & 15) << 3);
+            if (kk < k_lim && vec && mn + 8 <= mn_lim) {
+                const float4* p = reinterpret_cast<const float4*>(base + (size_t)kk * ld + mn);
+                float4 a = __ldg(p), b = __ldg(p + 1);
+                r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = (kk < k_lim && mn + i < mn_lim) ? __ldg(base + (size_t)kk * ld + mn + i) : 0.f;
+            }
+        }
+    }
+    // smem tile layout: s[k][mn] with row length 128 (+4 pad when written transposed)
+    __device__ __forceinline__ void store(float* s, int tid, const float (&r)[8]) const {
+        if constexpr (KCONTIG) {
+            const int mn = tid >> 1, kk = (tid & 1) << 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[(kk + i) * (GS_BM + 4) + mn] = r[i];
+        } else {
+            const int kk = tid >> 4, mn = (tid & 15) << 3;
+            float4* d = reinterpret_cast<float4*>(s + kk * (GS_BM + 4) + mn);
+            d[0] = make_float4(r[0], r[1], r[2], r[3]);
+            d[1] = make_float4(r[4], r[5], r[6], r[7]);
+        }
+    }
+};
+
+template <bool A_KCONTIG, bool B_KCONTIG>
+__global__ void __launch_bounds__(GS_THREADS, 2)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+             float* __restrict__ C, int ldc, const float* __restrict__ bias, float beta) {
+    __shared__ __align__(16) float As[2][GS_BK * (GS_BM + 4)];
+    __shared__ __align__(16) float Bs[2][GS_BK * (GS_BN + 4)];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GS_BM, n0 = blockIdx.x * GS_BN;
+    TileLoader<A_KCONTIG> la{A, lda, m0, M, K, false};
+    TileLoader<B_KCONTIG> lb{B, ldb, n0, N, K, false};
+    la.vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    lb.vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+
+    const int ty = tid >> 4, tx = tid & 15;     // 16x16 threads, each 8x8 outputs (split 4+4 for conflict-free LDS.128)
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float ra[8], rb[8];
+    la.load(0, tid, ra);
+    lb.load(0, tid, rb);
+    la.store(As[0], tid, ra);
+    lb.store(Bs[0], tid, rb);
+    __syncthreads();
+    const int nk = (K + GS_BK - 1) / GS_BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) {
+            la.load((kt + 1) * GS_BK, tid, ra);
+            lb.load((kt + 1) * GS_BK, tid, rb);
+        }
+        const float* as = As[cur];
+        const float* bs = Bs[cur];
+#pragma unroll
+        for (int k = 0; k < GS_BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(as + k * (GS_BM + 4) + ty * 4);
+            float4 a1 = *reinterpret_cast<const float4*>(as + k * (GS_BM + 4) + 64 + ty * 4);
+            float4 b0 = *reinterpret_cast<const float4*>(bs + k * (GS_BN + 4) + tx * 4);
+            float4 b1 = *reinterpret_cast<const float4*>(bs + k * (GS_BN + 4) + 64 + tx * 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            la.store(As[cur ^ 1], tid, ra);
+            lb.store(Bs[cur ^ 1], tid, rb);
+        }
+        __syncthreads();
+    }
+    // epilogue: rows ty*4+{0..3} and 64+ty*4+{0..3}; cols tx*4+{0..3} and 64+tx*4+{0..3}
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += __ldg(bias + n);
+            float* c = C + (size_t)m * ldc + n;
+            if (beta != 0.f) v = fmaf(beta, *c, v);
+            *c = v;
+        }
+    }
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ a, int M, int N, int lda, float* __restrict__ out) {
+    // block = 32 columns x 8 row-lanes; rows strided, tree-reduced in shared memory (fixed order -> deterministic)
+    __shared__ float red[8][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (n < N)
+        for (int m = threadIdx.y; m < M; m += 8) s += to_f32<T>(a[(size_t)m * lda + n]);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        out[n] = t;
+    }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = from_f32<D>(to_f32<S>(src[i]));
+}
+
+__global__ void swap01_kernel(const float* __restrict__ in, float* __restrict__ out, int D0, int D1, int C) {
+    // out[d1][d0][c] = in[d0][d1][c]
+    const size_t total = (size_t)D0 * D1 * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        size_t r = i / C;
+        int d0 = (int)(r % D0), d1 = (int)(r / D0);
+        out[i] = in[((size_t)d0 * D1 + d1) * C + c];
+    }
+}
+
+}  // namespace nsd
+
+extern "C" {
+
+int nsd_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                 float* C, int ldc, const float* bias, float beta, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm_f32: negative size");
+    if (M == 0 || N == 0) return NSD_OK;
+    NSD_CHECK_ARG(A && B && C, "gemm_f32: null pointer");
+    dim3 grid(cdiv(N, GS_BN), cdiv(M, GS_BM));
+    cudaStream_t s = (cudaStream_t)stream;
+    // op(A) is k-contiguous when A is stored [M,K]; op(B) is k-contiguous when B is stored [N,K]
+    if (!transa && transb) sgemm_kernel<true, true><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    else if (!transa && !transb) sgemm_kernel<true, false><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    else if (transa && !transb) sgemm_kernel<false, false><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    else sgemm_kernel<false, true><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(M >= 0 && N > 0, "colsum: bad size");
+    dim3 grid(cdiv(N, 32)), block(32, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a_dtype == NSD_F32) colsum_kernel<float><<<grid, block, 0, s>>>((const float*)a, M, N, lda, out);
+    else if (a_dtype == NSD_BF16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)a, M, N, lda, out);
+    else { set_error("colsum: bad dtype"); return NSD_ERR_INVALID; }
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+int nsd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream) {
+    using namespace nsd;
+    if (n == 0) return NSD_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int blocks = (int)std::min<size_t>(cdivz(n, 256), (size_t)sm_count() * 16);
+    if (src_dtype == NSD_F32 && dst_dtype == NSD_BF16) cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    else if (src_dtype == NSD_BF16 && dst_dtype == NSD_F32) cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    else if (src_dtype == NSD_F32 && dst_dtype == NSD_F32) cast_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, n);
+    else { set_error("cast: unsupported dtype pair %d->%d", src_dtype, dst_dtype); return NSD_ERR_INVALID; }
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+int nsd_swap01_f32(const float* in, float* out, int D0, int D1, int C, void* stream) {
+    using namespace nsd;
+    const size_t total = (size_t)D0 * D1 * C;
+    if (total == 0) return NSD_OK;
+    int blocks = (int)std::min<size_t>(cdivz(total, 256), (size_t)sm_count() * 8);
+    swap01_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, D0, D1, C);
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+}  // extern "C"

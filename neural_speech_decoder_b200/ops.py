@@ -1,0 +1,157 @@
+"""Tensor-level wrappers of the C-ABI entry points (no autograd here).
+
+Each function allocates its outputs with torch (caching allocator, current
+stream) and passes raw device pointers to ``libnsd_b200.so``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream, dtype_code, require_cuda
+
+
+def n_frames(T: int, kernel_len: int, stride_len: int) -> int:
+    if T < kernel_len:
+        # nn.Unfold raises RuntimeError for an input shorter than the kernel (model.py:96-101)
+        raise RuntimeError(f"sequence length {T} is shorter than kernelLen {kernel_len}")
+    return (T - kernel_len) // stride_len + 1
+
+
+# ------------------------------------------------------------------ K1
+def frontend_fwd(x, day_idx, day_w, day_b, taps, kernel_len, stride_len, out_dtype, err_flag=None):
+    """-> (patches [T'*B, N*K] time-major, ys [B,T,N], z [B,T,N])."""
+    require_cuda(x, "neuralInput")
+    B, T, N = x.shape
+    Tp = n_frames(T, kernel_len, stride_len)
+    x = x.contiguous().float()
+    day_idx = day_idx.to(device=x.device, dtype=torch.int64).contiguous()
+    ys = torch.empty_like(x)
+    z = torch.empty_like(x)
+    patches = torch.empty((Tp * B, N * kernel_len), device=x.device, dtype=out_dtype)
+    call("nsd_frontend_fwd", ptr(x), ptr(day_idx), ptr(day_w), ptr(day_b), ptr(taps), taps.numel(), B, T, N,
+         day_w.shape[0], kernel_len, stride_len, ptr(ys), ptr(z), ptr(patches), dtype_code(out_dtype),
+         ptr(err_flag), stream())
+    return patches, ys, z
+
+
+def frontend_bwd(dpatches, ys, z, day_idx, n_days, kernel_len, stride_len):
+    B, T, N = ys.shape
+    flat = torch.empty(n_days * N * N + n_days * N, device=ys.device, dtype=torch.float32)   # one gradient bucket
+    d_w = flat[:n_days * N * N].view(n_days, N, N)
+    d_b = flat[n_days * N * N:].view(n_days, 1, N)
+    nbytes = _lib.lib().nsd_frontend_bwd_workspace(B, N)
+    ws = torch.empty(nbytes, device=ys.device, dtype=torch.uint8)
+    call("nsd_frontend_bwd", ptr(dpatches), dtype_code(dpatches.dtype), ptr(ys), ptr(z), ptr(day_idx), B, T, N,
+         n_days, kernel_len, stride_len, ptr(d_w), ptr(d_b), ptr(ws), nbytes, stream())
+    return d_w, d_b
+
+
+# ------------------------------------------------------------------ K2
+def gemm(transa: bool, transb: bool, M: int, N: int, K: int, A, lda: int, B, ldb: int, C, ldc: int,
+         bias: Optional[torch.Tensor] = None, beta: float = 0.0, a_off: int = 0, b_off: int = 0, c_off: int = 0):
+    """C[M,N] = op(A) op(B) (+bias) (+beta*C); element offsets select sub-matrices of the buffers."""
+    esz_a, esz_b, esz_c = A.element_size(), B.element_size(), C.element_size()
+    pa, pb, pc = A.data_ptr() + a_off * esz_a, B.data_ptr() + b_off * esz_b, C.data_ptr() + c_off * esz_c
+    if A.dtype == torch.float32:
+        call("nsd_gemm_f32", int(transa), int(transb), M, N, K, pa, lda, pb, ldb, pc, ldc, ptr(bias), beta, stream())
+    else:
+        call("nsd_gemm_bf16", int(transa), int(transb), M, N, K, pa, lda, pb, ldb, pc, ldc, dtype_code(C.dtype),
+             ptr(bias), beta, stream())
+
+
+def colsum(a, M: int, N: int, lda: int, out, a_off: int = 0, out_off: int = 0):
+    call("nsd_colsum", a.data_ptr() + a_off * a.element_size(), dtype_code(a.dtype), M, N, lda,
+         out.data_ptr() + out_off * 4, stream())
+
+
+def cast(src, dst_dtype):
+    dst = torch.empty(src.shape, device=src.device, dtype=dst_dtype)
+    call("nsd_cast", ptr(src), dtype_code(src.dtype), ptr(dst), dtype_code(dst_dtype), src.numel(), stream())
+    return dst
+
+
+def swap01(x):
+    """[D0,D1,C] -> contiguous [D1,D0,C]."""
+    D0, D1, Cc = x.shape
+    out = torch.empty((D1, D0, Cc), device=x.device, dtype=torch.float32)
+    call("nsd_swap01_f32", ptr(x), ptr(out), D0, D1, Cc, stream())
+    return out
+
+
+# ------------------------------------------------------------------ K3
+def gru_fwd_f32(gi, ldgi, gi_off, w_hh, b_hh, Tp, B, H, reverse, hseq, ldh, h_off, saves):
+    r, z, n, hn = saves if saves is not None else (None, None, None, None)
+    call("nsd_gru_fwd_f32", gi.data_ptr() + gi_off * 4, ldgi, ptr(w_hh), ptr(b_hh), Tp, B, H, int(reverse),
+         hseq.data_ptr() + h_off * 4, ldh, ptr(r), ptr(z), ptr(n), ptr(hn), stream())
+
+
+def gru_bwd_f32(dhseq, lddh, dh_off, hseq, ldh, h_off, saves, w_hh, Tp, B, H, reverse, dgi, ldgi, dgi_off, dghn):
+    r, z, n, hn = saves
+    nbytes = _lib.lib().nsd_gru_bwd_workspace(B, H)
+    ws = torch.empty(nbytes, device=dgi.device, dtype=torch.uint8)
+    call("nsd_gru_bwd_f32", dhseq.data_ptr() + dh_off * 4, lddh, hseq.data_ptr() + h_off * 4, ldh, ptr(r), ptr(z),
+         ptr(n), ptr(hn), ptr(w_hh), Tp, B, H, int(reverse), dgi.data_ptr() + dgi_off * 4, ldgi, ptr(dghn), ptr(ws),
+         nbytes, stream())
+
+
+def dropout(x, p: float, seed: int):
+    out = torch.empty_like(x)
+    call("nsd_dropout", ptr(x), ptr(out), dtype_code(x.dtype), x.numel(), float(p), int(seed), stream())
+    return out
+
+
+# ------------------------------------------------------------------ K4 / K5
+def ctc_loss_raw(act, st, sb, sc, is_logits, targets, in_lens, tgt_lens, T, B, Cc, blank, reduction_mean, want_grad):
+    """Returns (loss scalar tensor, nll [B], grad or None).  grad has the memory layout (strides) of ``act``."""
+    dev = act.device
+    max_tgt = targets.shape[1]
+    nll = torch.empty(B, device=dev, dtype=torch.float32)
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    grad = torch.empty_like(act) if want_grad else None
+    nbytes = _lib.lib().nsd_ctc_workspace(T, B, Cc, max_tgt)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    call("nsd_ctc_loss", ptr(act), st, sb, sc, int(is_logits), ptr(targets), targets.stride(0), ptr(in_lens),
+         ptr(tgt_lens), T, B, Cc, blank, max_tgt, int(reduction_mean), ptr(nll), ptr(loss), ptr(grad), ptr(ws),
+         nbytes, stream())
+    return loss, nll, grad
+
+
+def log_softmax(x):
+    """Row-wise log-softmax over the last dim of a contiguous f32 tensor."""
+    out = torch.empty_like(x)
+    Cc = x.shape[-1]
+    call("nsd_log_softmax_f32", ptr(x), ptr(out), x.numel() // Cc, Cc, stream())
+    return out
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """torch.optim.Adam (L2-in-gradient, not AdamW) on a list of f32 tensors in as few launches as possible."""
+    import ctypes as C
+    n = len(params)
+    if n == 0:
+        return
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    numel = (C.c_int64 * n)(*[t.numel() for t in params])
+    call("nsd_adam_step", n, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq), numel, float(lr), float(beta1),
+         float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), stream())
+
+
+def greedy_decode_raw(act, st, sb, sc, lens, T, B, Cc, blank) -> Tuple[torch.Tensor, torch.Tensor]:
+    out = torch.empty((B, T), device=act.device, dtype=torch.int64)
+    out_len = torch.empty(B, device=act.device, dtype=torch.int32)
+    call("nsd_greedy_decode", ptr(act), st, sb, sc, ptr(lens), T, B, Cc, blank, ptr(out), ptr(out_len), stream())
+    return out, out_len
+
+
+def edit_distance_raw(dec, dec_len, tgt, tgt_len) -> torch.Tensor:
+    B = dec.shape[0]
+    max_len = max(int(tgt.shape[1]), 1)
+    nbytes = _lib.lib().nsd_edit_distance_workspace(B, max_len)
+    ws = torch.empty(nbytes, device=dec.device, dtype=torch.uint8)
+    dist = torch.empty(B, device=dec.device, dtype=torch.int32)
+    call("nsd_edit_distance", ptr(dec), dec.stride(0), ptr(dec_len), ptr(tgt), tgt.stride(0), ptr(tgt_len), B,
+         ptr(dist), ptr(ws), nbytes, stream())
+    return dist

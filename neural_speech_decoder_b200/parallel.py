@@ -1,0 +1,43 @@
+"""Batch-sharded data parallelism for the training step (new work -- the reference is
+single-GPU).  One process per GPU; every rank holds the full weights and a slice of the batch; the only
+exchange is the gradient all-reduce, issued bucket by bucket from INSIDE the hand-written backward as each
+layer's weight gradients become final, so NCCL (NVLink 5 / NVSwitch) runs under the remaining
+backward-through-time.  The 1/world average is folded into the Adam kernel's ``grad_scale``.
+
+Exactness: the reference loss is mean_b nll_b / len_b over the global batch; with equal per-rank batches,
+per-rank "mean" followed by gradient averaging reproduces it exactly.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, world_size: Optional[int] = None, group=None):
+        self.group = group
+        self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.handles: List = []
+        self.bytes = 0
+
+    @property
+    def grad_scale(self) -> float:
+        return 1.0 / self.world
+
+    def begin(self) -> None:
+        self.handles, self.bytes = [], 0
+
+    def bucket_ready(self, flat: torch.Tensor) -> None:
+        """Called by the backward with a flat buffer whose gradients are final.  The collective is enqueued on
+        NCCL's own stream behind the work already queued on the current stream and overlaps what follows."""
+        if self.world <= 1:
+            return
+        self.bytes += flat.numel() * flat.element_size()
+        self.handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self) -> None:
+        for h in self.handles:
+            h.wait()                      # current stream waits for the collective; no host block on NCCL
+        self.handles = []

@@ -1,0 +1,57 @@
+"""Hot-loop lines of the reference trainer, on the B200 kernels.
+
+Only what sits on the north-star path is mirrored here (neural_decoder_trainer.py):
+  make_optimizer  :163-175   Adam(lr, betas .9/.999, eps=0.1, weight_decay=l2) + LinearLR
+  train_step      :208-218, 242, 251-260   forward -> out_lens -> log-softmax + CTC -> backward -> step
+  eval_batch      :299-333   forward -> CTC loss -> greedy decode -> edit distance
+Data loading, wandb, checkpointing stay the reference's business; its ``trainModel`` runs unchanged with
+``GRUDecoder`` / ``CTCLoss`` swapped in.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import ctc as _ctc
+from .adam import FusedAdam
+
+
+def make_optimizer(model: torch.nn.Module, args: dict):
+    """trainer:163-175 (the non-AdamW branch, which the GRU configs use)."""
+    opt = FusedAdam(model.parameters(), lr=args["lrStart"], betas=(0.9, 0.999), eps=0.1,
+                    weight_decay=args.get("l2_decay", 0.0))
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=args["lrEnd"] / args["lrStart"],
+                                              total_iters=args["nBatch"])
+    return opt, sched
+
+
+def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, grad_sync=None) -> torch.Tensor:
+    """One optimisation step; returns the (device) loss scalar.  ``grad_sync`` is the data-parallel hook
+    (parallel.GradSync): it all-reduces gradients bucket by bucket while the backward is still running."""
+    model.grad_sync = grad_sync
+    pred = model.forward(X, dayIdx)                                         # trainer:208
+    lens = _ctc.out_lens(X_len, model.kernelLen, model.strideLen)           # trainer:209
+    loss = _ctc.ctc_loss_from_logits(pred, y, lens, y_len, blank=0, reduction="mean")   # trainer:210-218, 242
+    optimizer.zero_grad(set_to_none=True)                                   # trainer:251
+    if grad_sync is not None:
+        grad_sync.begin()
+    loss.backward()                                                         # trainer:252
+    if grad_sync is not None:
+        grad_sync.finish()
+    optimizer.step()                                                        # trainer:259
+    if scheduler is not None:
+        scheduler.step()                                                    # trainer:260
+    return loss.detach()
+
+
+@torch.no_grad()
+def eval_batch(model, X, y, X_len, y_len, dayIdx) -> Tuple[torch.Tensor, int, int]:
+    """trainer:299-333 for one batch: (ctc loss, sum edit distance, sum true length)."""
+    logits = model.forward(X, dayIdx)                                       # trainer:299
+    lens = _ctc.out_lens(X_len, model.kernelLen, model.strideLen)           # trainer:300
+    pred = _ctc.log_softmax_tbc(logits)                                     # trainer:301  [T',B,C] view
+    loss = _ctc.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(pred, y, lens, y_len)   # trainer:303-309
+    # decode from the log-probs, as the reference does: log-softmax can create ties the raw logits lack
+    dist, tot = _ctc.phoneme_error_rate(pred, lens, y, y_len)               # trainer:313-333
+    return loss, dist, tot

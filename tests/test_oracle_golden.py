@@ -98,3 +98,20 @@ def test_frontend_errors():
         O.unfold(np.zeros((1, 5, 2)), 8, 2)
     with pytest.raises(IndexError):
         O.day_affine(np.zeros((1, 4, 2)), np.zeros((2, 2, 2)), np.zeros((2, 1, 2)), np.array([2]))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_torch_port_matches_reference_fixture(name):
+    """bench.py's CPU baseline ("port") reproduces the reference's own outputs."""
+    import torch
+    from oracle import torch_port as P
+    g = load_golden(f"{name}_f32")
+    kw = golden_ctor(g)
+    m = P.PortGRUDecoder(**kw)
+    m.load_reference_state(golden_state(g))
+    m.eval()
+    X, y, X_len, y_len, day = (torch.from_numpy(g[k]) for k in ("X", "y", "X_len", "y_len", "dayIdx"))
+    pred = m(X, day)
+    np.testing.assert_allclose(pred.detach().numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+    loss = P.train_step(m, P.make_adam(m), X, y, X_len, y_len, day)
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
