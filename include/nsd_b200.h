@@ -87,6 +87,10 @@ int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const void* A, in
 int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, void* stream);
 /* dtype conversion of a contiguous buffer, f32 <-> bf16. */
 int nsd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
+/* bf16 copies of a row-major [R,C] matrix (f32 or bf16 source): dst [R,C] (ld_dst) and/or its transpose dstT [C,R]
+ * (ld_dstT); either may be NULL.  Produces the K-major operands nsd_gemm_bf16 needs for dgrad / wgrad. */
+int nsd_cast_transpose(const void* src, int src_dtype, int R, int C, int ld_src, void* dst, int ld_dst, void* dstT,
+                       int ld_dstT, void* stream);
 /* out[B,T,C] <- in[T,B,C] (or the inverse with the roles of T and B swapped by the caller). */
 int nsd_swap01_f32(const float* in, float* out, int D0, int D1, int C, void* stream);
 

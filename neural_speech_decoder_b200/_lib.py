@@ -32,6 +32,7 @@ SIGNATURES = {
     "nsd_gemm_bf16": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, f32, vp]),
     "nsd_colsum": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "nsd_cast": (i32, [vp, i32, vp, i32, sz, vp]),
+    "nsd_cast_transpose": (i32, [vp, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
     "nsd_swap01_f32": (i32, [vp, vp, i32, i32, i32, vp]),
     "nsd_gru_fwd_f32": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
     "nsd_gru_bwd_f32": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, sz, vp]),

@@ -155,6 +155,41 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size
     for (; i < n; i += stride) dst[i] = from_f32<D>(to_f32<S>(src[i]));
 }
 
+// dst[r][c] = bf16(src[r][c]) and/or dstT[c][r] = bf16(src[r][c]); 64x64 tiles through shared memory so that both
+// outputs are written in full 128-byte rows.  Makes the K-major operand copies the tcgen05 GEMM needs.
+template <typename S>
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const S* __restrict__ src, int R, int Cn, int ld_src,
+                                                             __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                                             __nv_bfloat16* __restrict__ dstT, int ld_dstT) {
+    __shared__ float tile[64][65];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    for (int i = ty; i < 64; i += 8) {
+        const int r = r0 + i;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = c0 + tx + 32 * h;
+            float v = 0.f;
+            if (r < R && c < Cn) {
+                v = to_f32<S>(src[(size_t)r * ld_src + c]);
+                if (dst) dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(v);
+            }
+            tile[i][tx + 32 * h] = v;
+        }
+    }
+    if (dstT == nullptr) return;
+    __syncthreads();
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i;                 // output row
+        if (c >= Cn) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + tx + 32 * h;   // output column
+            if (r < R) dstT[(size_t)c * ld_dstT + r] = __float2bfloat16_rn(tile[tx + 32 * h][i]);
+        }
+    }
+}
+
 __global__ void swap01_kernel(const float* __restrict__ in, float* __restrict__ out, int D0, int D1, int C) {
     // out[d1][d0][c] = in[d0][d1][c]
     const size_t total = (size_t)D0 * D1 * C;
@@ -208,6 +243,20 @@ int nsd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n,
     else if (src_dtype == NSD_BF16 && dst_dtype == NSD_F32) cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
     else if (src_dtype == NSD_F32 && dst_dtype == NSD_F32) cast_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, n);
     else { set_error("cast: unsupported dtype pair %d->%d", src_dtype, dst_dtype); return NSD_ERR_INVALID; }
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+int nsd_cast_transpose(const void* src, int src_dtype, int R, int Cn, int ld_src, void* dst, int ld_dst, void* dstT,
+                       int ld_dstT, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(R >= 0 && Cn >= 0 && (dst || dstT), "cast_transpose: bad arguments");
+    if (R == 0 || Cn == 0) return NSD_OK;
+    dim3 grid(cdiv(Cn, 64), cdiv(R, 64));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (src_dtype == NSD_F32) cast_transpose_kernel<float><<<grid, 256, 0, s>>>((const float*)src, R, Cn, ld_src, (__nv_bfloat16*)dst, ld_dst, (__nv_bfloat16*)dstT, ld_dstT);
+    else if (src_dtype == NSD_BF16) cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, R, Cn, ld_src, (__nv_bfloat16*)dst, ld_dst, (__nv_bfloat16*)dstT, ld_dstT);
+    else { set_error("cast_transpose: bad dtype"); return NSD_ERR_INVALID; }
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

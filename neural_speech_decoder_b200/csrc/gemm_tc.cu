@@ -1,8 +1,347 @@
-// K2 tensor-core path (tcgen05 + TMA).  Placeholder entry point until the kernel lands: fails loudly.
+// K2 tensor-core path: C[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (+beta*C), bf16 operands, fp32 accumulation.
+//
+// Hand-written sm_100a kernel: TMA (cp.async.bulk.tensor, 128-byte swizzle) stages K-major A / B tiles through a
+// shared-memory ring, ONE elected thread issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16) with the
+// accumulator in tensor memory, and four epilogue warps drain TMEM with tcgen05.ld while the next tile's MMAs
+// run into the second accumulator stage.  Persistent: one CTA per SM walks a grouped tile order.
+// It backs the time-batched W_ih projections of nn.GRU (reference model.py:50-57, 119), their dgrad / wgrad and
+// the time-batched W_hh wgrad.  Both operands must be K-major ("NT"); the callers keep transposed bf16 copies
+// (nsd_cast_transpose) where the natural layout is not.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 
-extern "C" int nsd_gemm_bf16(int, int, int, int, int, const void*, int, const void*, int, void*, int, int,
-                             const float*, float, void*) {
-    nsd::set_error("gemm_bf16: tcgen05 path not built yet");
-    return NSD_ERR_INVALID;
+namespace nsd {
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1, all 128 TMEM lanes)
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 256;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
+constexpr int ACC_STAGES = 2;
+constexpr long long SPIN_CYCLES = 6000000000LL;   // ~3 s: a broken pipeline traps instead of hanging the box
+
+template <int BN> struct Cfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : (ACC_STAGES * BN <= 64 ? 64 : (ACC_STAGES * BN <= 128 ? 128 : (ACC_STAGES * BN <= 256 ? 256 : 512)));
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0xFFFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
+            printf("nsd gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), registers = columns
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100),
+// layout type 2 = SWIZZLE_128B.  Advancing K by 16 bf16 (32 bytes) inside the atom adds 2 to the 16-byte address field.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major; canonical value 1)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TileCoord { int m_blk, n_blk; };
+__device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n) {
+    constexpr int GROUP_M = 16;     // 16 m-blocks x ~9 n-blocks live at once on 148 SMs: both operands stay L2-resident
+    const int per_group = GROUP_M * num_n;
+    const int g = t / per_group;
+    const int first_m = g * GROUP_M;
+    const int gsz = min(GROUP_M, num_m - first_m);
+    const int within = t - g * per_group;
+    return {first_m + within % gsz, within / gsz};
+}
+
+template <typename OutT> __device__ __forceinline__ void store4(OutT* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <int BN, typename OutT>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C, int ldc,
+               const float* __restrict__ bias, float beta, int M, int N, int K) {
+    using cfg = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                             // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + cfg::STAGES;              // [STAGES]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * cfg::STAGES;          // [ACC_STAGES] MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + ACC_STAGES;         // [ACC_STAGES] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int nk = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord(t, num_m, num_n);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
+                    tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, tc.m_blk * BM);
+                    tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tc.n_blk * BN);
+                    if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
+                    if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                         // accumulator complete -> epilogue
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int q = warp & 3;                                       // TMEM lane quadrant this warp may read
+        int acc = 0; uint32_t acc_phase = 0;
+        const bool vec_ok = ((ldc % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const TileCoord tc = tile_coord(t, num_m, num_n);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = tc.m_blk * BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = tc.n_blk * BN + c0;
+                if (col0 >= N) break;                                 // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                if (row < M) {
+                    OutT* crow = C + (size_t)row * ldc + col0;
+                    if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
+                            if (bias) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+                                v0 += bv.x; v1 += bv.y; v2 += bv.z; v3 += bv.w;
+                            }
+                            if (beta != 0.f) {
+                                v0 = fmaf(beta, to_f32<OutT>(crow[i]), v0); v1 = fmaf(beta, to_f32<OutT>(crow[i + 1]), v1);
+                                v2 = fmaf(beta, to_f32<OutT>(crow[i + 2]), v2); v3 = fmaf(beta, to_f32<OutT>(crow[i + 3]), v3);
+                            }
+                            store4<OutT>(crow + i, v0, v1, v2, v3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (col0 + i < N) {
+                                float v = __uint_as_float(r[i]);
+                                if (bias) v += __ldg(bias + col0 + i);
+                                if (beta != 0.f) v = fmaf(beta, to_f32<OutT>(crow[i]), v);
+                                crow[i] = from_f32<OutT>(v);
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle, OOB reads as 0
+static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("gemm_bf16: cuTensorMapEncodeTiled entry point not available"); return NSD_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return NSD_ERR_CUDA; }
+    return NSD_OK;
+}
+
+template <int BN, typename OutT>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta, int M, int N, int K, cudaStream_t s) {
+    using cfg = Cfg<BN>;
+    auto kern = gemm_tc_kernel<BN, OutT>;
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
+        attr_set = true;
+    }
+    const int tiles = cdiv(M, BM) * cdiv(N, BN);
+    const int grid = std::min(tiles, sm_count());
+    kern<<<grid, THREADS, cfg::SMEM, s>>>(ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K);
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+}  // namespace tc
+}  // namespace nsd
+
+extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                             void* C, int ldc, int c_dtype, const float* bias, float beta, void* stream) {
+    using namespace nsd;
+    using namespace nsd::tc;
+    NSD_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
+    if (M == 0 || N == 0) return NSD_OK;
+    NSD_CHECK_ARG(!transa && transb, "gemm_bf16: only the K-major form C = A[M,K] * B[N,K]^T is built (transa=0, transb=1); "
+                                     "make a transposed bf16 copy with nsd_cast_transpose");
+    NSD_CHECK_ARG(A && B && C, "gemm_bf16: null pointer");
+    NSD_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K, "gemm_bf16: lda=%d / ldb=%d must be multiples of 8 and >= K", lda, ldb);
+    NSD_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm_bf16: A and B must be 16-byte aligned");
+    NSD_CHECK_ARG(c_dtype == NSD_F32 || c_dtype == NSD_BF16, "gemm_bf16: bad output dtype");
+    NSD_CHECK_ARG(bias == nullptr || ((uintptr_t)bias & 15) == 0, "gemm_bf16: bias must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int BN = (N >= 192) ? 256 : (N >= 96 ? 128 : 64);
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, M, K, lda, BM);
+    if (rc) return rc;
+    rc = make_map(&tb, B, N, K, ldb, BN);
+    if (rc) return rc;
+    const bool f32 = c_dtype == NSD_F32;
+    if (BN == 256) return f32 ? launch<256, float>(ta, tb, C, ldc, bias, beta, M, N, K, s) : launch<256, __nv_bfloat16>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (BN == 128) return f32 ? launch<128, float>(ta, tb, C, ldc, bias, beta, M, N, K, s) : launch<128, __nv_bfloat16>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    return f32 ? launch<64, float>(ta, tb, C, ldc, bias, beta, M, N, K, s) : launch<64, __nv_bfloat16>(ta, tb, C, ldc, bias, beta, M, N, K, s);
 }

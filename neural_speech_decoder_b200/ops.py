@@ -73,6 +73,16 @@ def cast(src, dst_dtype):
     return dst
 
 
+def cast_transpose(src, want_copy: bool, want_t: bool):
+    """bf16 copy and/or bf16 transpose of a 2-D row-major tensor (last dim contiguous; row stride free)."""
+    R, Cn = src.shape
+    assert src.stride(1) == 1
+    dst = torch.empty((R, Cn), device=src.device, dtype=torch.bfloat16) if want_copy else None
+    dstT = torch.empty((Cn, R), device=src.device, dtype=torch.bfloat16) if want_t else None
+    call("nsd_cast_transpose", ptr(src), dtype_code(src.dtype), R, Cn, src.stride(0), ptr(dst), Cn, ptr(dstT), R, stream())
+    return dst, dstT
+
+
 def swap01(x):
     """[D0,D1,C] -> contiguous [D1,D0,C]."""
     D0, D1, Cc = x.shape

@@ -1,0 +1,66 @@
+"""K2 tensor-core GEMM (tcgen05 + TMA) against a plain fp32 reference of the same op on bf16-rounded inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from neural_speech_decoder_b200 import ops
+
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 256, 64), (128, 64, 128), (256, 128, 256), (200, 300, 192), (7552, 6144, 2048), (1000, 41 * 8, 72),
+    (6144, 1024, 7488), (130, 8200, 520), (64, 48, 64),
+])
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16"])
+def test_gemm_bf16_nt(M, N, K, out_dtype):
+    if out_dtype == "bf16" and M * N > 4e6:
+        pytest.skip("large case covered in f32")
+    g = torch.Generator(device="cpu").manual_seed(M * 31 + N * 7 + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    B = (torch.randn(N, K, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    odt = torch.float32 if out_dtype == "f32" else torch.bfloat16
+    C = torch.empty((M, N), device=DEV, dtype=odt)
+    ops.gemm(False, True, M, N, K, A, K, B, K, C, N, bias=bias)
+    ref = A.float() @ B.float().T + bias
+    tol = dict(rtol=2e-3, atol=2e-3) if out_dtype == "f32" else dict(rtol=1.6e-2, atol=2e-2)
+    torch.testing.assert_close(C.float(), ref, **tol)
+    # accumulate form: C <- A B^T + 0.5 C (no bias)
+    C0 = torch.randn((M, N), device=DEV).to(odt)
+    C1 = C0.clone()
+    ops.gemm(False, True, M, N, K, A, K, B, K, C1, N, beta=0.5)
+    torch.testing.assert_close(C1.float(), A.float() @ B.float().T + 0.5 * C0.float(), **tol)
+
+
+def test_gemm_bf16_strided_views_and_determinism():
+    """Sub-matrix operands (leading dimensions larger than K, offset pointers) as the model uses them."""
+    g = torch.Generator(device="cpu").manual_seed(0)
+    big_a = (torch.randn(300, 512, generator=g)).to(torch.bfloat16).to(DEV)
+    big_b = (torch.randn(400, 512, generator=g)).to(torch.bfloat16).to(DEV)
+    M, N, K = 300 - 64, 400, 512 - 128
+    C = torch.empty((M, 512), device=DEV)
+    ops.gemm(False, True, M, N, K, big_a, 512, big_b, 512, C, 512, a_off=64 * 512 + 64, b_off=128)
+    ref = big_a[64:, 64:64 + K].float() @ big_b[:, 128:128 + K].float().T
+    torch.testing.assert_close(C[:, :N], ref, rtol=2e-3, atol=2e-3)
+    C2 = torch.empty_like(C)
+    ops.gemm(False, True, M, N, K, big_a, 512, big_b, 512, C2, 512, a_off=64 * 512 + 64, b_off=128)
+    assert torch.equal(C[:, :N], C2[:, :N])
+
+
+def test_cast_transpose():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for R, Cn in [(64, 64), (70, 130), (7552, 96), (3, 5)]:
+        x = torch.randn(R, Cn, generator=g).to(DEV)
+        d, dT = ops.cast_transpose(x, True, True)
+        assert torch.equal(d, x.to(torch.bfloat16)) and torch.equal(dT, x.to(torch.bfloat16).T.contiguous())
+        xb = x.to(torch.bfloat16)
+        _, dT2 = ops.cast_transpose(xb, False, True)
+        assert torch.equal(dT2, xb.T.contiguous())
+    big = torch.randn(100, 300, generator=g).to(DEV)
+    view = big[:, 20:220]                                    # row stride 300, 200 columns
+    d, dT = ops.cast_transpose(view, True, True)
+    assert torch.equal(d, view.to(torch.bfloat16)) and torch.equal(dT, view.to(torch.bfloat16).T.contiguous())
