@@ -10,7 +10,7 @@ LIB := neural_speech_decoder_b200/libnsd_b200.so
 
 all: $(LIB)
 
-$(BUILD)/%.o: $(SRC_DIR)/%.cu $(SRC_DIR)/common.cuh include/nsd_b200.h
+$(BUILD)/%.o: $(SRC_DIR)/%.cu $(SRC_DIR)/common.cuh $(SRC_DIR)/tc_common.cuh include/nsd_b200.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
 

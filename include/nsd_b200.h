@@ -113,6 +113,22 @@ int nsd_gru_bwd_f32(const float* dhseq, int lddh, const float* hseq, int ldh, co
                     float* dgi, int ldgi, float* dghn, void* workspace, size_t workspace_bytes, void* stream);
 size_t nsd_gru_bwd_workspace(int B, int H);
 
+/* Tensor-core (bf16 operand, fp32 accumulate/state) form of the same recurrence: ONE cooperative launch walks all
+ * timesteps of one layer for D directions at once (direction 1, or direction 0 when reverse0 != 0, runs
+ * t = T'-1..0).  w_hh_bf16 is the bf16 copy of [weight_hh_l*, weight_hh_l*_reverse] stacked to [D*3H, H];
+ * b_hh is [D*3H]; gi is [T'*B, ldgi] with direction d at column d*3H; hseq (f32) and hseq_bf16 are [T'*B, ldh]
+ * with direction d at column d*H (the bf16 copy is what the CTAs exchange between steps and the next layer's GEMM
+ * operand); r,z,n,hn are [D][T'*B][H] (all NULL to skip).  Requires H % 64 == 0.  workspace: nsd_gru_tc_workspace. */
+int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
+                     int reverse0, float* hseq, void* hseq_bf16, int ldh, float* r, float* z, float* n, float* hn,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* BPTT of the above.  w_hhT_bf16 is the bf16 TRANSPOSE of each direction's W_hh stacked to [D*H, 3H].  Writes
+ * dgi_bf16 = [dr~,dz~,dn~] and dgh_bf16 = [dr~,dz~,dn~*r], both [T'*B, ldg] bf16 with direction d at column d*3H. */
+int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, const float* r, const float* z,
+                     const float* n, const float* hn, const void* w_hhT_bf16, int Tp, int B, int H, int D, int reverse0,
+                     void* dgi_bf16, void* dgh_bf16, int ldg, void* workspace, size_t workspace_bytes, void* stream);
+size_t nsd_gru_tc_workspace(int B, int H, int D);
+
 /* inter-layer dropout (nn.GRU dropout=p, train mode, model.py:55): out = x * mask / (1-p),
  * mask from a counter-based generator keyed by (seed, element index); the backward is the
  * same call on the gradient.  Distributional, not bit, parity with torch's generator.   */

@@ -7,20 +7,14 @@
 // It backs the time-batched W_ih projections of nn.GRU (reference model.py:50-57, 119), their dgrad / wgrad and
 // the time-batched W_hh wgrad.  Both operands must be K-major ("NT"); the callers keep transposed bf16 copies
 // (nsd_cast_transpose) where the natural layout is not.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nsd {
 namespace tc {
 
 constexpr int BM = 128;          // UMMA M (cta_group::1, all 128 TMEM lanes)
-constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int UMMA_K = 16;
 constexpr int THREADS = 256;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int ACC_STAGES = 2;
-constexpr long long SPIN_CYCLES = 6000000000LL;   // ~3 s: a broken pipeline traps instead of hanging the box
 
 template <int BN> struct Cfg {
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
@@ -30,86 +24,6 @@ template <int BN> struct Cfg {
     static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : (ACC_STAGES * BN <= 64 ? 64 : (ACC_STAGES * BN <= 128 ? 128 : (ACC_STAGES * BN <= 256 ? 256 : 512)));
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    unsigned int spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0xFFFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
-            printf("nsd gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// mbarrier arrives once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), registers = columns
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100),
-// layout type 2 = SWIZZLE_128B.  Advancing K by 16 bf16 (32 bytes) inside the atom adds 2 to the 16-byte address field.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major; canonical value 1)
-    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-    return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 struct TileCoord { int m_blk, n_blk; };
 __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n) {
@@ -286,8 +200,7 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
     return fn;
 }
 
-// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle, OOB reads as 0
-static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows) {
     PFN_cuTensorMapEncodeTiled enc = get_encode();
     if (!enc) { set_error("gemm_bf16: cuTensorMapEncodeTiled entry point not available"); return NSD_ERR_CUDA; }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -297,7 +210,7 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int 
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return NSD_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d ld=%d", (int)r, rows, cols, ld); return NSD_ERR_CUDA; }
     return NSD_OK;
 }
 
@@ -336,9 +249,9 @@ extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const 
     cudaStream_t s = (cudaStream_t)stream;
     const int BN = (N >= 192) ? 256 : (N >= 96 ? 128 : 64);
     CUtensorMap ta, tb;
-    int rc = make_map(&ta, A, M, K, lda, BM);
+    int rc = make_bf16_map(&ta, A, M, K, lda, BM);
     if (rc) return rc;
-    rc = make_map(&tb, B, N, K, ldb, BN);
+    rc = make_bf16_map(&tb, B, N, K, ldb, BN);
     if (rc) return rc;
     const bool f32 = c_dtype == NSD_F32;
     if (BN == 256) return f32 ? launch<256, float>(ta, tb, C, ldc, bias, beta, M, N, K, s) : launch<256, __nv_bfloat16>(ta, tb, C, ldc, bias, beta, M, N, K, s);

@@ -1,0 +1,168 @@
+"""bf16 tensor-core execution of GRUDecoder.forward / backward (precision="bf16").
+
+Same chain as model._DecoderFunction, with the dense contractions on tcgen05:
+  K1 (bf16 patches) -> per layer [K2 tcgen05 GEMM for both directions' W_ih at once -> K3 tcgen05 persistent
+  recurrence for both directions at once -> dropout] -> output layer (fp32 CUDA-core GEMM on the fp32 state).
+Parameters stay fp32 (master weights); bf16 operand copies are made per step.  Accumulation, hidden state, gate
+math, saved activations and all parameter gradients are fp32.  Reference: model.py:83-123, autograd of it.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops
+
+
+def _stack_bf16(ws, transpose: bool):
+    """bf16 copies of per-direction weights stacked for one launch.
+    transpose=False: [D*R, C] (rows of direction d at d*R).  transpose=True: W^T side by side, [C, D*R]."""
+    D = len(ws)
+    R, Cn = ws[0].shape
+    dev = ws[0].device
+    if not transpose:
+        out = torch.empty((D * R, Cn), device=dev, dtype=torch.bfloat16)
+        for d, w in enumerate(ws):
+            ops.cast_transpose_into(w, out[d * R:(d + 1) * R], None)
+    else:
+        out = torch.empty((Cn, D * R), device=dev, dtype=torch.bfloat16)
+        for d, w in enumerate(ws):
+            ops.cast_transpose_into(w, None, out[:, d * R:(d + 1) * R])
+    return out
+
+
+def _stack_rows_T(ws):
+    """[W_0^T ; W_1^T] stacked by rows: each W is [R, C] -> out [D*C, R]."""
+    D = len(ws)
+    R, Cn = ws[0].shape
+    out = torch.empty((D * Cn, R), device=ws[0].device, dtype=torch.bfloat16)
+    for d, w in enumerate(ws):
+        ops.cast_transpose_into(w, None, out[d * Cn:(d + 1) * Cn])
+    return out
+
+
+def _kmajor_T(src2d):
+    """bf16 transpose of a 2-D (row-strided) view, with the leading dimension padded to a multiple of 8 so the
+    result is a legal K-major TMA operand.  -> (tensor [C, ld], ld)."""
+    R, Cn = src2d.shape
+    ld = (R + 7) // 8 * 8
+    out = torch.empty((Cn, ld), device=src2d.device, dtype=torch.bfloat16)
+    ops.cast_transpose_into(src2d, None, out[:, :R])
+    return out, ld
+
+
+def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gru_w):
+    K, S, H, L, D = cfg["K"], cfg["S"], cfg["H"], cfg["L"], cfg["D"]
+    dev = x.device
+    B, T, N = x.shape
+    Tp = ops.n_frames(T, K, S)
+    M = Tp * B
+    day_idx = day_idx.to(device=dev, dtype=torch.int64).contiguous()
+    need_grad = any(t.requires_grad for t in (day_w, day_b, fc_w, fc_b) + tuple(gru_w))
+    patches, ys, z = ops.frontend_fwd(x, day_idx, day_w.detach().contiguous(), day_b.detach().contiguous(), taps,
+                                      K, S, torch.bfloat16, cfg["err_flag"])
+    inp = patches                                            # bf16 [M, in_l]
+    layers = []
+    hseq = None
+    for l in range(L):
+        in_l = inp.shape[1]
+        ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
+        w_ih_bf = _stack_bf16([w[0] for w in ws], False)                   # [D*3H, in_l]
+        w_hh_bf = _stack_bf16([w[1] for w in ws], False)                   # [D*3H, H]
+        b_ih = torch.cat([w[2] for w in ws]) if D > 1 else ws[0][2]
+        b_hh = torch.cat([w[3] for w in ws]) if D > 1 else ws[0][3]
+        gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
+        ops.gemm(False, True, M, D * 3 * H, in_l, inp, in_l, w_ih_bf, in_l, gi, D * 3 * H, bias=b_ih.contiguous())
+        hseq, hseq_bf, saves = ops.gru_fwd_bf16(gi, w_hh_bf, b_hh.contiguous(), Tp, B, H, D, False, need_grad)
+        del gi
+        nxt = hseq_bf
+        if cfg["p_drop"] > 0 and l < L - 1:
+            nxt = ops.dropout(hseq_bf, cfg["p_drop"], cfg["seed"] + l)
+        layers.append((inp, hseq, hseq_bf, saves))
+        inp = nxt
+    C = fc_w.shape[0]
+    logits_tm = torch.empty((M, C), device=dev, dtype=torch.float32)
+    ops.gemm(False, True, M, C, D * H, hseq, D * H, fc_w.detach(), D * H, logits_tm, C, bias=fc_b.detach())
+    logits = ops.swap01(logits_tm.view(Tp, B, C))
+    if need_grad:
+        ctx.cfg = cfg
+        ctx.dims = (B, T, N, Tp)
+        ctx.layers = layers
+        ctx.hid = hseq
+        ctx.front = (ys, z, day_idx)
+        ctx.weights = (day_w, fc_w, gru_w)
+        ctx.params = (day_w, day_b, fc_w, fc_b) + tuple(gru_w)
+    return logits
+
+
+def decoder_backward_tc(ctx, dlogits):
+    from .model import _assign_grads, _flat_views
+    cfg = ctx.cfg
+    K, S, H, L, D = cfg["K"], cfg["S"], cfg["H"], cfg["L"], cfg["D"]
+    B, T, N, Tp = ctx.dims
+    M = Tp * B
+    day_w, fc_w, gru_w = ctx.weights
+    dev = dlogits.device
+    C = fc_w.shape[0]
+    f32 = dict(device=dev, dtype=torch.float32)
+    gs = cfg.get("grad_sync")
+    dl_tm = ops.swap01(dlogits.contiguous().float()).view(M, C)
+    hid = ctx.hid
+    d_fc_w, d_fc_b = _flat_views([(C, D * H), (C,)], dev, gs)
+    ops.gemm(True, False, C, D * H, M, dl_tm, C, hid, D * H, d_fc_w, D * H)
+    ops.colsum(dl_tm, M, C, C, d_fc_b)
+    if gs is not None:
+        gs.bucket_ready(d_fc_w._base)
+    dh = torch.empty((M, D * H), **f32)
+    ops.gemm(False, False, M, D * H, C, dl_tm, C, fc_w.detach(), D * H, dh, D * H)
+    ggru: List[Optional[torch.Tensor]] = [None] * len(gru_w)
+    Mh = (Tp - 1) * B
+    for l in range(L - 1, -1, -1):
+        inp, hseq, hseq_bf, saves = ctx.layers[l]
+        in_l = inp.shape[1]
+        ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
+        if cfg["p_drop"] > 0 and l < L - 1:
+            dh = ops.dropout(dh, cfg["p_drop"], cfg["seed"] + l)
+        w_hhT_bf = _stack_rows_T([w[1] for w in ws])                       # [D*H, 3H]
+        dgi, dgh = ops.gru_bwd_bf16(dh, hseq, saves, w_hhT_bf, Tp, B, H, D, False)
+        # one flat bucket per layer, laid out so that each GEMM writes its whole (both-direction) block at once
+        v_wih, v_whh, v_bih, v_bhh = _flat_views([(D * 3 * H, in_l), (D * 3 * H, H), (D * 3 * H,), (D * 3 * H,)], dev, None,
+                                                 zero=(Tp == 1))
+        # wgrad W_ih: dW[D*3H, in_l] = dgi^T inp  (reduction over the T'*B rows -> both operands transposed to K-major)
+        dgiT, ldg = _kmajor_T(dgi)
+        inpT, ldi = _kmajor_T(inp)
+        ops.gemm(False, True, D * 3 * H, in_l, M, dgiT, ldg, inpT, ldi, v_wih, in_l)
+        ops.colsum(dgi, M, D * 3 * H, D * 3 * H, v_bih)
+        ops.colsum(dgh, M, D * 3 * H, D * 3 * H, v_bhh)
+        if Tp > 1:
+            for d in range(D):
+                # forward dir: dgh[t] pairs with h[t-1];  reverse dir: dgh[t] pairs with h[t+1]
+                g_lo, h_lo = (0, B) if d == 1 else (B, 0)
+                aT, lda = _kmajor_T(dgh[g_lo:g_lo + Mh, d * 3 * H:(d + 1) * 3 * H])
+                bT, ldb = _kmajor_T(hseq_bf[h_lo:h_lo + Mh, d * H:(d + 1) * H])
+                ops.gemm(False, True, 3 * H, H, Mh, aT, lda, bT, ldb, v_whh, H, c_off=d * 3 * H * H)
+        dinp = None
+        if l > 0 or day_w.requires_grad:
+            w_ihT_bf = _stack_bf16([w[0] for w in ws], True)               # [in_l, D*3H]
+            dinp = torch.empty((M, in_l), device=dev, dtype=torch.float32 if l > 0 else torch.bfloat16)
+            ops.gemm(False, True, M, in_l, D * 3 * H, dgi, D * 3 * H, w_ihT_bf, D * 3 * H, dinp, in_l)
+        for d in range(D):
+            base = (l * D + d) * 4
+            ggru[base:base + 4] = [v_wih[d * 3 * H:(d + 1) * 3 * H], v_whh[d * 3 * H:(d + 1) * 3 * H],
+                                   v_bih[d * 3 * H:(d + 1) * 3 * H], v_bhh[d * 3 * H:(d + 1) * 3 * H]]
+        if gs is not None:
+            gs.bucket_ready(v_wih._base)
+        ctx.layers[l] = None
+        dh = dinp
+    ys, z, day_idx = ctx.front
+    d_day_w = d_day_b = None
+    if dh is not None:
+        d_day_w, d_day_b = ops.frontend_bwd(dh, ys, z, day_idx, cfg["n_days"], K, S)
+        if gs is not None:
+            gs.bucket_ready(d_day_w._base)
+    ctx.layers = ctx.hid = ctx.front = None
+    grads = (d_day_w, d_day_b, d_fc_w, d_fc_b, *ggru)
+    if gs is not None:
+        return (None,) * 4 + _assign_grads(ctx.params, grads)
+    return (None, None, None, None) + grads

@@ -83,6 +83,14 @@ def cast_transpose(src, want_copy: bool, want_t: bool):
     return dst, dstT
 
 
+def cast_transpose_into(src, dst, dstT):
+    """bf16 copy (dst [R,C] view) and/or bf16 transpose (dstT [C,R] view) of a 2-D view; unit inner strides."""
+    R, Cn = src.shape
+    assert src.stride(1) == 1 and (dst is None or dst.stride(1) == 1) and (dstT is None or dstT.stride(1) == 1)
+    call("nsd_cast_transpose", ptr(src), dtype_code(src.dtype), R, Cn, src.stride(0), ptr(dst),
+         dst.stride(0) if dst is not None else 0, ptr(dstT), dstT.stride(0) if dstT is not None else 0, stream())
+
+
 def swap01(x):
     """[D0,D1,C] -> contiguous [D1,D0,C]."""
     D0, D1, Cc = x.shape
@@ -105,6 +113,34 @@ def gru_bwd_f32(dhseq, lddh, dh_off, hseq, ldh, h_off, saves, w_hh, Tp, B, H, re
     call("nsd_gru_bwd_f32", dhseq.data_ptr() + dh_off * 4, lddh, hseq.data_ptr() + h_off * 4, ldh, ptr(r), ptr(z),
          ptr(n), ptr(hn), ptr(w_hh), Tp, B, H, int(reverse), dgi.data_ptr() + dgi_off * 4, ldgi, ptr(dghn), ptr(ws),
          nbytes, stream())
+
+
+def gru_fwd_bf16(gi, w_hh_bf, b_hh, Tp, B, H, D, reverse0, want_saves):
+    """-> (hseq f32 [Tp*B, D*H], hseq bf16, saves (r,z,n,hn) each [D,Tp*B,H] or None)."""
+    dev = gi.device
+    M = Tp * B
+    hseq = torch.empty((M, D * H), device=dev, dtype=torch.float32)
+    hseq_bf = torch.empty((M, D * H), device=dev, dtype=torch.bfloat16)
+    sv = tuple(torch.empty((D, M, H), device=dev, dtype=torch.float32) for _ in range(4)) if want_saves else (None,) * 4
+    nbytes = _lib.lib().nsd_gru_tc_workspace(B, H, D)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    call("nsd_gru_fwd_bf16", ptr(gi), gi.stride(0), ptr(w_hh_bf), ptr(b_hh), Tp, B, H, D, int(reverse0), ptr(hseq),
+         ptr(hseq_bf), D * H, ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), ptr(ws), nbytes, stream())
+    return hseq, hseq_bf, (sv if want_saves else None)
+
+
+def gru_bwd_bf16(dhseq, hseq, saves, w_hhT_bf, Tp, B, H, D, reverse0):
+    """-> (dgi bf16 [Tp*B, D*3H] = [dr~,dz~,dn~], dgh bf16 = [dr~,dz~,dn~*r])."""
+    dev = dhseq.device
+    M = Tp * B
+    dgi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.bfloat16)
+    dgh = torch.empty((M, D * 3 * H), device=dev, dtype=torch.bfloat16)
+    nbytes = _lib.lib().nsd_gru_tc_workspace(B, H, D)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    r, z, n, hn = saves
+    call("nsd_gru_bwd_bf16", ptr(dhseq), dhseq.stride(0), ptr(hseq), hseq.stride(0), ptr(r), ptr(z), ptr(n), ptr(hn),
+         ptr(w_hhT_bf), Tp, B, H, D, int(reverse0), ptr(dgi), ptr(dgh), D * 3 * H, ptr(ws), nbytes, stream())
+    return dgi, dgh
 
 
 def dropout(x, p: float, seed: int):
