@@ -10,18 +10,21 @@
 // thread reads r/z/n pre-activations of its own (row, 8 units) with tcgen05.ld and does the gate math without any
 // cross-thread exchange.  Steps are separated by a per-direction grid barrier (release/acquire counter in global
 // memory) that only the TMA-producer thread waits on; everyone else sleeps on mbarriers.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace nsd {
 namespace rtc {
 using namespace nsd::tc;
 
-constexpr int BT = 64;                  // batch rows per UMMA (M = 64: TMEM lane = (row % 16) + 32 * (row / 16))
+constexpr int BT = 64;                  // batch rows per tile (UMMA M = 128 with rows 64..127 unused: TMEM lane = row)
 constexpr int STAGES = 8;               // A-operand ring depth
 constexpr int A_STAGE = BT * BK * 2;    // 8 KB per k-block
 constexpr int CTRL_THREADS = 128;       // warp 0: TMA + grid barrier, warp 1: MMA issue, warp 2: TMEM alloc, warp 3: idle
 constexpr int UPT = 8;                  // hidden units per epilogue thread
-constexpr int TMEM_COLS = 64;
+constexpr int TMEM_COLS = 256;             // 4 accumulation chains x (3U <= 48) columns
+constexpr int CHAINS = BK / UMMA_K;
 constexpr int CNT_STRIDE = 32;          // uint32 slots between the two directions' step counters (128 B apart)
 
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -47,7 +50,7 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int w_bytes) {
     Smem s;
     s.w = base;
     s.a = base + w_bytes;                       // w_bytes is a multiple of 1024
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s.a + STAGES * A_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s.a + (STAGES + 1) * A_STAGE);   // +1: the M=128 descriptor of the last stage reads 8 KB past it
     s.full = bars; s.empty = bars + STAGES; s.wbar = bars + 2 * STAGES; s.tmem_full = s.wbar + 1; s.tmem_empty = s.wbar + 2;
     s.tmem_slot = reinterpret_cast<uint32_t*>(s.wbar + 3);
     return s;
@@ -70,7 +73,14 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.s
 struct Common {
     int Tp, B, H, D, U, reverse0, nper;     // nper = CTAs per direction = H / U
     unsigned int* counters;
+    int dbg;                                // debug (NSD_GRU_DBG): 1 = skip the MMAs (timing experiment)
+    long long* trace;                       // debug (NSD_GRU_TRACE=1): clock64 stamps of block 0, [step < 16][8 events]
 };
+
+constexpr int TRACE_STEPS = 16;
+__device__ __forceinline__ void stamp(const Common& c, int s, int ev) {
+    if (c.trace != nullptr && blockIdx.x == 0 && s < TRACE_STEPS) c.trace[s * 8 + ev] = clock64();
+}
 
 // The control warps of both kernels: stream `nkb` k-blocks of A rows [row0, row0+64) per (step, batch tile) through the
 // ring and accumulate A * Wslice^T into TMEM.  a_row(step) gives the first A row of the step being consumed.
@@ -79,6 +89,9 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                                               const Common& c, int d, int nkb, int a_col0, bool bptt) {
     const int n_bt = (c.B + BT - 1) / BT;
     const bool rev = (d == 1) || (c.reverse0 != 0);
+    // Every CTA of a direction streams the SAME rows; starting each at a different k-block spreads the simultaneous
+    // requests over many L2 slices instead of 64 CTAs hammering one 8 KB box at a time.
+    const int rot = (int)(((long long)(blockIdx.x - d * c.nper) * nkb) / c.nper);
     if (warp == 0 && lane == 0) {
         int stage = 0; uint32_t phase = 0;
         for (int s = 1; s < c.Tp; ++s) {
@@ -88,17 +101,22 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
             else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
             grid_wait(c.counters + d * CNT_STRIDE, (unsigned int)(s * c.nper));
             fence_proxy_async();
+            stamp(c, s, 0);
             for (int bt = 0; bt < n_bt; ++bt) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&sm.empty[stage], phase ^ 1);
                     mbar_expect_tx(&sm.full[stage], A_STAGE);
-                    tma_load_2d(tmA, &sm.full[stage], sm.a + stage * A_STAGE, a_col0 + kb * BK, t_src * c.B + bt * BT);
+                    int kk = kb + rot; if (kk >= nkb) kk -= nkb;
+                    tma_load_2d(tmA, &sm.full[stage], sm.a + stage * A_STAGE, a_col0 + kk * BK, t_src * c.B + bt * BT);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            stamp(c, s, 1);
         }
     } else if (warp == 1 && lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(BT, NB);
+        // UMMA M = 128 over a 64-row tile: an M = 64 smem-sourced MMA costs ~128 cycles whatever N is; with M = 128 the
+        // cost scales with N.  Rows 64..127 alias the next 8 KB of shared memory (finite junk); their TMEM lanes are ignored.
+        constexpr uint32_t idesc = make_idesc_bf16(128, NB);
         mbar_wait(sm.wbar, 0);
         int stage = 0; uint32_t phase = 0; uint32_t it = 0;
         for (int s = 1; s < c.Tp; ++s) {
@@ -108,15 +126,20 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&sm.full[stage], phase);
                     tcgen05_fence_after();
+                    if (kb == 0 && bt == 0) stamp(c, s, 2);
                     const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sm.a + stage * A_STAGE));
-                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.w + (size_t)kb * NB * 128));
+                    int kk = kb + rot; if (kk >= nkb) kk -= nkb;
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.w + (size_t)kk * NB * 128));
+                    // 4 independent accumulation chains (one per 16-wide k-slice of the block), summed by the epilogue:
+                    // back-to-back MMAs into ONE small-N accumulator serialise on its read-modify-write latency
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        if (c.dbg != 1) umma_bf16(tmem_base + (uint32_t)(k * NB), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, kb != 0);
                     umma_commit(&sm.empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(sm.tmem_full);
+                if (bt == 0) stamp(c, s, 3);
             }
         }
     }
@@ -192,7 +215,7 @@ gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int d = blockIdx.x / c.nper;
     const int u0 = (blockIdx.x - d * c.nper) * U;
     const bool rev = (d == 1) || (c.reverse0 != 0);
-    const uint32_t tmem_base = setup<NB>(sm, warp, lane, EPI_WARPS);
+    const uint32_t tmem_base = setup<NB>(sm, warp, lane, EPI_WARPS / 2);
 
     if (warp == 0 && lane == 0) {
         // stationary weights: rows g*H + u0 .. +U of this direction's W_hh, all of K, once
@@ -206,45 +229,64 @@ gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else {
         // ------------------------------------------------------------ epilogue: gates for (row, 8 units)
         const int e = warp - 4, q = e & 3, grp = e >> 2;
-        const bool lane_ok = lane < 16;
+        const bool lane_ok = q < 2;                        // TMEM lanes 0..63 hold the 64 batch rows; warps on lanes 64..127 idle
         const int ub = u0 + grp * UPT;                      // first of this thread's 8 units
-        float bh[3][8];
-#pragma unroll
-        for (int g = 0; g < 3; ++g) ld8g(p.b_hh + d * 3 * H + g * H + ub, bh[g]);
         const int n_bt = (B + BT - 1) / BT;
         uint32_t it = 0;
+        float k_h[8], k_r[8], k_z[8], k_n[8], k_g[8];       // deferred stores (single batch tile)
+        bool last_ok = false; size_t last_m = 0;
         for (int s = 0; s < c.Tp; ++s) {
             const int t = rev ? (c.Tp - 1 - s) : s;
             const int tprev = rev ? t + 1 : t - 1;
             for (int bt = 0; bt < n_bt; ++bt) {
-                const int b = bt * BT + q * 16 + lane;
+                const int b = bt * BT + q * 32 + lane;
                 const bool row_ok = lane_ok && b < B;
                 const size_t m = (size_t)t * B + b;
-                float gi[3][8], hp[8];
+                float gi[3][8], hp[8], bn[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) hp[i] = 0.f;
+                for (int i = 0; i < 8; ++i) { hp[i] = 0.f; bn[i] = 0.f; }
                 if (row_ok) {
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) ld8g(p.gi + m * p.ldgi + d * 3 * H + g * H + ub, gi[g]);
-                    if (s > 0) ld8(p.hseq + ((size_t)tprev * B + b) * p.ldh + d * H + ub, hp);   // written by this very thread
+                    for (int g = 0; g < 3; ++g) {
+                        float bh[8];                          // b_hh: L1-resident, re-read instead of pinning 24 registers
+                        ld8g(p.gi + m * p.ldgi + d * 3 * H + g * H + ub, gi[g]);
+                        ld8g(p.b_hh + d * 3 * H + g * H + ub, bh);
+                        if (g < 2) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) gi[g][i] += bh[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) bn[i] = bh[i];
+                        }
+                    }
+                    if (s > 0) {
+                        if (n_bt > 1) ld8(p.hseq + ((size_t)tprev * B + b) * p.ldh + d * H + ub, hp);   // written by this very thread
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) hp[i] = k_h[i];                                 // still in registers
+                        }
+                    }
                 }
                 float acc[3][8];
                 if (s > 0) {
                     mbar_wait(sm.tmem_full, it & 1);
                     tcgen05_fence_after();
-                    uint32_t raw[3][8];
+                    if (threadIdx.x == CTRL_THREADS && bt == 0) stamp(c, s, 4);
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * UPT);
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) tmem_ld_32x8(taddr + (uint32_t)(g * U), raw[g]);
-                    tmem_ld_wait();
+                    for (int g = 0; g < 3; ++g) {
+                        uint32_t raw[CHAINS][8];
+#pragma unroll
+                        for (int ch = 0; ch < CHAINS; ++ch) tmem_ld_32x8(taddr + (uint32_t)(ch * NB + g * U), raw[ch]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            acc[g][i] = (__uint_as_float(raw[0][i]) + __uint_as_float(raw[1][i])) + (__uint_as_float(raw[2][i]) + __uint_as_float(raw[3][i]));
+                    }
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(sm.tmem_empty);
+                    if (lane == 0 && lane_ok) mbar_arrive(sm.tmem_empty);
                     ++it;
-#pragma unroll
-                    for (int g = 0; g < 3; ++g)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[g][i] = __uint_as_float(raw[g][i]);
                 } else {
 #pragma unroll
                     for (int g = 0; g < 3; ++g)
@@ -255,26 +297,43 @@ gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     float rr[8], zz[8], nn[8], gn[8], hv[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        rr[i] = fast_sigmoid(gi[0][i] + acc[0][i] + bh[0][i]);
-                        zz[i] = fast_sigmoid(gi[1][i] + acc[1][i] + bh[1][i]);
-                        gn[i] = acc[2][i] + bh[2][i];
+                        rr[i] = fast_sigmoid(gi[0][i] + acc[0][i]);
+                        zz[i] = fast_sigmoid(gi[1][i] + acc[1][i]);
+                        gn[i] = acc[2][i] + bn[i];
                         nn[i] = fast_tanh(fmaf(rr[i], gn[i], gi[2][i]));
                         hv[i] = fmaf(zz[i], hp[i] - nn[i], nn[i]);          // (1-z)*n + z*h_prev
                     }
+                    // the bf16 state is what the other CTAs wait for: store it first, publish, then write the rest
                     st8_bf16(p.hseq_bf + m * p.ldh + d * H + ub, hv);
-                    st8(p.hseq + m * p.ldh + d * H + ub, hv);
-                    if (p.r) {
-                        const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
-                        st8(p.r + o, rr); st8(p.z + o, zz); st8(p.n + o, nn); st8(p.hn + o, gn);
+                    if (n_bt > 1) {
+                        st8(p.hseq + m * p.ldh + d * H + ub, hv);
+                        if (p.r) {
+                            const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
+                            st8(p.r + o, rr); st8(p.z + o, zz); st8(p.n + o, nn); st8(p.hn + o, gn);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { k_h[i] = hv[i]; k_r[i] = rr[i]; k_z[i] = zz[i]; k_n[i] = nn[i]; k_g[i] = gn[i]; }
                     }
                 }
+                last_ok = row_ok; last_m = m;
             }
             // publish step s: every epilogue thread's stores -> one release increment of the direction's counter
+            if (threadIdx.x == CTRL_THREADS) stamp(c, s, 5);
             fence_proxy_async();
-            epi_bar_sync(EPI_WARPS * 32);
+            epi_bar_sync(EPI_WARPS * 32);    // idle warps arrive too
             if (threadIdx.x == CTRL_THREADS) {
+                stamp(c, s, 6);
                 __threadfence();
                 atomicAdd(c.counters + d * CNT_STRIDE, 1u);
+                stamp(c, s, 7);
+            }
+            if (n_bt == 1 && last_ok) {                      // off the critical path: nobody else reads these during the launch
+                st8(p.hseq + last_m * p.ldh + d * H + ub, k_h);
+                if (p.r) {
+                    const size_t o = ((size_t)d * c.Tp * B + last_m) * H + ub;
+                    st8(p.r + o, k_r); st8(p.z + o, k_z); st8(p.n + o, k_n); st8(p.hn + o, k_g);
+                }
             }
         }
     }
@@ -305,7 +364,7 @@ gru_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constan
     const int d = blockIdx.x / c.nper;
     const int u0 = (blockIdx.x - d * c.nper) * U;
     const bool rev = (d == 1) || (c.reverse0 != 0);
-    const uint32_t tmem_base = setup<NB>(sm, warp, lane, EPI_WARPS);
+    const uint32_t tmem_base = setup<NB>(sm, warp, lane, EPI_WARPS / 2);
 
     if (warp == 0 && lane == 0) {
         // stationary weights: rows u0 .. u0+U of this direction's W_hh^T [H, 3H], all of K = 3H, once
@@ -317,16 +376,18 @@ gru_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constan
         control_warps<NB>(sm, &tmG, warp, lane, tmem_base, c, d, nkb, d * 3 * H, true);
     } else {
         const int e = warp - 4, q = e & 3, grp = e >> 2;
-        const bool lane_ok = lane < 16;
+        const bool lane_ok = q < 2;                        // TMEM lanes 0..63 hold the 64 batch rows; warps on lanes 64..127 idle
         const int ub = u0 + grp * UPT;
         const int n_bt = (B + BT - 1) / BT;
         uint32_t it = 0;
+        float k_r[8], k_z[8], k_n[8], k_c[8];               // deferred stores / carry kept in registers (single batch tile)
+        bool last_ok = false; size_t last_m = 0;
         for (int s = 0; s < c.Tp; ++s) {
             const int t = rev ? s : (c.Tp - 1 - s);                  // BPTT visits time in the opposite order of the forward pass
             const int tprev = rev ? t + 1 : t - 1;                   // forward-time predecessor (source of h_{t-1})
             const bool has_prev = rev ? (t + 1 < c.Tp) : (t > 0);
             for (int bt = 0; bt < n_bt; ++bt) {
-                const int b = bt * BT + q * 16 + lane;
+                const int b = bt * BT + q * 32 + lane;
                 const bool row_ok = lane_ok && b < B;
                 const size_t m = (size_t)t * B + b;
                 float dh[8], rr[8], zz[8], nn[8], gn[8], hp[8], cr[8];
@@ -337,21 +398,30 @@ gru_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constan
                     ld8g(p.dhseq + m * p.lddh + d * H + ub, dh);
                     ld8g(p.r + o, rr); ld8g(p.z + o, zz); ld8g(p.n + o, nn); ld8g(p.hn + o, gn);
                     if (has_prev) ld8g(p.hseq + ((size_t)tprev * B + b) * p.ldh + d * H + ub, hp);
-                    if (s > 0) ld8(p.carry + ((size_t)d * B + b) * H + ub, cr);                 // written by this very thread
+                    if (s > 0) {
+                        if (n_bt > 1) ld8(p.carry + ((size_t)d * B + b) * H + ub, cr);          // written by this very thread
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) cr[i] = k_c[i];                         // still in registers
+                        }
+                    }
                 }
                 float acc[8];
                 if (s > 0) {
                     mbar_wait(sm.tmem_full, it & 1);
                     tcgen05_fence_after();
-                    uint32_t raw[8];
-                    tmem_ld_32x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * UPT), raw);
+                    if (threadIdx.x == CTRL_THREADS && bt == 0) stamp(c, s, 4);
+                    uint32_t raw[CHAINS][8];
+#pragma unroll
+                    for (int ch = 0; ch < CHAINS; ++ch) tmem_ld_32x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * NB + grp * UPT), raw[ch]);
                     tmem_ld_wait();
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(sm.tmem_empty);
+                    if (lane == 0 && lane_ok) mbar_arrive(sm.tmem_empty);
                     ++it;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]);
+                    for (int i = 0; i < 8; ++i)
+                        acc[i] = (__uint_as_float(raw[0][i]) + __uint_as_float(raw[1][i])) + (__uint_as_float(raw[2][i]) + __uint_as_float(raw[3][i]));
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -371,16 +441,29 @@ gru_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constan
                     }
                     __nv_bfloat16* gi_row = p.dgi + m * p.ldg + d * 3 * H + ub;
                     __nv_bfloat16* gh_row = p.dgh + m * p.ldg + d * 3 * H + ub;
-                    st8_bf16(gi_row, drt); st8_bf16(gi_row + H, dzt); st8_bf16(gi_row + 2 * H, dnt);
-                    st8_bf16(gh_row, drt); st8_bf16(gh_row + H, dzt); st8_bf16(gh_row + 2 * H, dgn);
-                    st8(p.carry + ((size_t)d * B + b) * H + ub, cr);
+                    st8_bf16(gh_row, drt); st8_bf16(gh_row + H, dzt); st8_bf16(gh_row + 2 * H, dgn);   // what the other CTAs wait for
+                    if (n_bt > 1) {
+                        st8_bf16(gi_row, drt); st8_bf16(gi_row + H, dzt); st8_bf16(gi_row + 2 * H, dnt);
+                        st8(p.carry + ((size_t)d * B + b) * H + ub, cr);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { k_r[i] = drt[i]; k_z[i] = dzt[i]; k_n[i] = dnt[i]; k_c[i] = cr[i]; }
+                    }
                 }
+                last_ok = row_ok; last_m = m;
             }
+            if (threadIdx.x == CTRL_THREADS) stamp(c, s, 5);
             fence_proxy_async();
-            epi_bar_sync(EPI_WARPS * 32);
+            epi_bar_sync(EPI_WARPS * 32);    // idle warps arrive too
             if (threadIdx.x == CTRL_THREADS) {
+                stamp(c, s, 6);
                 __threadfence();
                 atomicAdd(c.counters + d * CNT_STRIDE, 1u);
+                stamp(c, s, 7);
+            }
+            if (n_bt == 1 && last_ok) {                      // off the critical path
+                __nv_bfloat16* gi_row = p.dgi + last_m * p.ldg + d * 3 * H + ub;
+                st8_bf16(gi_row, k_r); st8_bf16(gi_row + H, k_z); st8_bf16(gi_row + 2 * H, k_n);
             }
         }
     }
@@ -395,7 +478,7 @@ static int pick_units(int H, int D) {
     return 0;
 }
 
-static size_t smem_bytes(int w_bytes) { return (size_t)w_bytes + STAGES * A_STAGE + 1024 + 256; }
+static size_t smem_bytes(int w_bytes) { return (size_t)w_bytes + (STAGES + 1) * A_STAGE + 1024 + 256; }
 
 template <typename Kern, typename P>
 static int launch_coop(Kern kern, int grid, int threads, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1, const P& p, cudaStream_t s) {
@@ -407,6 +490,30 @@ static int launch_coop(Kern kern, int grid, int threads, size_t smem, const CUte
     NSD_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), args, smem, s));
     count_launch(1);
     return NSD_OK;
+}
+
+// Debug aid: NSD_GRU_TRACE=1 prints block 0's per-step event times (SM cycles relative to the step's barrier pass).
+static long long* trace_begin() {
+    const char* e = getenv("NSD_GRU_TRACE");
+    if (!e || e[0] != '1') return nullptr;
+    long long* d = nullptr;
+    if (cudaMalloc(&d, sizeof(long long) * TRACE_STEPS * 8) != cudaSuccess) return nullptr;
+    cudaMemset(d, 0, sizeof(long long) * TRACE_STEPS * 8);
+    return d;
+}
+static void trace_end(const char* who, long long* d, cudaStream_t s) {
+    if (!d) return;
+    long long h[TRACE_STEPS * 8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    fprintf(stderr, "[%s trace, cycles] step: barrier->tma_issued mma_first_full mma_committed epi_wake epi_stored epi_bar published | step period\n", who);
+    for (int st = 1; st < TRACE_STEPS; ++st) {
+        const long long* r = h + st * 8;
+        if (r[0] == 0) break;
+        fprintf(stderr, "  s=%2d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", st, r[1] - r[0], r[2] - r[0], r[3] - r[0], r[4] - r[0],
+                r[5] - r[0], r[6] - r[0], r[7] - r[0], st > 1 ? r[0] - h[(st - 1) * 8] : 0LL);
+    }
 }
 
 static int check_shape(const char* who, int Tp, int B, int H, int D, int* U) {
@@ -443,13 +550,16 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     rc = make_bf16_map(&tmH, hseq_bf16, (long long)Tp * B, D * H, ldh, BT);
     if (rc) return rc;
     FwdParams p;
-    p.c = {Tp, B, H, D, U, reverse0, H / U, reinterpret_cast<unsigned int*>(workspace)};
+    long long* tr = trace_begin();
+    p.c = {Tp, B, H, D, U, reverse0, H / U, reinterpret_cast<unsigned int*>(workspace), getenv("NSD_GRU_DBG") ? atoi(getenv("NSD_GRU_DBG")) : 0, tr};
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
     const int grid = D * (H / U);
     const size_t smem = smem_bytes(3 * U * H * 2);
-    if (U == 8) return launch_coop(gru_fwd_tc_kernel<8>, grid, CTRL_THREADS + 128, smem, tmW, tmH, p, s);
-    return launch_coop(gru_fwd_tc_kernel<16>, grid, CTRL_THREADS + 256, smem, tmW, tmH, p, s);
+    rc = (U == 8) ? launch_coop(gru_fwd_tc_kernel<8>, grid, CTRL_THREADS + 128, smem, tmW, tmH, p, s)
+                  : launch_coop(gru_fwd_tc_kernel<16>, grid, CTRL_THREADS + 256, smem, tmW, tmH, p, s);
+    trace_end("gru_fwd_bf16", tr, s);
+    return rc;
 }
 
 int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, const float* r, const float* z,
@@ -470,14 +580,17 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     rc = make_bf16_map(&tmG, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, BT);
     if (rc) return rc;
     BwdParams p;
-    p.c = {Tp, B, H, D, U, reverse0, H / U, reinterpret_cast<unsigned int*>(workspace)};
+    long long* tr = trace_begin();
+    p.c = {Tp, B, H, D, U, reverse0, H / U, reinterpret_cast<unsigned int*>(workspace), getenv("NSD_GRU_DBG") ? atoi(getenv("NSD_GRU_DBG")) : 0, tr};
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
     p.carry = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
     const int grid = D * (H / U);
     const size_t smem = smem_bytes(U * 3 * H * 2);
-    if (U == 8) return launch_coop(gru_bwd_tc_kernel<8>, grid, CTRL_THREADS + 128, smem, tmWT, tmG, p, s);
-    return launch_coop(gru_bwd_tc_kernel<16>, grid, CTRL_THREADS + 256, smem, tmWT, tmG, p, s);
+    rc = (U == 8) ? launch_coop(gru_bwd_tc_kernel<8>, grid, CTRL_THREADS + 128, smem, tmWT, tmG, p, s)
+                  : launch_coop(gru_bwd_tc_kernel<16>, grid, CTRL_THREADS + 256, smem, tmWT, tmG, p, s);
+    trace_end("gru_bwd_bf16", tr, s);
+    return rc;
 }
 
 }  // extern "C"
