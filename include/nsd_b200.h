@@ -83,8 +83,10 @@ int nsd_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, in
 int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const void* A, int lda, const void* B,
                   int ldb, void* C, int ldc, int c_dtype, const float* bias, float beta, void* stream);
 
-/* column sums: out[n] = sum_m a[m*lda + n]  (bias gradients). */
-int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, void* stream);
+/* column sums: out[n] = sum_m a[m*lda + n]  (bias gradients); two fixed-order stages, workspace nsd_colsum_workspace(N). */
+int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, void* workspace, size_t workspace_bytes,
+               void* stream);
+size_t nsd_colsum_workspace(int N);
 /* dtype conversion of a contiguous buffer, f32 <-> bf16. */
 int nsd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 /* bf16 copies of a row-major [R,C] matrix (f32 or bf16 source): dst [R,C] (ld_dst) and/or its transpose dstT [C,R]

@@ -130,22 +130,48 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const fl
     }
 }
 
-template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ a, int M, int N, int lda, float* __restrict__ out) {
-    // block = 32 columns x 8 row-lanes; rows strided, tree-reduced in shared memory (fixed order -> deterministic)
-    __shared__ float red[8][33];
-    const int n = blockIdx.x * 32 + threadIdx.x;
-    float s = 0.f;
-    if (n < N)
-        for (int m = threadIdx.y; m < M; m += 8) s += to_f32<T>(a[(size_t)m * lda + n]);
-    red[threadIdx.y][threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.y == 0 && n < N) {
-        float t = 0.f;
+// Column sums (bias gradients), two deterministic stages: partial[c][n] over row chunk c, then a fixed-order sum over c.
+// VEC = elements per thread along n (2 for bf16 so that a warp reads full 128-byte rows).
+constexpr int CS_CHUNKS = 64;
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, int M, int N, int lda, int rows_per_chunk,
+                                                             float* __restrict__ partial) {
+    __shared__ float red[4][64 * VEC + 1];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int n = (blockIdx.x * 64 + tx) * VEC;
+    const int m0 = blockIdx.y * rows_per_chunk, m1 = min(M, m0 + rows_per_chunk);
+    float s[VEC];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-        out[n] = t;
+    for (int v = 0; v < VEC; ++v) s[v] = 0.f;
+    if (n < N) {
+        for (int m = m0 + ty; m < m1; m += 4) {
+            if constexpr (VEC == 2 && sizeof(T) == 2) {
+                if (n + 1 < N) {
+                    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(a + (size_t)m * lda + n);
+                    s[0] += __bfloat162float(v2.x); s[1] += __bfloat162float(v2.y);
+                } else s[0] += to_f32<T>(a[(size_t)m * lda + n]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (n + v < N) s[v] += to_f32<T>(a[(size_t)m * lda + n + v]);
+            }
+        }
     }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) red[ty][tx * VEC + v] = s[v];
+    __syncthreads();
+    if (ty == 0 && n < N) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (n + v < N) partial[(size_t)blockIdx.y * N + n + v] = (red[0][tx * VEC + v] + red[1][tx * VEC + v]) + (red[2][tx * VEC + v] + red[3][tx * VEC + v]);
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int N, int chunks, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * N + n];
+    out[n] = s;
 }
 
 template <typename S, typename D>
@@ -156,36 +182,58 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size
 }
 
 // dst[r][c] = bf16(src[r][c]) and/or dstT[c][r] = bf16(src[r][c]); 64x64 tiles through shared memory so that both
-// outputs are written in full 128-byte rows.  Makes the K-major operand copies the tcgen05 GEMM needs.
-template <typename S>
+// outputs are written in full rows.  Makes the K-major operand copies the tcgen05 GEMM needs.  VEC2: every thread moves
+// element PAIRS (8-byte f32 / 4-byte bf16 loads, 4-byte bf16x2 stores in both layouts); needs even leading dimensions,
+// 4/8-byte aligned bases; odd tails fall to the scalar instantiation.
+template <typename S, bool VEC2>
 __global__ void __launch_bounds__(256) cast_transpose_kernel(const S* __restrict__ src, int R, int Cn, int ld_src,
                                                              __nv_bfloat16* __restrict__ dst, int ld_dst,
                                                              __nv_bfloat16* __restrict__ dstT, int ld_dstT) {
     __shared__ float tile[64][65];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    for (int i = ty; i < 64; i += 8) {
-        const int r = r0 + i;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int c = c0 + tx + 32 * h;
-            float v = 0.f;
-            if (r < R && c < Cn) {
-                v = to_f32<S>(src[(size_t)r * ld_src + c]);
-                if (dst) dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(v);
+    if constexpr (VEC2) {
+        for (int i = ty; i < 64; i += 8) {
+            const int r = r0 + i, c = c0 + 2 * tx;
+            float v0 = 0.f, v1 = 0.f;
+            if (r < R && c < Cn) {               // Cn is even here, so c + 1 < Cn too
+                if constexpr (sizeof(S) == 4) { const float2 v = *reinterpret_cast<const float2*>(src + (size_t)r * ld_src + c); v0 = v.x; v1 = v.y; }
+                else { const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + (size_t)r * ld_src + c); v0 = __bfloat162float(v.x); v1 = __bfloat162float(v.y); }
+                if (dst) *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)r * ld_dst + c) = __floats2bfloat162_rn(v0, v1);
             }
-            tile[i][tx + 32 * h] = v;
+            tile[i][2 * tx] = v0; tile[i][2 * tx + 1] = v1;
         }
-    }
-    if (dstT == nullptr) return;
-    __syncthreads();
-    for (int i = ty; i < 64; i += 8) {
-        const int c = c0 + i;                 // output row
-        if (c >= Cn) continue;
+        if (dstT == nullptr) return;
+        __syncthreads();
+        for (int i = ty; i < 64; i += 8) {
+            const int c = c0 + i, r = r0 + 2 * tx;
+            if (c < Cn && r < R)                 // R is even here
+                *reinterpret_cast<__nv_bfloat162*>(dstT + (size_t)c * ld_dstT + r) = __floats2bfloat162_rn(tile[2 * tx][i], tile[2 * tx + 1][i]);
+        }
+    } else {
+        for (int i = ty; i < 64; i += 8) {
+            const int r = r0 + i;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int r = r0 + tx + 32 * h;   // output column
-            if (r < R) dstT[(size_t)c * ld_dstT + r] = __float2bfloat16_rn(tile[tx + 32 * h][i]);
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + tx + 32 * h;
+                float v = 0.f;
+                if (r < R && c < Cn) {
+                    v = to_f32<S>(src[(size_t)r * ld_src + c]);
+                    if (dst) dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(v);
+                }
+                tile[i][tx + 32 * h] = v;
+            }
+        }
+        if (dstT == nullptr) return;
+        __syncthreads();
+        for (int i = ty; i < 64; i += 8) {
+            const int c = c0 + i;
+            if (c >= Cn) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = r0 + tx + 32 * h;
+                if (r < R) dstT[(size_t)c * ld_dstT + r] = __float2bfloat16_rn(tile[tx + 32 * h][i]);
+            }
         }
     }
 }
@@ -222,14 +270,26 @@ int nsd_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, in
     return NSD_OK;
 }
 
-int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, void* stream) {
+size_t nsd_colsum_workspace(int N) { return sizeof(float) * (size_t)nsd::CS_CHUNKS * (size_t)(N > 0 ? N : 1); }
+
+int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, void* workspace, size_t workspace_bytes,
+               void* stream) {
     using namespace nsd;
     NSD_CHECK_ARG(M >= 0 && N > 0, "colsum: bad size");
-    dim3 grid(cdiv(N, 32)), block(32, 8);
+    if (workspace_bytes < nsd_colsum_workspace(N)) { set_error("colsum: workspace too small"); return NSD_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
-    if (a_dtype == NSD_F32) colsum_kernel<float><<<grid, block, 0, s>>>((const float*)a, M, N, lda, out);
-    else if (a_dtype == NSD_BF16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)a, M, N, lda, out);
-    else { set_error("colsum: bad dtype"); return NSD_ERR_INVALID; }
+    float* partial = reinterpret_cast<float*>(workspace);
+    const int rows_per_chunk = std::max(4, cdiv(cdiv(std::max(M, 1), CS_CHUNKS), 4) * 4);
+    const int chunks = std::max(1, cdiv(M, rows_per_chunk));
+    if (a_dtype == NSD_BF16) {
+        const bool vec = ((lda & 1) == 0) && (((uintptr_t)a & 3) == 0);
+        if (vec) colsum_partial_kernel<__nv_bfloat16, 2><<<dim3(cdiv(N, 128), chunks), 256, 0, s>>>((const __nv_bfloat16*)a, M, N, lda, rows_per_chunk, partial);
+        else colsum_partial_kernel<__nv_bfloat16, 1><<<dim3(cdiv(N, 64), chunks), 256, 0, s>>>((const __nv_bfloat16*)a, M, N, lda, rows_per_chunk, partial);
+    } else if (a_dtype == NSD_F32) {
+        colsum_partial_kernel<float, 1><<<dim3(cdiv(N, 64), chunks), 256, 0, s>>>((const float*)a, M, N, lda, rows_per_chunk, partial);
+    } else { set_error("colsum: bad dtype"); return NSD_ERR_INVALID; }
+    NSD_LAUNCH_CHECK();
+    colsum_final_kernel<<<cdiv(N, 256), 256, 0, s>>>(partial, N, chunks, out);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -254,9 +314,17 @@ int nsd_cast_transpose(const void* src, int src_dtype, int R, int Cn, int ld_src
     if (R == 0 || Cn == 0) return NSD_OK;
     dim3 grid(cdiv(Cn, 64), cdiv(R, 64));
     cudaStream_t s = (cudaStream_t)stream;
-    if (src_dtype == NSD_F32) cast_transpose_kernel<float><<<grid, 256, 0, s>>>((const float*)src, R, Cn, ld_src, (__nv_bfloat16*)dst, ld_dst, (__nv_bfloat16*)dstT, ld_dstT);
-    else if (src_dtype == NSD_BF16) cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, R, Cn, ld_src, (__nv_bfloat16*)dst, ld_dst, (__nv_bfloat16*)dstT, ld_dstT);
-    else { set_error("cast_transpose: bad dtype"); return NSD_ERR_INVALID; }
+    const int esz = (src_dtype == NSD_F32) ? 4 : 2;
+    const bool vec = (R % 2 == 0) && (Cn % 2 == 0) && (ld_src % 2 == 0) && (((uintptr_t)src & (size_t)(2 * esz - 1)) == 0) &&
+                     (!dst || ((ld_dst % 2 == 0) && (((uintptr_t)dst & 3) == 0))) && (!dstT || ((ld_dstT % 2 == 0) && (((uintptr_t)dstT & 3) == 0)));
+    __nv_bfloat16* d0 = (__nv_bfloat16*)dst; __nv_bfloat16* d1 = (__nv_bfloat16*)dstT;
+    if (src_dtype == NSD_F32) {
+        if (vec) cast_transpose_kernel<float, true><<<grid, 256, 0, s>>>((const float*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+        else cast_transpose_kernel<float, false><<<grid, 256, 0, s>>>((const float*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+    } else if (src_dtype == NSD_BF16) {
+        if (vec) cast_transpose_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+        else cast_transpose_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+    } else { set_error("cast_transpose: bad dtype"); return NSD_ERR_INVALID; }
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

@@ -109,7 +109,7 @@ __device__ __forceinline__ void stamp(const Common& c, int s, int ev) {
 // Shared memory: [A boxes: nkb x 8 KB][W slice: nkb x NB x 128 B][inbox: CS x NIN floats x 64 rows][barriers]
 // (A first: the M=128 descriptor of the last box reads 8 KB past it, i.e. into the weights -- finite junk, ignored lanes)
 struct Smem {
-    uint8_t* a; uint8_t* w; float* inbox; float* outbox;   // (CS-1) slots each: [slot][gate][row][16 floats]
+    uint8_t* a; uint8_t* w; __nv_bfloat16* inbox; __nv_bfloat16* outbox;   // (CS-1) slots each: [slot][gate][row][16 bf16]
     uint64_t* full;        // [nkb] A box landed
     uint64_t* wbar; uint64_t* tmem_full; uint64_t* tmem_empty; uint64_t* inbox_bar;
     uint32_t* tmem_slot;
@@ -121,8 +121,8 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int nkb_max, int nb, int inb
     s.a = base;
     s.w = base + (size_t)nkb_max * A_BOX;
     const size_t w_bytes = (size_t)nkb_max * nb * 128;
-    s.inbox = reinterpret_cast<float*>(s.w + (w_bytes < (size_t)A_BOX ? (size_t)A_BOX : w_bytes));
-    s.outbox = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.inbox) + inbox_bytes);
+    s.inbox = reinterpret_cast<__nv_bfloat16*>(s.w + (w_bytes < (size_t)A_BOX ? (size_t)A_BOX : w_bytes));
+    s.outbox = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(s.inbox) + inbox_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.outbox) + inbox_bytes);
     s.full = bars; s.wbar = bars + nkb_max; s.tmem_full = s.wbar + 1; s.tmem_empty = s.wbar + 2; s.inbox_bar = s.wbar + 3;
     s.tmem_slot = reinterpret_cast<uint32_t*>(s.wbar + 4);
@@ -256,9 +256,11 @@ __device__ __forceinline__ void stage_gate(uint32_t trow, int col0, int gate, in
             for (int i = 0; i < 8; ++i) own[i] = __uint_as_float(raw[p][i]);
         } else {
             const int slot = (p - me - 1 + CS) % CS;
-            float* dst = sm.outbox + ((size_t)(slot * NG + gate) * BT + row) * U + UPT * grp;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(raw[p][0], raw[p][1], raw[p][2], raw[p][3]);
-            *reinterpret_cast<uint4*>(dst + 4) = make_uint4(raw[p][4], raw[p][5], raw[p][6], raw[p][7]);
+            // partial sums travel as bf16 (the DSMEM link moves ~10 B/cycle/SM): 3 of the 4 addends carry 2^-9 relative rounding
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[p][i]);
+            st8_bf16(sm.outbox + ((size_t)(slot * NG + gate) * BT + row) * U + UPT * grp, v);
         }
     }
 }
@@ -267,7 +269,7 @@ __device__ __forceinline__ void stage_gate(uint32_t trow, int col0, int gate, in
 // threads have fenced (generic -> async proxy) and synchronised.
 template <int NG>
 __device__ __forceinline__ void send_outbox(const Smem& sm, int me) {
-    constexpr uint32_t BYTES = NG * BT * U * 4;
+    constexpr uint32_t BYTES = NG * BT * U * 2;
 #pragma unroll
     for (int p = 0; p < CS; ++p) {
         if (p == me) continue;
@@ -284,10 +286,13 @@ template <int NG>
 __device__ __forceinline__ void add_inbox(const Smem& sm, int gate, int row, int grp, float (&acc)[8]) {
 #pragma unroll
     for (int slot = 0; slot < CS - 1; ++slot) {
-        float v[8];
-        ld8(sm.inbox + ((size_t)(slot * NG + gate) * BT + row) * U + UPT * grp, v);
+        const uint4 u = *reinterpret_cast<const uint4*>(sm.inbox + ((size_t)(slot * NG + gate) * BT + row) * U + UPT * grp);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        for (int i = 0; i < 4; ++i) {                        // bf16 -> f32 is a 16-bit shift
+            acc[2 * i] += __uint_as_float(w[i] << 16);
+            acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+        }
     }
 }
 
@@ -303,7 +308,7 @@ struct FwdParams {
 __global__ void __launch_bounds__(THREADS, 1)
 gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
     constexpr int NB = 3 * UC;                       // 192 gate columns of the cluster
-    constexpr int INBOX = (CS - 1) * 3 * BT * U * 4;
+    constexpr int INBOX = (CS - 1) * 3 * BT * U * 2;
     extern __shared__ uint8_t smem_raw[];
     const Common& c = p.c;
     const int H = c.H, B = c.B;
@@ -367,7 +372,7 @@ gru_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
                 if (s > 0) {
-                    if (threadIdx.x == CTRL_THREADS) mbar_expect_tx(sm.inbox_bar, (uint32_t)((CS - 1) * 3 * BT * U * 4));
+                    if (threadIdx.x == CTRL_THREADS) mbar_expect_tx(sm.inbox_bar, (uint32_t)((CS - 1) * 3 * BT * U * 2));
                     if (lane_ok) {
                         if (nkb > 0) { mbar_wait(sm.tmem_full, it & 1); tcgen05_fence_after(); }
                         if (threadIdx.x == CTRL_THREADS && bt == 0) stamp(c, s, 4);
@@ -435,7 +440,7 @@ struct BwdParams {
 __global__ void __launch_bounds__(THREADS, 1)
 gru_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     constexpr int NB = UC;                           // 64 output units of the cluster
-    constexpr int INBOX = (CS - 1) * BT * U * 4;
+    constexpr int INBOX = (CS - 1) * BT * U * 2;
     extern __shared__ uint8_t smem_raw[];
     const Common& c = p.c;
     const int H = c.H, B = c.B;
@@ -488,7 +493,7 @@ gru_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = 0.f;
                 if (s > 0) {
-                    if (threadIdx.x == CTRL_THREADS) mbar_expect_tx(sm.inbox_bar, (uint32_t)((CS - 1) * BT * U * 4));
+                    if (threadIdx.x == CTRL_THREADS) mbar_expect_tx(sm.inbox_bar, (uint32_t)((CS - 1) * BT * U * 2));
                     if (lane_ok) {
                         if (nkb > 0) { mbar_wait(sm.tmem_full, it & 1); tcgen05_fence_after(); }
                         if (threadIdx.x == CTRL_THREADS && bt == 0) stamp(c, s, 4);
@@ -633,7 +638,7 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
     const int nkb_max = (H / BK + CS - 1) / CS;
-    const size_t smem = smem_bytes(nkb_max, 3 * UC, (CS - 1) * 3 * BT * U * 4);
+    const size_t smem = smem_bytes(nkb_max, 3 * UC, (CS - 1) * 3 * BT * U * 2);
     NSD_CHECK_ARG(smem <= 227 * 1024, "gru_fwd_bf16: hidden size %d needs %zu B of shared memory per CTA", H, smem);
     rc = launch_cluster_coop(gru_fwd_tc_kernel, D * (H / U), smem, tmW, tmH, p, s);
     trace_end("gru_fwd_bf16", tr, s, D * (H / U));
@@ -662,7 +667,7 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
     const int nkb_max = (3 * H / BK + CS - 1) / CS;
-    const size_t smem = smem_bytes(nkb_max, UC, (CS - 1) * BT * U * 4);
+    const size_t smem = smem_bytes(nkb_max, UC, (CS - 1) * BT * U * 2);
     NSD_CHECK_ARG(smem <= 227 * 1024, "gru_bwd_bf16: hidden size %d needs %zu B of shared memory per CTA", H, smem);
     rc = launch_cluster_coop(gru_bwd_tc_kernel, D * (H / U), smem, tmWT, tmG, p, s);
     trace_end("gru_bwd_bf16", tr, s, D * (H / U));

@@ -2,7 +2,7 @@
 
 Same chain as model._DecoderFunction, with the dense contractions on tcgen05:
   K1 (bf16 patches) -> per layer [K2 tcgen05 GEMM for both directions' W_ih at once -> K3 tcgen05 persistent
-  recurrence for both directions at once -> dropout] -> output layer (fp32 CUDA-core GEMM on the fp32 state).
+  recurrence for both directions at once -> dropout] -> output layer (tcgen05 GEMM, N = 41 classes).
 Parameters stay fp32 (master weights); bf16 operand copies are made per step.  Accumulation, hidden state, gate
 math, saved activations and all parameter gradients are fp32.  Reference: model.py:83-123, autograd of it.
 """
@@ -15,31 +15,22 @@ import torch
 from . import ops
 
 
-def _stack_bf16(ws, transpose: bool):
-    """bf16 copies of per-direction weights stacked for one launch.
-    transpose=False: [D*R, C] (rows of direction d at d*R).  transpose=True: W^T side by side, [C, D*R]."""
+def _bf16_stacks(ws, want_t: bool, t_side_by_side: bool):
+    """One pass over each direction's fp32 weight [R, C]: the bf16 copies stacked by rows [D*R, C] and, if asked, the
+    bf16 transposes -- side by side [C, D*R] (W_ih^T for dgrad) or stacked by rows [D*C, R] (W_hh^T for BPTT)."""
     D = len(ws)
     R, Cn = ws[0].shape
     dev = ws[0].device
-    if not transpose:
-        out = torch.empty((D * R, Cn), device=dev, dtype=torch.bfloat16)
-        for d, w in enumerate(ws):
-            ops.cast_transpose_into(w, out[d * R:(d + 1) * R], None)
-    else:
-        out = torch.empty((Cn, D * R), device=dev, dtype=torch.bfloat16)
-        for d, w in enumerate(ws):
-            ops.cast_transpose_into(w, None, out[:, d * R:(d + 1) * R])
-    return out
-
-
-def _stack_rows_T(ws):
-    """[W_0^T ; W_1^T] stacked by rows: each W is [R, C] -> out [D*C, R]."""
-    D = len(ws)
-    R, Cn = ws[0].shape
-    out = torch.empty((D * Cn, R), device=ws[0].device, dtype=torch.bfloat16)
+    out = torch.empty((D * R, Cn), device=dev, dtype=torch.bfloat16)
+    outT = None
+    if want_t:
+        outT = torch.empty((Cn, D * R) if t_side_by_side else (D * Cn, R), device=dev, dtype=torch.bfloat16)
     for d, w in enumerate(ws):
-        ops.cast_transpose_into(w, None, out[d * Cn:(d + 1) * Cn])
-    return out
+        tv = None
+        if want_t:
+            tv = outT[:, d * R:(d + 1) * R] if t_side_by_side else outT[d * Cn:(d + 1) * Cn]
+        ops.cast_transpose_into(w, out[d * R:(d + 1) * R], tv)
+    return out, outT
 
 
 def _kmajor_T(src2d):
@@ -68,8 +59,8 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
     for l in range(L):
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
-        w_ih_bf = _stack_bf16([w[0] for w in ws], False)                   # [D*3H, in_l]
-        w_hh_bf = _stack_bf16([w[1] for w in ws], False)                   # [D*3H, H]
+        w_ih_bf, w_ihT_bf = _bf16_stacks([w[0] for w in ws], need_grad and (l > 0 or day_w.requires_grad), True)   # [D*3H, in_l], [in_l, D*3H]
+        w_hh_bf, w_hhT_bf = _bf16_stacks([w[1] for w in ws], need_grad, False)                                     # [D*3H, H], [D*H, 3H]
         b_ih = torch.cat([w[2] for w in ws]) if D > 1 else ws[0][2]
         b_hh = torch.cat([w[3] for w in ws]) if D > 1 else ws[0][3]
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
@@ -79,17 +70,18 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
         nxt = hseq_bf
         if cfg["p_drop"] > 0 and l < L - 1:
             nxt = ops.dropout(hseq_bf, cfg["p_drop"], cfg["seed"] + l)
-        layers.append((inp, hseq, hseq_bf, saves))
+        layers.append((inp, hseq, hseq_bf, saves, w_ihT_bf, w_hhT_bf))
         inp = nxt
     C = fc_w.shape[0]
     logits_tm = torch.empty((M, C), device=dev, dtype=torch.float32)
-    ops.gemm(False, True, M, C, D * H, hseq, D * H, fc_w.detach(), D * H, logits_tm, C, bias=fc_b.detach())
+    fc_w_bf, fc_wT_bf = ops.cast_transpose(fc_w.detach(), True, False)[0], None
+    ops.gemm(False, True, M, C, D * H, hseq_bf, D * H, fc_w_bf, D * H, logits_tm, C, bias=fc_b.detach().contiguous())
     logits = ops.swap01(logits_tm.view(Tp, B, C))
     if need_grad:
         ctx.cfg = cfg
         ctx.dims = (B, T, N, Tp)
         ctx.layers = layers
-        ctx.hid = hseq
+        ctx.hid = hseq_bf
         ctx.front = (ys, z, day_idx)
         ctx.weights = (day_w, fc_w, gru_w)
         ctx.params = (day_w, day_b, fc_w, fc_b) + tuple(gru_w)
@@ -110,21 +102,27 @@ def decoder_backward_tc(ctx, dlogits):
     dl_tm = ops.swap01(dlogits.contiguous().float()).view(M, C)
     hid = ctx.hid
     d_fc_w, d_fc_b = _flat_views([(C, D * H), (C,)], dev, gs)
-    ops.gemm(True, False, C, D * H, M, dl_tm, C, hid, D * H, d_fc_w, D * H)
+    # output layer on tensor cores: d_fc_w = dl^T hid (reduction over T'*B), dh = dl fc_w (reduction over the C classes)
+    dlT, ldl = _kmajor_T(dl_tm)                                            # [C, ld>=M]
+    hidT, ldhT = _kmajor_T(hid)                                            # [D*H, ld>=M]
+    ops.gemm(False, True, C, D * H, M, dlT, ldl, hidT, ldhT, d_fc_w, D * H)
     ops.colsum(dl_tm, M, C, C, d_fc_b)
     if gs is not None:
         gs.bucket_ready(d_fc_w._base)
+    Cp = (C + 7) // 8 * 8
+    dl_bf = torch.empty((M, Cp), device=dev, dtype=torch.bfloat16)
+    ops.cast_transpose_into(dl_tm, dl_bf[:, :C], None)
+    fc_wT, ldw = _kmajor_T(fc_w.detach())                                  # [D*H, ld>=C]
     dh = torch.empty((M, D * H), **f32)
-    ops.gemm(False, False, M, D * H, C, dl_tm, C, fc_w.detach(), D * H, dh, D * H)
+    ops.gemm(False, True, M, D * H, C, dl_bf, Cp, fc_wT, ldw, dh, D * H)
     ggru: List[Optional[torch.Tensor]] = [None] * len(gru_w)
     Mh = (Tp - 1) * B
     for l in range(L - 1, -1, -1):
-        inp, hseq, hseq_bf, saves = ctx.layers[l]
+        inp, hseq, hseq_bf, saves, w_ihT_bf, w_hhT_bf = ctx.layers[l]
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
         if cfg["p_drop"] > 0 and l < L - 1:
             dh = ops.dropout(dh, cfg["p_drop"], cfg["seed"] + l)
-        w_hhT_bf = _stack_rows_T([w[1] for w in ws])                       # [D*H, 3H]
         dgi, dgh = ops.gru_bwd_bf16(dh, hseq, saves, w_hhT_bf, Tp, B, H, D, False)
         # one flat bucket per layer, laid out so that each GEMM writes its whole (both-direction) block at once
         v_wih, v_whh, v_bih, v_bhh = _flat_views([(D * 3 * H, in_l), (D * 3 * H, H), (D * 3 * H,), (D * 3 * H,)], dev, None,
@@ -144,7 +142,6 @@ def decoder_backward_tc(ctx, dlogits):
                 ops.gemm(False, True, 3 * H, H, Mh, aT, lda, bT, ldb, v_whh, H, c_off=d * 3 * H * H)
         dinp = None
         if l > 0 or day_w.requires_grad:
-            w_ihT_bf = _stack_bf16([w[0] for w in ws], True)               # [in_l, D*3H]
             dinp = torch.empty((M, in_l), device=dev, dtype=torch.float32 if l > 0 else torch.bfloat16)
             ops.gemm(False, True, M, in_l, D * 3 * H, dgi, D * 3 * H, w_ihT_bf, D * 3 * H, dinp, in_l)
         for d in range(D):

@@ -63,8 +63,10 @@ def gemm(transa: bool, transb: bool, M: int, N: int, K: int, A, lda: int, B, ldb
 
 
 def colsum(a, M: int, N: int, lda: int, out, a_off: int = 0, out_off: int = 0):
+    nbytes = _lib.lib().nsd_colsum_workspace(N)
+    ws = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
     call("nsd_colsum", a.data_ptr() + a_off * a.element_size(), dtype_code(a.dtype), M, N, lda,
-         out.data_ptr() + out_off * 4, stream())
+         out.data_ptr() + out_off * 4, ptr(ws), nbytes, stream())
 
 
 def cast(src, dst_dtype):
