@@ -48,7 +48,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
     *reinterpret_cast<uint2*>(p) = u;
 }
 
-template <int BN, typename OutT>
+template <int BN, typename OutT, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C, int ldc,
                const float* __restrict__ bias, float beta, int M, int N, int K) {
@@ -95,8 +95,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
-                    tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, tc.m_blk * BM);
-                    tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tc.n_blk * BN);
+                    if constexpr (!A_MN) tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, tc.m_blk * BM);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i) tma_load_2d(&tmA, &full_bar[stage], sa + i * 8192, tc.m_blk * BM + 64 * i, kb * BK);
+                    }
+                    if constexpr (!B_MN) tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tc.n_blk * BN);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES + i * 8192, tc.n_blk * BN + 64 * i, kb * BK);
+                    }
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -104,7 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===================== MMA issuer (one elected lane) =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -115,11 +123,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
-                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + cfg::A_BYTES);
+                    const uint64_t adesc = A_MN ? make_mnmajor_sw128_desc(sa, 8192) : make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(sa + cfg::A_BYTES, 8192) : make_kmajor_sw128_desc(sa + cfg::A_BYTES);
+                    // K advance of 16 elements: 32 bytes along a K-major row, two 1024-byte k groups in an MN-major tile
+                    constexpr uint64_t a_step = A_MN ? (2048 >> 4) : (32 >> 4), b_step = B_MN ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_bf16(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
                     umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
                     if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -214,10 +224,14 @@ int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int cols, 
     return NSD_OK;
 }
 
-template <int BN, typename OutT>
+int make_bf16_map_mn(CUtensorMap* map, const void* base, long long k_rows, int mn_cols, int ld) {
+    return make_bf16_map(map, base, k_rows, mn_cols, ld, BK);      // inner dim = mn (64-wide box), outer = k (64 rows)
+}
+
+template <int BN, typename OutT, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta, int M, int N, int K, cudaStream_t s) {
     using cfg = Cfg<BN>;
-    auto kern = gemm_tc_kernel<BN, OutT>;
+    auto kern = gemm_tc_kernel<BN, OutT, A_MN, B_MN>;
     static bool attr_set = false;       // per instantiation
     if (!attr_set) {
         NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
@@ -233,28 +247,40 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc
 }  // namespace tc
 }  // namespace nsd
 
+template <int BN, typename OutT>
+static int dispatch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta,
+                           int M, int N, int K, cudaStream_t s) {
+    using namespace nsd::tc;
+    if (!a_mn && !b_mn) return launch<BN, OutT, false, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (!a_mn && b_mn) return launch<BN, OutT, false, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (a_mn && b_mn) return launch<BN, OutT, true, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    return launch<BN, OutT, true, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+}
+
 extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                              void* C, int ldc, int c_dtype, const float* bias, float beta, void* stream) {
     using namespace nsd;
     using namespace nsd::tc;
     NSD_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
     if (M == 0 || N == 0) return NSD_OK;
-    NSD_CHECK_ARG(!transa && transb, "gemm_bf16: only the K-major form C = A[M,K] * B[N,K]^T is built (transa=0, transb=1); "
-                                     "make a transposed bf16 copy with nsd_cast_transpose");
     NSD_CHECK_ARG(A && B && C, "gemm_bf16: null pointer");
-    NSD_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K, "gemm_bf16: lda=%d / ldb=%d must be multiples of 8 and >= K", lda, ldb);
+    // op(A) [M,K]: stored [M,K] (K-major) if !transa, [K,M] (M-major) if transa.  op(B) [K,N]: stored [N,K] (K-major) if
+    // transb, [K,N] (N-major) if !transb.  Both majors are native UMMA operand layouts: no transposed copies needed.
+    const bool a_mn = transa != 0, b_mn = transb == 0;
+    NSD_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "gemm_bf16: lda=%d / ldb=%d must be multiples of 8", lda, ldb);
+    NSD_CHECK_ARG(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "gemm_bf16: leading dimension smaller than the row length");
     NSD_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm_bf16: A and B must be 16-byte aligned");
     NSD_CHECK_ARG(c_dtype == NSD_F32 || c_dtype == NSD_BF16, "gemm_bf16: bad output dtype");
     NSD_CHECK_ARG(bias == nullptr || ((uintptr_t)bias & 15) == 0, "gemm_bf16: bias must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const int BN = (N >= 192) ? 256 : (N >= 96 ? 128 : 64);
     CUtensorMap ta, tb;
-    int rc = make_bf16_map(&ta, A, M, K, lda, BM);
+    int rc = a_mn ? make_bf16_map_mn(&ta, A, K, M, lda) : make_bf16_map(&ta, A, M, K, lda, BM);
     if (rc) return rc;
-    rc = make_bf16_map(&tb, B, N, K, ldb, BN);
+    rc = b_mn ? make_bf16_map_mn(&tb, B, K, N, ldb) : make_bf16_map(&tb, B, N, K, ldb, BN);
     if (rc) return rc;
     const bool f32 = c_dtype == NSD_F32;
-    if (BN == 256) return f32 ? launch<256, float>(ta, tb, C, ldc, bias, beta, M, N, K, s) : launch<256, __nv_bfloat16>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (BN == 128) return f32 ? launch<128, float>(ta, tb, C, ldc, bias, beta, M, N, K, s) : launch<128, __nv_bfloat16>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    return f32 ? launch<64, float>(ta, tb, C, ldc, bias, beta, M, N, K, s) : launch<64, __nv_bfloat16>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (BN == 256) return f32 ? dispatch_layout<256, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<256, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (BN == 128) return f32 ? dispatch_layout<128, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<128, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+    return f32 ? dispatch_layout<64, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<64, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
 }

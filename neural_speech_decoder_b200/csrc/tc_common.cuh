@@ -14,6 +14,8 @@ constexpr long long SPIN_CYCLES = 6000000000LL;   // ~3 s: a broken pipeline tra
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle, OOB reads as 0
 int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows);
+// same, for an MN-major operand stored [K rows, MN cols] (ld elements per row): box = [64 k-rows, 64 mn-cols]
+int make_bf16_map_mn(CUtensorMap* map, const void* base, long long k_rows, int mn_cols, int ld);
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,9 +92,23 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
 }
+// MN-major, 128B-swizzled operand tile (the operand's M/N index is the contiguous one in memory): TMA boxes of
+// [64 k-rows][64 mn-elements = 128 B], one box (8 KB) per 64-wide mn chunk, boxes back to back.  Canonical UMMA layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = byte distance between mn chunks (one box), SBO = distance
+// between 8-row k groups (1024 B).  Advancing K by 16 (two 8-row groups) adds 2048 bytes to the start address.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t chunk_stride_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((chunk_stride_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset
+    d |= (uint64_t)(1024 >> 4) << 32;                             // stride byte offset
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 

@@ -33,16 +33,6 @@ def _bf16_stacks(ws, want_t: bool, t_side_by_side: bool):
     return out, outT
 
 
-def _kmajor_T(src2d):
-    """bf16 transpose of a 2-D (row-strided) view, with the leading dimension padded to a multiple of 8 so the
-    result is a legal K-major TMA operand.  -> (tensor [C, ld], ld)."""
-    R, Cn = src2d.shape
-    ld = (R + 7) // 8 * 8
-    out = torch.empty((Cn, ld), device=src2d.device, dtype=torch.bfloat16)
-    ops.cast_transpose_into(src2d, None, out[:, :R])
-    return out, ld
-
-
 def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gru_w):
     K, S, H, L, D = cfg["K"], cfg["S"], cfg["H"], cfg["L"], cfg["D"]
     dev = x.device
@@ -59,8 +49,8 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
     for l in range(L):
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
-        w_ih_bf, w_ihT_bf = _bf16_stacks([w[0] for w in ws], need_grad and (l > 0 or day_w.requires_grad), True)   # [D*3H, in_l], [in_l, D*3H]
-        w_hh_bf, w_hhT_bf = _bf16_stacks([w[1] for w in ws], need_grad, False)                                     # [D*3H, H], [D*H, 3H]
+        w_ih_bf, _ = _bf16_stacks([w[0] for w in ws], False, True)                     # [D*3H, in_l]
+        w_hh_bf, w_hhT_bf = _bf16_stacks([w[1] for w in ws], need_grad, False)         # [D*3H, H], [D*H, 3H] (BPTT operand)
         b_ih = torch.cat([w[2] for w in ws]) if D > 1 else ws[0][2]
         b_hh = torch.cat([w[3] for w in ws]) if D > 1 else ws[0][3]
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
@@ -70,11 +60,11 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
         nxt = hseq_bf
         if cfg["p_drop"] > 0 and l < L - 1:
             nxt = ops.dropout(hseq_bf, cfg["p_drop"], cfg["seed"] + l)
-        layers.append((inp, hseq, hseq_bf, saves, w_ihT_bf, w_hhT_bf))
+        layers.append((inp, hseq, hseq_bf, saves, w_ih_bf, w_hhT_bf))
         inp = nxt
     C = fc_w.shape[0]
     logits_tm = torch.empty((M, C), device=dev, dtype=torch.float32)
-    fc_w_bf, fc_wT_bf = ops.cast_transpose(fc_w.detach(), True, False)[0], None
+    fc_w_bf = ops.cast_transpose(fc_w.detach(), True, False)[0]
     ops.gemm(False, True, M, C, D * H, hseq_bf, D * H, fc_w_bf, D * H, logits_tm, C, bias=fc_b.detach().contiguous())
     logits = ops.swap01(logits_tm.view(Tp, B, C))
     if need_grad:
@@ -84,6 +74,7 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
         ctx.hid = hseq_bf
         ctx.front = (ys, z, day_idx)
         ctx.weights = (day_w, fc_w, gru_w)
+        ctx.fc_w_bf = fc_w_bf
         ctx.params = (day_w, day_b, fc_w, fc_b) + tuple(gru_w)
     return logits
 
@@ -102,23 +93,20 @@ def decoder_backward_tc(ctx, dlogits):
     dl_tm = ops.swap01(dlogits.contiguous().float()).view(M, C)
     hid = ctx.hid
     d_fc_w, d_fc_b = _flat_views([(C, D * H), (C,)], dev, gs)
-    # output layer on tensor cores: d_fc_w = dl^T hid (reduction over T'*B), dh = dl fc_w (reduction over the C classes)
-    dlT, ldl = _kmajor_T(dl_tm)                                            # [C, ld>=M]
-    hidT, ldhT = _kmajor_T(hid)                                            # [D*H, ld>=M]
-    ops.gemm(False, True, C, D * H, M, dlT, ldl, hidT, ldhT, d_fc_w, D * H)
-    ops.colsum(dl_tm, M, C, C, d_fc_b)
-    if gs is not None:
-        gs.bucket_ready(d_fc_w._base)
+    # output layer on tensor cores.  Reductions over the T'*B rows take their operands in the natural (MN-major) layout.
     Cp = (C + 7) // 8 * 8
     dl_bf = torch.empty((M, Cp), device=dev, dtype=torch.bfloat16)
     ops.cast_transpose_into(dl_tm, dl_bf[:, :C], None)
-    fc_wT, ldw = _kmajor_T(fc_w.detach())                                  # [D*H, ld>=C]
+    ops.gemm(True, False, C, D * H, M, dl_bf, Cp, hid, D * H, d_fc_w, D * H)            # d_fc_w = dl^T hid
+    ops.colsum(dl_tm, M, C, C, d_fc_b)
+    if gs is not None:
+        gs.bucket_ready(d_fc_w._base)
     dh = torch.empty((M, D * H), **f32)
-    ops.gemm(False, True, M, D * H, C, dl_bf, Cp, fc_wT, ldw, dh, D * H)
+    ops.gemm(False, False, M, D * H, C, dl_bf, Cp, ctx.fc_w_bf, D * H, dh, D * H)       # dh = dl fc_w
     ggru: List[Optional[torch.Tensor]] = [None] * len(gru_w)
     Mh = (Tp - 1) * B
     for l in range(L - 1, -1, -1):
-        inp, hseq, hseq_bf, saves, w_ihT_bf, w_hhT_bf = ctx.layers[l]
+        inp, hseq, hseq_bf, saves, w_ih_bf, w_hhT_bf = ctx.layers[l]
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
         if cfg["p_drop"] > 0 and l < L - 1:
@@ -127,23 +115,20 @@ def decoder_backward_tc(ctx, dlogits):
         # one flat bucket per layer, laid out so that each GEMM writes its whole (both-direction) block at once
         v_wih, v_whh, v_bih, v_bhh = _flat_views([(D * 3 * H, in_l), (D * 3 * H, H), (D * 3 * H,), (D * 3 * H,)], dev, None,
                                                  zero=(Tp == 1))
-        # wgrad W_ih: dW[D*3H, in_l] = dgi^T inp  (reduction over the T'*B rows -> both operands transposed to K-major)
-        dgiT, ldg = _kmajor_T(dgi)
-        inpT, ldi = _kmajor_T(inp)
-        ops.gemm(False, True, D * 3 * H, in_l, M, dgiT, ldg, inpT, ldi, v_wih, in_l)
+        # wgrad W_ih: dW[D*3H, in_l] = dgi^T inp -- reduction over the T'*B rows, both operands M/N-major as stored
+        ops.gemm(True, False, D * 3 * H, in_l, M, dgi, D * 3 * H, inp, in_l, v_wih, in_l)
         ops.colsum(dgi, M, D * 3 * H, D * 3 * H, v_bih)
         ops.colsum(dgh, M, D * 3 * H, D * 3 * H, v_bhh)
         if Tp > 1:
             for d in range(D):
-                # forward dir: dgh[t] pairs with h[t-1];  reverse dir: dgh[t] pairs with h[t+1]
+                # forward dir: dgh[t] pairs with h[t-1];  reverse dir: dgh[t] pairs with h[t+1]  (row-range views, no copies)
                 g_lo, h_lo = (0, B) if d == 1 else (B, 0)
-                aT, lda = _kmajor_T(dgh[g_lo:g_lo + Mh, d * 3 * H:(d + 1) * 3 * H])
-                bT, ldb = _kmajor_T(hseq_bf[h_lo:h_lo + Mh, d * H:(d + 1) * H])
-                ops.gemm(False, True, 3 * H, H, Mh, aT, lda, bT, ldb, v_whh, H, c_off=d * 3 * H * H)
+                ops.gemm(True, False, 3 * H, H, Mh, dgh, D * 3 * H, hseq_bf, D * H, v_whh, H,
+                         a_off=g_lo * D * 3 * H + d * 3 * H, b_off=h_lo * D * H + d * H, c_off=d * 3 * H * H)
         dinp = None
         if l > 0 or day_w.requires_grad:
             dinp = torch.empty((M, in_l), device=dev, dtype=torch.float32 if l > 0 else torch.bfloat16)
-            ops.gemm(False, True, M, in_l, D * 3 * H, dgi, D * 3 * H, w_ihT_bf, D * 3 * H, dinp, in_l)
+            ops.gemm(False, False, M, in_l, D * 3 * H, dgi, D * 3 * H, w_ih_bf, in_l, dinp, in_l)       # dgrad: dgi W_ih
         for d in range(D):
             base = (l * D + d) * 4
             ggru[base:base + 4] = [v_wih[d * 3 * H:(d + 1) * 3 * H], v_whh[d * 3 * H:(d + 1) * 3 * H],

@@ -36,6 +36,36 @@ def test_gemm_bf16_nt(M, N, K, out_dtype):
     torch.testing.assert_close(C1.float(), A.float() @ B.float().T + 0.5 * C0.float(), **tol)
 
 
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (64, 64, 128), (200, 304, 192), (6144, 2048, 7552), (3072, 1024, 7488),
+                                   (7552, 2048, 48), (41 + 7, 2048, 7552), (136, 72, 328)])
+def test_gemm_bf16_mn_major_operands(ta, tb, M, N, K):
+    """A stored [K,M] (transa) and/or B stored [K,N] (!transb): the natural layouts of wgrad / dgrad operands."""
+    g = torch.Generator(device="cpu").manual_seed(M * 31 + N * 7 + K + 2 * ta + tb)
+    A = (torch.randn((K, M) if ta else (M, K), generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    B = (torch.randn((N, K) if tb else (K, N), generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    C = torch.empty((M, N), device=DEV)
+    ops.gemm(ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C, N)
+    opA = A.float().T if ta else A.float()
+    opB = B.float().T if tb else B.float()
+    torch.testing.assert_close(C, opA @ opB, rtol=2e-3, atol=2e-3 * max(1.0, (K / 64) ** 0.5))
+
+
+def test_gemm_bf16_mn_major_row_offsets():
+    """W_hh wgrad form: both operands are row ranges of time-major activations (pointer offsets, K = (T'-1)*B rows)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    Bt, Tp, H = 5, 9, 64
+    Mrows = Tp * Bt
+    dgh = torch.randn(Mrows, 2 * 3 * H, generator=g).to(torch.bfloat16).to(DEV)
+    hs = torch.randn(Mrows, 2 * H, generator=g).to(torch.bfloat16).to(DEV)
+    Mh = (Tp - 1) * Bt
+    out = torch.empty((3 * H, H), device=DEV)
+    d = 1
+    ops.gemm(True, False, 3 * H, H, Mh, dgh, 2 * 3 * H, hs, 2 * H, out, H, a_off=0 * 2 * 3 * H + d * 3 * H, b_off=Bt * 2 * H + d * H)
+    ref = dgh[0:Mh, d * 3 * H:(d + 1) * 3 * H].float().T @ hs[Bt:Bt + Mh, d * H:(d + 1) * H].float()
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
 def test_gemm_bf16_strided_views_and_determinism():
     """Sub-matrix operands (leading dimensions larger than K, offset pointers) as the model uses them."""
     g = torch.Generator(device="cpu").manual_seed(0)
