@@ -1,0 +1,732 @@
+// K3 tensor-core path: persistent GRU recurrence (forward and BPTT) on tcgen05 with the recurrent weights
+// STATIONARY IN TENSOR MEMORY (reference nn.GRU, model.py:50-57, 104-119).
+//
+// One cooperative launch walks all timesteps of one layer, both directions at once.  Measured on B200
+// (scratch/umma_ts_bench.cu): one tcgen05.mma (M=128, K=16) costs max(46, N/2) cycles, with the A operand read from
+// tensor memory at no extra cost.  So the weights are the A operand (M = gate rows, loaded once into TMEM with
+// tcgen05.st), the batch is N, and the only per-step operand traffic is the previous state (B operand, TMA -> smem):
+//
+//   * forward: a cluster of 4 CTAs owns 64 hidden units of one direction.  CTA j holds in TMEM, for all 64 units x
+//     3 gates (two M tiles of 96 rows), the columns of W_hh that multiply ITS QUARTER of h_{t-1} (K split, 16 MMAs per
+//     tile per step at H = 1024).  BPTT: a cluster of 4 owns 128 units; CTA j holds W_hh^T[128 units, its quarter of
+//     the 3H gate index] (one full M tile, 48 MMAs per step; 16 clusters of 8 CTAs are not co-resident on a B200).
+//   * the partial sums D[gate row, batch] meet through distributed shared memory: each epilogue thread owns one TMEM
+//     lane (= one gate row), converts its row to bf16 and stages it in the outbox of the CTA that finalises that unit;
+//     one cp.async.bulk per peer completes the peer's inbox mbarrier.  Each CTA finalises 16 (BPTT: 32) units: gate math
+//     for (batch row, 4 units) per thread and pass, bf16 state stored first and published, fp32 state / saved gates after.
+//   * steps are separated by a grid barrier per (direction, batch group): a release/acquire counter in global memory
+//     that only the TMA-producer thread polls.
+//   * LATENCY HIDING: the batch is cut into groups of 32 rows (UMMA N = 32) that are independent sequences.  Two
+//     groups are in flight at once, each with its own smem operand buffer, TMEM accumulator, in/outbox and epilogue
+//     warpgroup, so the barrier + exchange latency of one group runs under the MMAs and gate math of the other.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace nsd {
+namespace rts {
+using namespace nsd::tc;
+
+constexpr int NG = 32;                  // batch rows per group = UMMA N
+constexpr int BOX_BYTES = NG * 128;     // one [32 rows x 64 k] bf16 box, 128B-swizzled
+constexpr int CTRL_THREADS = 128;       // warp 0: TMA + grid barrier, warp 1: MMA issue, warp 2: TMEM alloc, warp 3: idle
+constexpr int WG_THREADS = 128;         // one epilogue warpgroup per in-flight batch group
+constexpr int THREADS = CTRL_THREADS + 2 * WG_THREADS;
+constexpr int TMEM_COLS = 512;
+constexpr int A_COL0 = 128;             // TMEM: accumulators at columns [0, 128), stationary weights at [128, 512)
+constexpr int CNT_STRIDE = 32;          // uint32 slots between two step counters (128 B apart)
+constexpr int TRACE_STEPS = 16;
+
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned int spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if ((++spins & 0xFFFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
+            printf("nsd gru_ts: inbox timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
+    if (ld_acquire_u32(counter) >= target) return;
+    const long long t0 = clock64();
+    unsigned int spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+        if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
+            printf("nsd gru_ts: grid barrier timeout (block %d, have %u want %u)\n", blockIdx.x, ld_acquire_u32(counter), target);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void wg_bar_sync(int gg) { asm volatile("bar.sync %0, %1;" ::"r"(1 + gg), "n"(WG_THREADS) : "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: A = stationary weights, lane = row, two bf16 of consecutive k per 32-bit column
+__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+struct Common {
+    int Tp, B, H, D, reverse0;
+    int nper;                               // CTAs per direction
+    int G;                                  // batch groups of NG rows
+    int ktot, kper;                         // reduction length (H forward, 3H BPTT) and its share per CTA (multiple of 16)
+    unsigned int* counters;                 // [D][G] step counters, CNT_STRIDE apart
+    long long* trace;                       // debug (NSD_GRU_TRACE=1)
+};
+__device__ __forceinline__ void stamp(const Common& c, int s, int ev) {
+    if (c.trace == nullptr) return;
+    if (blockIdx.x == 0 && s < TRACE_STEPS) c.trace[s * 8 + ev] = clock64();
+    if (s == 8) {                           // every block, one step, global nanosecond timer: skew across CTAs
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        c.trace[TRACE_STEPS * 8 + blockIdx.x * 8 + ev] = (long long)g;
+    }
+}
+
+// Exchange rows are [gate][unit 0..UU-1][batch 0..31]; the batch index is rotated per unit so that both the row-wise
+// writers (lane = unit, 16-byte stores) and the column-wise readers (lane = (batch, unit/4), scalar loads) are
+// bank-conflict free.
+__device__ __forceinline__ int rot_f32(int u) { return ((4 * ((u >> 2) & 1) + 2 * ((u >> 3) & 1) + 2 * ((u >> 1) & 1) + (u & 1)) & 7) * 4; }
+__device__ __forceinline__ int rot_bf16(int u) { return (((u >> 1) & 3) ^ ((u >> 3) & 1)) * 8; }
+
+// Shared memory: [B operand: 2 buffers x nbox_max boxes][inbox: 2 x (CS-1) messages][outbox: same][self: 2 x fp32 rows][barriers]
+struct Smem {
+    uint8_t* b; uint8_t* inbox; uint8_t* outbox; float* self;
+    uint64_t* full; uint64_t* tmem_full; uint64_t* inbox_bar;     // [2] each
+    uint32_t* tmem_slot;
+};
+__device__ __forceinline__ Smem carve(uint8_t* raw, int nbox_max, int msgs_bytes, int self_bytes) {
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    Smem s;
+    s.b = base;
+    s.inbox = base + (size_t)2 * nbox_max * BOX_BYTES;
+    s.outbox = s.inbox + 2 * msgs_bytes;
+    s.self = reinterpret_cast<float*>(s.outbox + 2 * msgs_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.self) + 2 * self_bytes);
+    s.full = bars; s.tmem_full = bars + 2; s.inbox_bar = bars + 4;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    return s;
+}
+static size_t smem_bytes(int nbox_max, int msgs_bytes, int self_bytes) {
+    return (size_t)2 * nbox_max * BOX_BYTES + 4 * (size_t)msgs_bytes + 2 * (size_t)self_bytes + 8 * 8 + 1024 + 64;
+}
+
+__device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane) {
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.inbox_bar[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    __syncwarp();
+    cluster_sync_all();                 // every CTA's barriers exist before any peer pushes into its inbox
+    tcgen05_fence_after();
+    return *sm.tmem_slot;
+}
+__device__ __forceinline__ void teardown(int warp, uint32_t tmem_base) {
+    tcgen05_fence_before();
+    __syncthreads();
+    __syncwarp();
+    cluster_sync_all();                 // nobody leaves while a peer may still push into its shared memory
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// One row of the stationary operand into this thread's TMEM lane: k in [k_lo, k_lo + 2*kc) of `src_row` (nullptr or
+// beyond k_hi -> zeros), columns [col0, col0 + kc), 8 columns (= 16 bf16 = 32 bytes) per step, steps c0 = first, first+stride, ..
+__device__ __forceinline__ void load_a_row(uint32_t taddr_row, const __nv_bfloat16* src_row, int k_lo, int k_hi, int kc, int first, int stride) {
+    for (int c0 = first * 8; c0 < kc; c0 += stride * 8) {
+        uint32_t v[8];
+        if (src_row != nullptr && k_lo + 2 * c0 < k_hi) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src_row + k_lo + 2 * c0));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(src_row + k_lo + 2 * c0 + 8));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0u;
+        }
+        tmem_st_32x8(taddr_row + (uint32_t)c0, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// Control warps of both kernels.  Item (s, g): step s >= 1 of batch group g consumes the rows the direction produced
+// in step s-1 of that group.  Groups run in pairs (2p, 2p+1); group parity selects the buffers.  No "buffer free"
+// barriers are needed: passing the grid barrier of (s, g) implies that this CTA published (s-1, g), i.e. that its
+// MMAs and its epilogue for the previous use of the same buffers are finished.
+template <int NT>
+__device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, int warp, int lane, uint32_t tmem_base,
+                                              const Common& c, int d, int k_lo, int nslab, int nbox, int nbox_max, int b_col0, bool bptt) {
+    const bool rev = (d == 1) || (c.reverse0 != 0);
+    const int kc = c.kper / 2;
+    if (warp == 0 && lane == 0) {
+        for (int g0 = 0; g0 < c.G; g0 += 2) {
+            for (int s = 1; s < c.Tp; ++s) {
+                int t_src;
+                if (!bptt) { const int t = rev ? (c.Tp - 1 - s) : s; t_src = rev ? t + 1 : t - 1; }
+                else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
+                for (int gg = 0; gg < 2 && g0 + gg < c.G; ++gg) {
+                    const int g = g0 + gg;
+                    grid_wait(c.counters + (d * c.G + g) * CNT_STRIDE, (unsigned int)(s * c.nper));
+                    if (g == 0) stamp(c, s, 0);
+                    if (nbox > 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(&sm.full[gg], (uint32_t)(nbox * BOX_BYTES));
+                        for (int i = 0; i < nbox; ++i)
+                            tma_load_2d(tmB, &sm.full[gg], sm.b + (size_t)(gg * nbox_max + i) * BOX_BYTES, b_col0 + k_lo + i * BK, t_src * c.B + g * NG);
+                    } else {
+                        mbar_arrive(&sm.full[gg]);
+                    }
+                    if (g == 0) stamp(c, s, 1);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NG);
+        uint32_t n[2] = {0u, 0u};
+        for (int g0 = 0; g0 < c.G; g0 += 2) {
+            for (int s = 1; s < c.Tp; ++s) {
+                for (int gg = 0; gg < 2 && g0 + gg < c.G; ++gg) {
+                    mbar_wait(&sm.full[gg], n[gg] & 1);
+                    ++n[gg];
+                    if (g0 + gg == 0) stamp(c, s, 2);
+                    if (nslab > 0) {
+                        tcgen05_fence_after();
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            const uint32_t dcol = tmem_base + (uint32_t)((gg * NT + t) * NG);
+                            const uint32_t acol = tmem_base + (uint32_t)(A_COL0 + t * kc);
+                            for (int sl = 0; sl < nslab; ++sl) {
+                                const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.b + (size_t)(gg * nbox_max + (sl >> 2)) * BOX_BYTES)) + (uint64_t)(2 * (sl & 3));
+                                umma_ts_bf16(dcol, acol + (uint32_t)(sl * 8), bdesc, idesc, sl != 0);
+                            }
+                        }
+                        umma_commit(&sm.tmem_full[gg]);
+                    } else {
+                        mbar_arrive(&sm.tmem_full[gg]);
+                    }
+                    if (g0 + gg == 0) stamp(c, s, 3);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void ld4g(const float* p, float (&v)[4]) {    // read-only for the whole launch
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&a);
+}
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const float (&v)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+}
+
+// Phase A of the exchange: this thread's TMEM lane of accumulator tile `dcol` is gate row (gate, cluster unit ul) with
+// 32 batch columns.  The CTA that finalises unit ul is rank ul / UU: keep the row (fp32) if that is me, else stage it as
+// bf16 in the outbox slot of that peer (slot = (peer - me - 1) mod CS).
+template <int CS, int NGATE, int UU>
+__device__ __forceinline__ void stage_row(uint32_t taddr, bool have, int gate, int ul, int me, float* self, uint8_t* outbox) {
+    uint32_t raw[32];
+    if (have) {
+        tmem_ld_32x32(taddr, raw);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = 0u;
+    }
+    const int owner = ul / UU, uo = ul % UU;
+    if (owner == me) {
+        float* dst = self + (gate * UU + uo) * NG;
+        const int rot = rot_f32(uo);
+#pragma unroll
+        for (int cq = 0; cq < 8; ++cq)
+            *reinterpret_cast<uint4*>(dst + ((4 * cq + rot) & (NG - 1))) = make_uint4(raw[4 * cq], raw[4 * cq + 1], raw[4 * cq + 2], raw[4 * cq + 3]);
+    } else if (owner < CS) {
+        const int slot = (owner - me - 1 + CS) % CS;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(outbox) + ((slot * NGATE + gate) * UU + uo) * NG;
+        const int rot = rot_bf16(uo);
+#pragma unroll
+        for (int cq = 0; cq < 4; ++cq) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(raw[8 * cq]), __uint_as_float(raw[8 * cq + 1]));
+            u.y = pack_bf16(__uint_as_float(raw[8 * cq + 2]), __uint_as_float(raw[8 * cq + 3]));
+            u.z = pack_bf16(__uint_as_float(raw[8 * cq + 4]), __uint_as_float(raw[8 * cq + 5]));
+            u.w = pack_bf16(__uint_as_float(raw[8 * cq + 6]), __uint_as_float(raw[8 * cq + 7]));
+            *reinterpret_cast<uint4*>(dst + ((8 * cq + rot) & (NG - 1))) = u;
+        }
+    }
+}
+// One bulk shared->distributed-shared copy per peer: my outbox slot for peer p lands in p's inbox slot for me
+// ((me - p - 1) mod CS) and completes p's inbox mbarrier with the byte count.  Thread i < CS-1 serves peer (me+1+i) mod CS.
+template <int CS, int NGATE, int UU>
+__device__ __forceinline__ void send_message(uint8_t* outbox, uint8_t* inbox, uint64_t* inbox_bar, int me, int i) {
+    constexpr uint32_t MSG = NGATE * UU * NG * 2;
+    const int p = (me + 1 + i) % CS;
+    const int out_slot = i, in_slot = (me - p - 1 + CS) % CS;
+    const uint32_t src = smem_u32(outbox + (size_t)out_slot * MSG);
+    const uint32_t dst = map_to_cta(smem_u32(inbox + (size_t)in_slot * MSG), (uint32_t)p);
+    const uint32_t bar = map_to_cta(smem_u32(inbox_bar), (uint32_t)p);
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "r"(src), "r"(MSG), "r"(bar) : "memory");
+}
+// Phase B: sum of my fp32 partial and the CS-1 bf16 partials for (gate, units u0 .. u0+3, batch row bl)
+template <int CS, int NGATE, int UU>
+__device__ __forceinline__ void gather(const float* self, const uint8_t* inbox, int gate, int u0, int bl, float (&acc)[4]) {
+    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(inbox);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int u = u0 + i;
+        float a = self[(gate * UU + u) * NG + ((bl + rot_f32(u)) & (NG - 1))];
+        const int cb = (bl + rot_bf16(u)) & (NG - 1);
+#pragma unroll
+        for (int slot = 0; slot < CS - 1; ++slot) a += __bfloat162float(in[((slot * NGATE + gate) * UU + u) * NG + cb]);
+        acc[i] = a;
+    }
+}
+
+// =============================================================================================== forward
+struct FwdParams {
+    Common c;
+    const __nv_bfloat16* w;               // [D*3H, H] bf16 W_hh, gate rows r | z | n per direction
+    const float* gi; int ldgi;            // [Tp*B, D*3H] = x W_ih^T + b_ih
+    const float* b_hh;                    // [D*3H]
+    float* hseq; __nv_bfloat16* hseq_bf; int ldh;    // [Tp*B, D*H]; the bf16 copy is what the other CTAs TMA-load
+    float* r; float* z; float* n; float* hn;         // [D][Tp*B][H] or null
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
+    constexpr int CS = 4, NT = 2, NGATE = 3, U = 16;
+    constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
+    extern __shared__ uint8_t smem_raw[];
+    const Common& c = p.c;
+    const int H = c.H, B = c.B;
+    const int me = (int)cluster_rank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x / c.nper;
+    const int uc0 = ((blockIdx.x - d * c.nper) / CS) * (CS * U);        // first unit of the cluster
+    const bool rev = (d == 1) || (c.reverse0 != 0);
+    const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
+    const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK, nbox_max = (c.kper + BK - 1) / BK;
+    const int kc = c.kper / 2;
+    const Smem sm = carve(smem_raw, nbox_max, MSGS, SELF);
+    const uint32_t tmem_base = setup(sm, warp, lane);
+
+    if (warp >= 4) {
+        // stationary weights: tile t = units uc0 + 32t .. +32, lanes [r | z | n | unused] x 32 units, my quarter of K
+        const int e = warp - 4, w4 = e & 3, t = e >> 2;
+        const int unit = uc0 + 32 * t + lane;
+        const __nv_bfloat16* row = (w4 < 3 && unit < H) ? p.w + (size_t)(d * 3 * H + w4 * H + unit) * H : nullptr;
+        load_a_row(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(A_COL0 + t * kc), row, k_lo, k_hi, kc, 0, 1);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+
+    if (warp < 4) {
+        control_warps<NT>(sm, &tmH, warp, lane, tmem_base, c, d, k_lo, nslab, nbox, nbox_max, d * H, false);
+    } else {
+        // ------------------------------------------------------------ epilogue warpgroup gg: batch groups of parity gg
+        const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
+        const int bl = te >> 2, uo4 = te & 3;
+        const int ub = uc0 + me * U + 4 * uo4;             // first of this thread's 4 units
+        uint8_t* inbox = sm.inbox + gg * MSGS;
+        uint8_t* outbox = sm.outbox + gg * MSGS;
+        float* self = sm.self + gg * (SELF / 4);
+        float bh[3][4];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) ld4g(p.b_hh + d * 3 * H + g * H + ub, bh[g]);
+        uint32_t it = 0;
+        for (int g0 = 0; g0 + gg < c.G; g0 += 2) {
+            const int grp = g0 + gg;
+            const int b = grp * NG + bl;
+            const bool row_ok = b < B;
+            float k_h[4] = {0.f, 0.f, 0.f, 0.f};          // h_{t-1} of this thread's (row, 4 units), fp32, in registers
+            for (int s = 0; s < c.Tp; ++s) {
+                const int t = rev ? (c.Tp - 1 - s) : s;
+                const size_t m = (size_t)t * B + b;
+                float gi[3][4];
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        ld4g(p.gi + m * p.ldgi + d * 3 * H + g * H + ub, gi[g]);
+                        if (g < 2) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) gi[g][i] += bh[g][i];
+                        }
+                    }
+                }
+                float acc[3][4];
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
+                if (s > 0) {
+                    if (te == 0) mbar_expect_tx(&sm.inbox_bar[gg], (uint32_t)MSGS);
+                    mbar_wait(&sm.tmem_full[gg], it & 1);
+                    tcgen05_fence_after();
+                    if (te == 0 && grp == 0) stamp(c, s, 4);
+                    if (w4 < 3) {
+#pragma unroll
+                        for (int t2 = 0; t2 < NT; ++t2)
+                            stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)((gg * NT + t2) * NG), nslab > 0, w4,
+                                                 32 * t2 + lane, me, self, outbox);
+                    }
+                    tcgen05_fence_before();
+                    fence_proxy_async_smem();
+                    wg_bar_sync(gg);
+                    if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[gg], me, te);
+                    mbar_wait_cluster(&sm.inbox_bar[gg], it & 1);
+                    if (te == 0 && grp == 0) stamp(c, s, 5);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) gather<CS, NGATE, U>(self, inbox, g, 4 * uo4, bl, acc[g]);
+                    ++it;
+                }
+                float rr[4], zz[4], nn[4], gn[4];
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        rr[i] = fast_sigmoid(gi[0][i] + acc[0][i]);
+                        zz[i] = fast_sigmoid(gi[1][i] + acc[1][i]);
+                        gn[i] = acc[2][i] + bh[2][i];
+                        nn[i] = fast_tanh(fmaf(rr[i], gn[i], gi[2][i]));
+                        k_h[i] = fmaf(zz[i], k_h[i] - nn[i], nn[i]);        // (1-z)*n + z*h_prev
+                    }
+                    // the bf16 state is what the other CTAs wait for: store it first, publish, then write the rest
+                    st4_bf16(p.hseq_bf + m * p.ldh + d * H + ub, k_h);
+                }
+                if (te == 0 && grp == 0) stamp(c, s, 6);
+                wg_bar_sync(gg);                             // (the consumer fences generic->async proxy after its acquire)
+                if (te == 0) {
+                    __threadfence();
+                    atomicAdd(c.counters + (d * c.G + grp) * CNT_STRIDE, 1u);
+                    if (grp == 0) stamp(c, s, 7);
+                }
+                if (row_ok) {                                // off the critical path: nobody else reads these during the launch
+                    st4(p.hseq + m * p.ldh + d * H + ub, k_h);
+                    if (p.r) {
+                        const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
+                        st4(p.r + o, rr); st4(p.z + o, zz); st4(p.n + o, nn); st4(p.hn + o, gn);
+                    }
+                }
+            }
+        }
+    }
+    teardown(warp, tmem_base);
+}
+
+// =============================================================================================== BPTT
+struct BwdParams {
+    Common c;
+    const __nv_bfloat16* wT;              // [D*H, 3H] bf16 transpose of W_hh per direction
+    const float* dhseq; int lddh;         // [Tp*B, D*H] gradient w.r.t. every emitted h_t
+    const float* hseq; int ldh;           // forward hidden states (f32)
+    const float* r; const float* z; const float* n; const float* hn;   // [D][Tp*B][H]
+    __nv_bfloat16* dgi; __nv_bfloat16* dgh; int ldg;    // [Tp*B, D*3H]: [dr~,dz~,dn~] and [dr~,dz~,dn~*r]
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
+    constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16;       // NP passes of (batch row, 4 units) per thread
+    constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
+    extern __shared__ uint8_t smem_raw[];
+    const Common& c = p.c;
+    const int H = c.H, B = c.B;
+    const int me = (int)cluster_rank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x / c.nper;
+    const int uc0 = ((blockIdx.x - d * c.nper) / CS) * (CS * U);
+    const bool rev = (d == 1) || (c.reverse0 != 0);
+    const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
+    const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK, nbox_max = (c.kper + BK - 1) / BK;
+    const int kc = c.kper / 2;
+    const Smem sm = carve(smem_raw, nbox_max, MSGS, SELF);
+    const uint32_t tmem_base = setup(sm, warp, lane);
+
+    if (warp >= 4) {
+        // stationary weights: lane = unit uc0 + lane of W_hh^T [H, 3H], my quarter of the gate index; the two warpgroups
+        // interleave the column chunks
+        const int e = warp - 4, w4 = e & 3, half = e >> 2;
+        const int unit = uc0 + w4 * 32 + lane;
+        const __nv_bfloat16* row = unit < H ? p.wT + (size_t)(d * H + unit) * (3 * H) : nullptr;
+        load_a_row(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)A_COL0, row, k_lo, k_hi, kc, half, 2);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+
+    if (warp < 4) {
+        control_warps<NT>(sm, &tmG, warp, lane, tmem_base, c, d, k_lo, nslab, nbox, nbox_max, d * 3 * H, true);
+    } else {
+        const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
+        const int bl = te >> 2, uo4 = te & 3;
+        const int ub0 = uc0 + me * U + 4 * uo4;             // pass q handles units ub0 + 16q .. +3
+        uint8_t* inbox = sm.inbox + gg * MSGS;
+        uint8_t* outbox = sm.outbox + gg * MSGS;
+        float* self = sm.self + gg * (SELF / 4);
+        uint32_t it = 0;
+        for (int g0 = 0; g0 + gg < c.G; g0 += 2) {
+            const int grp = g0 + gg;
+            const int b = grp * NG + bl;
+            float cr[NP][4];                                 // dh_t * z_t carried to the next step, in registers
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cr[q][i] = 0.f;
+            for (int s = 0; s < c.Tp; ++s) {
+                const int t = rev ? s : (c.Tp - 1 - s);              // BPTT visits time in the opposite order of the forward pass
+                const int tprev = rev ? t + 1 : t - 1;               // forward-time predecessor (source of h_{t-1})
+                const bool has_prev = rev ? (t + 1 < c.Tp) : (t > 0);
+                const size_t m = (size_t)t * B + b;
+                float dh[NP][4], rr[NP][4], zz[NP][4], nn[NP][4], gn[NP][4], hp[NP][4];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const int ub = ub0 + 16 * q;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) hp[q][i] = 0.f;
+                    if (b < B && ub < H) {                   // H % 64 == 0: a pass's 16 units are all inside or all outside
+                        const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
+                        ld4g(p.dhseq + m * p.lddh + d * H + ub, dh[q]);
+                        ld4g(p.r + o, rr[q]); ld4g(p.z + o, zz[q]); ld4g(p.n + o, nn[q]); ld4g(p.hn + o, gn[q]);
+                        if (has_prev) ld4g(p.hseq + ((size_t)tprev * B + b) * p.ldh + d * H + ub, hp[q]);
+                    }
+                }
+                float acc[NP][4];
+#pragma unroll
+                for (int q = 0; q < NP; ++q)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
+                if (s > 0) {
+                    if (te == 0) mbar_expect_tx(&sm.inbox_bar[gg], (uint32_t)MSGS);
+                    mbar_wait(&sm.tmem_full[gg], it & 1);
+                    tcgen05_fence_after();
+                    if (te == 0 && grp == 0) stamp(c, s, 4);
+                    stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(gg * NT * NG), nslab > 0, 0, w4 * 32 + lane, me, self, outbox);
+                    tcgen05_fence_before();
+                    fence_proxy_async_smem();
+                    wg_bar_sync(gg);
+                    if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[gg], me, te);
+                    mbar_wait_cluster(&sm.inbox_bar[gg], it & 1);
+                    if (te == 0 && grp == 0) stamp(c, s, 5);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) gather<CS, NGATE, U>(self, inbox, 0, 16 * q + 4 * uo4, bl, acc[q]);
+                    ++it;
+                }
+                float drt[NP][4], dzt[NP][4], dnt[NP][4];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const int ub = ub0 + 16 * q;
+                    if (b < B && ub < H) {
+                        float dgn[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float dht = dh[q][i] + cr[q][i] + acc[q][i];
+                            const float dn = dht * (1.0f - zz[q][i]);
+                            const float dz = dht * (hp[q][i] - nn[q][i]);
+                            dnt[q][i] = dn * (1.0f - nn[q][i] * nn[q][i]);
+                            dzt[q][i] = dz * zz[q][i] * (1.0f - zz[q][i]);
+                            drt[q][i] = dnt[q][i] * gn[q][i] * rr[q][i] * (1.0f - rr[q][i]);
+                            dgn[i] = dnt[q][i] * rr[q][i];
+                            cr[q][i] = dht * zz[q][i];
+                        }
+                        __nv_bfloat16* gh_row = p.dgh + m * p.ldg + d * 3 * H + ub;
+                        st4_bf16(gh_row, drt[q]); st4_bf16(gh_row + H, dzt[q]); st4_bf16(gh_row + 2 * H, dgn);   // what the other CTAs wait for
+                    }
+                }
+                if (te == 0 && grp == 0) stamp(c, s, 6);
+                wg_bar_sync(gg);                             // (the consumer fences generic->async proxy after its acquire)
+                if (te == 0) {
+                    __threadfence();
+                    atomicAdd(c.counters + (d * c.G + grp) * CNT_STRIDE, 1u);
+                    if (grp == 0) stamp(c, s, 7);
+                }
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {               // off the critical path
+                    const int ub = ub0 + 16 * q;
+                    if (b < B && ub < H) {
+                        __nv_bfloat16* gi_row = p.dgi + m * p.ldg + d * 3 * H + ub;
+                        st4_bf16(gi_row, drt[q]); st4_bf16(gi_row + H, dzt[q]); st4_bf16(gi_row + 2 * H, dnt[q]);
+                    }
+                }
+            }
+        }
+    }
+    teardown(warp, tmem_base);
+}
+
+// ---------------------------------------------------------------- host side
+template <typename Kern, typename P>
+static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const P& p, cudaStream_t s) {
+    NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = cs; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs; cfg.numAttrs = 2;
+    int max_clusters = 0;
+    NSD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters * cs < grid) { set_error("gru_ts: %d CTAs in clusters of %d cannot be co-resident (max %d clusters)", grid, cs, max_clusters); return NSD_ERR_INVALID; }
+    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, p));
+    count_launch(1);
+    return NSD_OK;
+}
+
+// Debug aid: NSD_GRU_TRACE=1 prints block 0's per-step event times of batch group 0 (SM cycles relative to the step's barrier pass).
+static long long* trace_begin() {
+    const char* e = getenv("NSD_GRU_TRACE");
+    if (!e || e[0] != '1') return nullptr;
+    long long* d = nullptr;
+    if (cudaMalloc(&d, sizeof(long long) * (TRACE_STEPS + 160) * 8) != cudaSuccess) return nullptr;
+    cudaMemset(d, 0, sizeof(long long) * (TRACE_STEPS + 160) * 8);
+    return d;
+}
+static void trace_end(const char* who, long long* d, cudaStream_t s, int grid = 0) {
+    if (!d) return;
+    static long long h[(TRACE_STEPS + 160) * 8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    fprintf(stderr, "[%s trace, group 0, cycles] step: barrier->tma_issued operand_landed mma_committed epi_wake inbox_complete state_stored published | step period\n", who);
+    for (int st = 1; st < TRACE_STEPS; ++st) {
+        const long long* r = h + st * 8;
+        if (r[0] == 0) break;
+        fprintf(stderr, "  s=%2d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", st, r[1] - r[0], r[2] - r[0], r[3] - r[0], r[4] - r[0],
+                r[5] - r[0], r[6] - r[0], r[7] - r[0], st > 1 ? r[0] - h[(st - 1) * 8] : 0LL);
+    }
+    long long t0 = -1;
+    for (int b = 0; b < grid && b < 160; ++b) { const long long v = h[(TRACE_STEPS + b) * 8]; if (v > 0 && (t0 < 0 || v < t0)) t0 = v; }
+    if (t0 > 0) {
+        fprintf(stderr, "  step 8 per block [ns after first barrier pass]: pass / mma_committed / epi_wake / inbox / stored / published\n");
+        for (int b = 0; b < grid && b < 160; ++b) {
+            const long long* r = h + (TRACE_STEPS + b) * 8;
+            fprintf(stderr, "   blk %3d: %6lld %6lld %6lld %6lld %6lld %6lld\n", b, r[0] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0, r[7] - t0);
+        }
+    }
+}
+
+static int n_groups(int B) { return (B + NG - 1) / NG; }
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int check_shape(const char* who, int Tp, int B, int H, int D, int cs, int u) {
+    if (!(Tp > 0 && B > 0 && H > 0 && (D == 1 || D == 2))) { set_error("%s: bad sizes Tp=%d B=%d H=%d D=%d", who, Tp, B, H, D); return NSD_ERR_INVALID; }
+    if (H % 64 != 0 || H > 1024) { set_error("%s: hidden size %d must be a multiple of 64 and at most 1024 on the tensor-core path", who, H); return NSD_ERR_INVALID; }
+    const int grid = D * cdiv(H, cs * u) * cs;
+    if (grid > sm_count()) { set_error("%s: hidden size %d x %d directions needs %d co-resident CTAs", who, H, D, grid); return NSD_ERR_INVALID; }
+    return NSD_OK;
+}
+
+}  // namespace rts
+}  // namespace nsd
+
+extern "C" {
+
+size_t nsd_gru_tc_workspace(int B, int H, int D) {
+    (void)H;
+    return 256 + (size_t)D * nsd::rts::n_groups(B) * nsd::rts::CNT_STRIDE * sizeof(unsigned int);
+}
+
+int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
+                     int reverse0, float* hseq, void* hseq_bf16, int ldh, float* r, float* z, float* n, float* hn,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace nsd;
+    using namespace nsd::rts;
+    constexpr int CS = 4, U = 16;
+    int rc = check_shape("gru_fwd_bf16", Tp, B, H, D, CS, U);
+    if (rc) return rc;
+    NSD_CHECK_ARG((r && z && n && hn) || (!r && !z && !n && !hn), "gru_fwd_bf16: save pointers must be all set or all NULL");
+    NSD_CHECK_ARG((ldgi % 4) == 0 && (ldh % 8) == 0, "gru_fwd_bf16: ldgi must be a multiple of 4 and ldh of 8");
+    if (workspace_bytes < nsd_gru_tc_workspace(B, H, D)) { set_error("gru_fwd_bf16: workspace too small"); return NSD_ERR_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NSD_CUDA(cudaMemsetAsync(workspace, 0, nsd_gru_tc_workspace(B, H, D), s));
+    CUtensorMap tmH;
+    rc = make_bf16_map(&tmH, hseq_bf16, (long long)Tp * B, D * H, ldh, NG);
+    if (rc) return rc;
+    FwdParams p;
+    long long* tr = trace_begin();
+    const int nper = cdiv(H, CS * U) * CS;
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, round_up(cdiv(H, CS), UMMA_K), reinterpret_cast<unsigned int*>(workspace), tr};
+    p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
+    p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
+    p.r = r; p.z = z; p.n = n; p.hn = hn;
+    const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
+    rc = launch_cluster_coop(gru_fwd_ts_kernel, D * nper, CS, smem, tmH, p, s);
+    trace_end("gru_fwd_bf16", tr, s, D * nper);
+    return rc;
+}
+
+int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, const float* r, const float* z,
+                     const float* n, const float* hn, const void* w_hhT_bf16, int Tp, int B, int H, int D, int reverse0,
+                     void* dgi_bf16, void* dgh_bf16, int ldg, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace nsd;
+    using namespace nsd::rts;
+    constexpr int CS = 4, U = 32;
+    int rc = check_shape("gru_bwd_bf16", Tp, B, H, D, CS, U);
+    if (rc) return rc;
+    NSD_CHECK_ARG((lddh % 4) == 0 && (ldh % 4) == 0 && (ldg % 8) == 0, "gru_bwd_bf16: leading dimensions must be multiples of 4 (f32) / 8 (bf16)");
+    if (workspace_bytes < nsd_gru_tc_workspace(B, H, D)) { set_error("gru_bwd_bf16: workspace too small"); return NSD_ERR_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NSD_CUDA(cudaMemsetAsync(workspace, 0, nsd_gru_tc_workspace(B, H, D), s));
+    CUtensorMap tmG;
+    rc = make_bf16_map(&tmG, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG);
+    if (rc) return rc;
+    BwdParams p;
+    long long* tr = trace_begin();
+    const int nper = cdiv(H, CS * U) * CS;
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, round_up(cdiv(3 * H, CS), UMMA_K), reinterpret_cast<unsigned int*>(workspace), tr};
+    p.wT = reinterpret_cast<const __nv_bfloat16*>(w_hhT_bf16);
+    p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
+    p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
+    const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * U * NG * 2, U * NG * 4);
+    rc = launch_cluster_coop(gru_bwd_ts_kernel, D * nper, CS, smem, tmG, p, s);
+    trace_end("gru_bwd_bf16", tr, s, D * nper);
+    return rc;
+}
+
+}  // extern "C"
