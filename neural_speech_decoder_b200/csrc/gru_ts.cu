@@ -85,6 +85,14 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
         }
     }
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void red_release_add(unsigned int* p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void wg_bar_sync(int gg) { asm volatile("bar.sync %0, %1;" ::"r"(1 + gg), "n"(WG_THREADS) : "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]: A = stationary weights, lane = row, two bf16 of consecutive k per 32-bit column
@@ -105,17 +113,28 @@ struct Common {
     int nper;                               // CTAs per direction
     int G;                                  // batch groups of NG rows
     int ktot, kper;                         // reduction length (H forward, 3H BPTT) and its share per CTA (multiple of 16)
-    unsigned int* counters;                 // [D][G] step counters, CNT_STRIDE apart
+    int cs, upz, nzone;                         // units per zone (= per cluster) and zones per direction
+    unsigned int* counters;                 // [D][G][nzone] step counters, CNT_STRIDE apart: CS arrivals per step
     long long* trace;                       // debug (NSD_GRU_TRACE=1)
 };
-__device__ __forceinline__ void stamp(const Common& c, int s, int ev) {
+// Debug stamps go to shared memory (a global store here would sit in front of the next fence) and are dumped at exit.
+__device__ __forceinline__ void stamp(const Common& c, long long* tsm, int s, int ev) {
     if (c.trace == nullptr) return;
-    if (blockIdx.x == 0 && s < TRACE_STEPS) c.trace[s * 8 + ev] = clock64();
+    if (blockIdx.x == 0 && s < TRACE_STEPS) tsm[s * 8 + ev] = clock64();
     if (s == 8) {                           // every block, one step, global nanosecond timer: skew across CTAs
         unsigned long long g;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-        c.trace[TRACE_STEPS * 8 + blockIdx.x * 8 + ev] = (long long)g;
+        tsm[TRACE_STEPS * 8 + ev] = (long long)g;
     }
+}
+__device__ __forceinline__ void trace_dump(const Common& c, const long long* tsm) {      // after a __syncthreads
+    if (c.trace == nullptr) return;
+    for (int i = threadIdx.x; i < 8; i += blockDim.x) c.trace[TRACE_STEPS * 8 + blockIdx.x * 8 + i] = tsm[TRACE_STEPS * 8 + i];
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < TRACE_STEPS * 8; i += blockDim.x) c.trace[i] = tsm[i];
+}
+__device__ __forceinline__ unsigned int* zone_counter(const Common& c, int d, int g, int zone) {
+    return c.counters + (size_t)((d * c.G + g) * c.nzone + zone) * CNT_STRIDE;
 }
 
 // Exchange rows are [gate][unit 0..UU-1][batch 0..31]; the batch index is rotated per unit so that both the row-wise
@@ -129,6 +148,7 @@ struct Smem {
     uint8_t* b; uint8_t* inbox; uint8_t* outbox; float* self;
     uint64_t* full; uint64_t* tmem_full; uint64_t* inbox_bar;     // [2] each
     uint32_t* tmem_slot;
+    long long* trace;
 };
 __device__ __forceinline__ Smem carve(uint8_t* raw, int nbox_max, int msgs_bytes, int self_bytes) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -140,10 +160,11 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int nbox_max, int msgs_bytes
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.self) + 2 * self_bytes);
     s.full = bars; s.tmem_full = bars + 2; s.inbox_bar = bars + 4;
     s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    s.trace = reinterpret_cast<long long*>(bars + 8);
     return s;
 }
 static size_t smem_bytes(int nbox_max, int msgs_bytes, int self_bytes) {
-    return (size_t)2 * nbox_max * BOX_BYTES + 4 * (size_t)msgs_bytes + 2 * (size_t)self_bytes + 8 * 8 + 1024 + 64;
+    return (size_t)2 * nbox_max * BOX_BYTES + 4 * (size_t)msgs_bytes + 2 * (size_t)self_bytes + 8 * 8 + (TRACE_STEPS + 1) * 64 + 1024 + 64;
 }
 
 __device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane) {
@@ -162,9 +183,10 @@ __device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane) {
     tcgen05_fence_after();
     return *sm.tmem_slot;
 }
-__device__ __forceinline__ void teardown(int warp, uint32_t tmem_base) {
+__device__ __forceinline__ void teardown(int warp, uint32_t tmem_base, const Common& c, const Smem& sm) {
     tcgen05_fence_before();
     __syncthreads();
+    trace_dump(c, sm.trace);
     __syncwarp();
     cluster_sync_all();                 // nobody leaves while a peer may still push into its shared memory
     if (warp == 2) {
@@ -197,10 +219,20 @@ __device__ __forceinline__ void load_a_row(uint32_t taddr_row, const __nv_bfloat
 // MMAs and its epilogue for the previous use of the same buffers are finished.
 template <int NT>
 __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, int warp, int lane, uint32_t tmem_base,
-                                              const Common& c, int d, int k_lo, int nslab, int nbox, int nbox_max, int b_col0, bool bptt) {
+                                              const Common& c, int d, int my_zone, int k_lo, int k_hi, int nslab, int nbox, int nbox_max,
+                                              int b_col0, bool bptt) {
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int kc = c.kper / 2;
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+        // Lane i < nbox fetches box i of this CTA's K share: it waits for the zone(s) that produce those columns (a 64-wide
+        // box touches at most two).  Lane 31 waits for this CTA's own cluster: once it has published (s-1, g), my MMAs and
+        // epilogue of (s-1, g) are finished and my peers have drained their inboxes, so every buffer of parity gg is free.
+        int z0 = my_zone, z1 = my_zone;
+        if (lane < nbox) {
+            const int c0 = k_lo + lane * BK, c1 = min(c0 + BK, k_hi) - 1;
+            z0 = (c0 % c.H) / c.upz; z1 = (c1 % c.H) / c.upz;
+        }
+        const bool poller = lane < nbox || lane == 31;
         for (int g0 = 0; g0 < c.G; g0 += 2) {
             for (int s = 1; s < c.Tp; ++s) {
                 int t_src;
@@ -208,21 +240,28 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                 else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
                 for (int gg = 0; gg < 2 && g0 + gg < c.G; ++gg) {
                     const int g = g0 + gg;
-                    grid_wait(c.counters + (d * c.G + g) * CNT_STRIDE, (unsigned int)(s * c.nper));
-                    if (g == 0) stamp(c, s, 0);
-                    if (nbox > 0) {
-                        fence_proxy_async();
-                        mbar_expect_tx(&sm.full[gg], (uint32_t)(nbox * BOX_BYTES));
-                        for (int i = 0; i < nbox; ++i)
-                            tma_load_2d(tmB, &sm.full[gg], sm.b + (size_t)(gg * nbox_max + i) * BOX_BYTES, b_col0 + k_lo + i * BK, t_src * c.B + g * NG);
-                    } else {
+                    const unsigned int want = (unsigned int)(s * c.cs);
+                    if (poller) {
+                        grid_wait(zone_counter(c, d, g, z0), want);
+                        if (z1 != z0) grid_wait(zone_counter(c, d, g, z1), want);
+                    }
+                    __syncwarp();
+                    if (lane == 0 && nbox > 0) mbar_expect_tx(&sm.full[gg], (uint32_t)(nbox * BOX_BYTES));
+                    __syncwarp();
+                    if (lane == 0 && g == 0) stamp(c, sm.trace, s, 0);
+                    if (lane < nbox) {
+                        asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy writes (acquired above) -> TMA reads
+                        tma_load_2d(tmB, &sm.full[gg], sm.b + (size_t)(gg * nbox_max + lane) * BOX_BYTES, b_col0 + k_lo + lane * BK, t_src * c.B + g * NG);
+                    } else if (lane == 0) {
                         mbar_arrive(&sm.full[gg]);
                     }
-                    if (g == 0) stamp(c, s, 1);
+                    if (lane == 0 && g == 0) stamp(c, sm.trace, s, 1);
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
+        // The whole warp walks the items; one elected lane issues the MMAs (the compiler then keeps the operands in
+        // uniform registers instead of emitting a per-instruction R2UR waterfall, which made the issue rate the bound).
         constexpr uint32_t idesc = make_idesc_bf16(128, NG);
         uint32_t n[2] = {0u, 0u};
         for (int g0 = 0; g0 < c.G; g0 += 2) {
@@ -230,23 +269,30 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                 for (int gg = 0; gg < 2 && g0 + gg < c.G; ++gg) {
                     mbar_wait(&sm.full[gg], n[gg] & 1);
                     ++n[gg];
-                    if (g0 + gg == 0) stamp(c, s, 2);
-                    if (nslab > 0) {
-                        tcgen05_fence_after();
+                    if (lane == 0 && g0 + gg == 0) stamp(c, sm.trace, s, 2);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        if (nslab > 0) {
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) {
-                            const uint32_t dcol = tmem_base + (uint32_t)((gg * NT + t) * NG);
-                            const uint32_t acol = tmem_base + (uint32_t)(A_COL0 + t * kc);
-                            for (int sl = 0; sl < nslab; ++sl) {
-                                const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.b + (size_t)(gg * nbox_max + (sl >> 2)) * BOX_BYTES)) + (uint64_t)(2 * (sl & 3));
-                                umma_ts_bf16(dcol, acol + (uint32_t)(sl * 8), bdesc, idesc, sl != 0);
+                            for (int t = 0; t < NT; ++t) {
+                                const uint32_t dcol = tmem_base + (uint32_t)((gg * NT + t) * NG);
+                                uint32_t acol = tmem_base + (uint32_t)(A_COL0 + t * kc);
+                                uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.b + (size_t)(gg * nbox_max) * BOX_BYTES));
+                                for (int sl = 0; sl < nslab; sl += 4, acol += 32u, bdesc += (uint64_t)(BOX_BYTES >> 4)) {   // one box = 4 slabs
+                                    const int ns = nslab - sl;
+                                    umma_ts_bf16(dcol, acol, bdesc, idesc, sl != 0);
+                                    if (ns > 1) umma_ts_bf16(dcol, acol + 8u, bdesc + 2u, idesc, 1u);
+                                    if (ns > 2) umma_ts_bf16(dcol, acol + 16u, bdesc + 4u, idesc, 1u);
+                                    if (ns > 3) umma_ts_bf16(dcol, acol + 24u, bdesc + 6u, idesc, 1u);
+                                }
                             }
+                            umma_commit(&sm.tmem_full[gg]);
+                        } else {
+                            mbar_arrive(&sm.tmem_full[gg]);
                         }
-                        umma_commit(&sm.tmem_full[gg]);
-                    } else {
-                        mbar_arrive(&sm.tmem_full[gg]);
                     }
-                    if (g0 + gg == 0) stamp(c, s, 3);
+                    __syncwarp();
+                    if (lane == 0 && g0 + gg == 0) stamp(c, sm.trace, s, 3);
                 }
             }
         }
@@ -346,14 +392,17 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
     const Common& c = p.c;
     const int H = c.H, B = c.B;
     const int me = (int)cluster_rank();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = blockIdx.x / c.nper;
-    const int uc0 = ((blockIdx.x - d * c.nper) / CS) * (CS * U);        // first unit of the cluster
+    const int my_zone = (blockIdx.x - d * c.nper) / CS;
+    const int uc0 = my_zone * (CS * U);                                  // first unit of the cluster
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
     const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK, nbox_max = (c.kper + BK - 1) / BK;
     const int kc = c.kper / 2;
     const Smem sm = carve(smem_raw, nbox_max, MSGS, SELF);
+    if (c.trace != nullptr)
+        for (int i = threadIdx.x; i < (TRACE_STEPS + 1) * 8; i += blockDim.x) sm.trace[i] = 0;
     const uint32_t tmem_base = setup(sm, warp, lane);
 
     if (warp >= 4) {
@@ -368,7 +417,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT>(sm, &tmH, warp, lane, tmem_base, c, d, k_lo, nslab, nbox, nbox_max, d * H, false);
+        control_warps<NT>(sm, &tmH, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * H, false);
     } else {
         // ------------------------------------------------------------ epilogue warpgroup gg: batch groups of parity gg
         const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
@@ -409,7 +458,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
                     if (te == 0) mbar_expect_tx(&sm.inbox_bar[gg], (uint32_t)MSGS);
                     mbar_wait(&sm.tmem_full[gg], it & 1);
                     tcgen05_fence_after();
-                    if (te == 0 && grp == 0) stamp(c, s, 4);
+                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 4);
                     if (w4 < 3) {
 #pragma unroll
                         for (int t2 = 0; t2 < NT; ++t2)
@@ -421,7 +470,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
                     wg_bar_sync(gg);
                     if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[gg], me, te);
                     mbar_wait_cluster(&sm.inbox_bar[gg], it & 1);
-                    if (te == 0 && grp == 0) stamp(c, s, 5);
+                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 5);
 #pragma unroll
                     for (int g = 0; g < 3; ++g) gather<CS, NGATE, U>(self, inbox, g, 4 * uo4, bl, acc[g]);
                     ++it;
@@ -439,12 +488,11 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
                     // the bf16 state is what the other CTAs wait for: store it first, publish, then write the rest
                     st4_bf16(p.hseq_bf + m * p.ldh + d * H + ub, k_h);
                 }
-                if (te == 0 && grp == 0) stamp(c, s, 6);
+                if (te == 0 && grp == 0) stamp(c, sm.trace, s, 6);
                 wg_bar_sync(gg);                             // (the consumer fences generic->async proxy after its acquire)
                 if (te == 0) {
-                    __threadfence();
-                    atomicAdd(c.counters + (d * c.G + grp) * CNT_STRIDE, 1u);
-                    if (grp == 0) stamp(c, s, 7);
+                    red_release_add(zone_counter(c, d, grp, my_zone));
+                    if (grp == 0) stamp(c, sm.trace, s, 7);
                 }
                 if (row_ok) {                                // off the critical path: nobody else reads these during the launch
                     st4(p.hseq + m * p.ldh + d * H + ub, k_h);
@@ -456,7 +504,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
             }
         }
     }
-    teardown(warp, tmem_base);
+    teardown(warp, tmem_base, c, sm);
 }
 
 // =============================================================================================== BPTT
@@ -477,14 +525,17 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     const Common& c = p.c;
     const int H = c.H, B = c.B;
     const int me = (int)cluster_rank();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = blockIdx.x / c.nper;
-    const int uc0 = ((blockIdx.x - d * c.nper) / CS) * (CS * U);
+    const int my_zone = (blockIdx.x - d * c.nper) / CS;
+    const int uc0 = my_zone * (CS * U);
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
     const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK, nbox_max = (c.kper + BK - 1) / BK;
     const int kc = c.kper / 2;
     const Smem sm = carve(smem_raw, nbox_max, MSGS, SELF);
+    if (c.trace != nullptr)
+        for (int i = threadIdx.x; i < (TRACE_STEPS + 1) * 8; i += blockDim.x) sm.trace[i] = 0;
     const uint32_t tmem_base = setup(sm, warp, lane);
 
     if (warp >= 4) {
@@ -500,7 +551,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT>(sm, &tmG, warp, lane, tmem_base, c, d, k_lo, nslab, nbox, nbox_max, d * 3 * H, true);
+        control_warps<NT>(sm, &tmG, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * 3 * H, true);
     } else {
         const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
         const int bl = te >> 2, uo4 = te & 3;
@@ -544,14 +595,14 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
                     if (te == 0) mbar_expect_tx(&sm.inbox_bar[gg], (uint32_t)MSGS);
                     mbar_wait(&sm.tmem_full[gg], it & 1);
                     tcgen05_fence_after();
-                    if (te == 0 && grp == 0) stamp(c, s, 4);
+                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 4);
                     stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(gg * NT * NG), nslab > 0, 0, w4 * 32 + lane, me, self, outbox);
                     tcgen05_fence_before();
                     fence_proxy_async_smem();
                     wg_bar_sync(gg);
                     if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[gg], me, te);
                     mbar_wait_cluster(&sm.inbox_bar[gg], it & 1);
-                    if (te == 0 && grp == 0) stamp(c, s, 5);
+                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 5);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) gather<CS, NGATE, U>(self, inbox, 0, 16 * q + 4 * uo4, bl, acc[q]);
                     ++it;
@@ -577,12 +628,11 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
                         st4_bf16(gh_row, drt[q]); st4_bf16(gh_row + H, dzt[q]); st4_bf16(gh_row + 2 * H, dgn);   // what the other CTAs wait for
                     }
                 }
-                if (te == 0 && grp == 0) stamp(c, s, 6);
+                if (te == 0 && grp == 0) stamp(c, sm.trace, s, 6);
                 wg_bar_sync(gg);                             // (the consumer fences generic->async proxy after its acquire)
                 if (te == 0) {
-                    __threadfence();
-                    atomicAdd(c.counters + (d * c.G + grp) * CNT_STRIDE, 1u);
-                    if (grp == 0) stamp(c, s, 7);
+                    red_release_add(zone_counter(c, d, grp, my_zone));
+                    if (grp == 0) stamp(c, sm.trace, s, 7);
                 }
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {               // off the critical path
@@ -595,7 +645,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
             }
         }
     }
-    teardown(warp, tmem_base);
+    teardown(warp, tmem_base, c, sm);
 }
 
 // ---------------------------------------------------------------- host side
@@ -668,8 +718,7 @@ static int check_shape(const char* who, int Tp, int B, int H, int D, int cs, int
 extern "C" {
 
 size_t nsd_gru_tc_workspace(int B, int H, int D) {
-    (void)H;
-    return 256 + (size_t)D * nsd::rts::n_groups(B) * nsd::rts::CNT_STRIDE * sizeof(unsigned int);
+    return 256 + (size_t)D * nsd::rts::n_groups(B) * nsd::cdiv(H, 64) * nsd::rts::CNT_STRIDE * sizeof(unsigned int);
 }
 
 int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
@@ -691,7 +740,7 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     FwdParams p;
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, round_up(cdiv(H, CS), UMMA_K), reinterpret_cast<unsigned int*>(workspace), tr};
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, round_up(cdiv(H, CS), UMMA_K), CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
     p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
@@ -719,7 +768,7 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     BwdParams p;
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, round_up(cdiv(3 * H, CS), UMMA_K), reinterpret_cast<unsigned int*>(workspace), tr};
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, round_up(cdiv(3 * H, CS), UMMA_K), CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
     p.wT = reinterpret_cast<const __nv_bfloat16*>(w_hhT_bf16);
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
