@@ -120,15 +120,21 @@ size_t nsd_gru_bwd_workspace(int B, int H);
  * t = T'-1..0).  w_hh_bf16 is the bf16 copy of [weight_hh_l*, weight_hh_l*_reverse] stacked to [D*3H, H];
  * b_hh is [D*3H]; gi is [T'*B, ldgi] with direction d at column d*3H; hseq (f32) and hseq_bf16 are [T'*B, ldh]
  * with direction d at column d*H (the bf16 copy is what the CTAs exchange between steps and the next layer's GEMM
- * operand); r,z,n,hn are [D][T'*B][H] (all NULL to skip).  Requires H % 64 == 0.  workspace: nsd_gru_tc_workspace. */
+ * operand); r,z,n,hn are [D][T'*B][H] (all NULL to skip).  Requires H % 64 == 0.  workspace: nsd_gru_tc_workspace.
+ * Fused inter-layer dropout (model.py:55): if hdrop_bf16 != NULL it receives nsd_dropout(hseq_bf16, p_drop, seed)
+ * (same mask, same rounding) as a second [T'*B, ldh] bf16 tensor -- the next layer's input in train mode. */
 int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
                      int reverse0, float* hseq, void* hseq_bf16, int ldh, float* r, float* z, float* n, float* hn,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* hdrop_bf16, float p_drop, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT of the above.  w_hhT_bf16 is the bf16 TRANSPOSE of each direction's W_hh stacked to [D*H, 3H].  Writes
- * dgi_bf16 = [dr~,dz~,dn~] and dgh_bf16 = [dr~,dz~,dn~*r], both [T'*B, ldg] bf16 with direction d at column d*3H. */
+ * dgi_bf16 = [dr~,dz~,dn~] and dgh_bf16 = [dr~,dz~,dn~*r], both [T'*B, ldg] bf16 with direction d at column d*3H.
+ * p_drop > 0: dhseq is the gradient w.r.t. the DROPPED output (mask of nsd_dropout(., p_drop, seed) over the
+ * contiguous [T'*B, lddh] tensor) and is masked/scaled on load.  db_ih/db_hh (both or neither; [D*3H] f32, overwritten):
+ * the bias gradients = column sums of dgi / dgh over all T'*B rows, accumulated in fp32 before the bf16 rounding. */
 int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, const float* r, const float* z,
                      const float* n, const float* hn, const void* w_hhT_bf16, int Tp, int B, int H, int D, int reverse0,
-                     void* dgi_bf16, void* dgh_bf16, int ldg, void* workspace, size_t workspace_bytes, void* stream);
+                     void* dgi_bf16, void* dgh_bf16, int ldg, float p_drop, uint64_t seed, float* db_ih, float* db_hh,
+                     void* workspace, size_t workspace_bytes, void* stream);
 size_t nsd_gru_tc_workspace(int B, int H, int D);
 
 /* inter-layer dropout (nn.GRU dropout=p, train mode, model.py:55): out = x * mask / (1-p),

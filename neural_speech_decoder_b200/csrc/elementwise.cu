@@ -3,27 +3,13 @@
 
 namespace nsd {
 
-// Philox4x32-10 counter-based generator: 4 uniform 32-bit words per (key, counter).
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += W0; key.y += W1;
-    }
-    return ctr;
-}
-
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, size_t n, float p, float inv_keep, uint64_t seed) {
     // one Philox call covers 4 consecutive elements; the mask depends only on (seed, element index)
     const size_t nq = (n + 3) / 4;
-    const uint32_t thresh = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f);
+    const uint32_t thresh = dropout_threshold(p);
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u),
-                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const uint4 r = dropout_bits(q, seed);
         const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

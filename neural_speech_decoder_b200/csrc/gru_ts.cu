@@ -149,6 +149,7 @@ struct Smem {
     uint64_t* full; uint64_t* tmem_full; uint64_t* inbox_bar;     // [2] each
     uint32_t* tmem_slot;
     long long* trace;
+    float* bsum;                                                   // BPTT: [2 warpgroups][32 values][128 threads] bias-gradient partial sums
 };
 __device__ __forceinline__ Smem carve(uint8_t* raw, int nbox_max, int msgs_bytes, int self_bytes) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -161,10 +162,11 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int nbox_max, int msgs_bytes
     s.full = bars; s.tmem_full = bars + 2; s.inbox_bar = bars + 4;
     s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
     s.trace = reinterpret_cast<long long*>(bars + 8);
+    s.bsum = reinterpret_cast<float*>(s.trace + (TRACE_STEPS + 1) * 8);
     return s;
 }
-static size_t smem_bytes(int nbox_max, int msgs_bytes, int self_bytes) {
-    return (size_t)2 * nbox_max * BOX_BYTES + 4 * (size_t)msgs_bytes + 2 * (size_t)self_bytes + 8 * 8 + (TRACE_STEPS + 1) * 64 + 1024 + 64;
+static size_t smem_bytes(int nbox_max, int msgs_bytes, int self_bytes, size_t extra = 0) {
+    return extra + (size_t)2 * nbox_max * BOX_BYTES + 4 * (size_t)msgs_bytes + 2 * (size_t)self_bytes + 8 * 8 + (TRACE_STEPS + 1) * 64 + 1024 + 64;
 }
 
 __device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane) {
@@ -382,6 +384,7 @@ struct FwdParams {
     const float* b_hh;                    // [D*3H]
     float* hseq; __nv_bfloat16* hseq_bf; int ldh;    // [Tp*B, D*H]; the bf16 copy is what the other CTAs TMA-load
     float* r; float* z; float* n; float* hn;         // [D][Tp*B][H] or null
+    __nv_bfloat16* hdrop; uint32_t drop_thresh; float inv_keep; uint64_t seed;   // fused inter-layer dropout output (or null)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -500,6 +503,16 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
                         const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
                         st4(p.r + o, rr); st4(p.z + o, zz); st4(p.n + o, nn); st4(p.hn + o, gn);
                     }
+                    if (p.hdrop) {                           // same mask and rounding as nsd_dropout on the bf16 [Tp*B, ldh] tensor
+                        const size_t e = m * p.ldh + d * H + ub;
+                        const uint4 bits = dropout_bits(e >> 2, p.seed);
+                        const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
+                        float o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            o[i] = bw[i] >= p.drop_thresh ? __bfloat162float(__float2bfloat16_rn(k_h[i])) * p.inv_keep : 0.f;
+                        st4_bf16(p.hdrop + e, o);
+                    }
                 }
             }
         }
@@ -515,6 +528,8 @@ struct BwdParams {
     const float* hseq; int ldh;           // forward hidden states (f32)
     const float* r; const float* z; const float* n; const float* hn;   // [D][Tp*B][H]
     __nv_bfloat16* dgi; __nv_bfloat16* dgh; int ldg;    // [Tp*B, D*3H]: [dr~,dz~,dn~] and [dr~,dz~,dn~*r]
+    uint32_t drop_thresh; float inv_keep; uint64_t seed;   // dropout mask of this layer's output, applied to dhseq (thresh 0 = none)
+    float* db_ih; float* db_hh;                          // [D*3H] column sums of dgi / dgh over all rows (or null), pre-zeroed
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -559,6 +574,9 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
         uint8_t* inbox = sm.inbox + gg * MSGS;
         uint8_t* outbox = sm.outbox + gg * MSGS;
         float* self = sm.self + gg * (SELF / 4);
+        float* bsum = sm.bsum + (size_t)gg * 16 * NP * WG_THREADS + te;
+        if (p.db_ih)
+            for (int v = 0; v < 16 * NP; ++v) bsum[v * WG_THREADS] = 0.f;
         uint32_t it = 0;
         for (int g0 = 0; g0 + gg < c.G; g0 += 2) {
             const int grp = g0 + gg;
@@ -582,6 +600,12 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
                     if (b < B && ub < H) {                   // H % 64 == 0: a pass's 16 units are all inside or all outside
                         const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
                         ld4g(p.dhseq + m * p.lddh + d * H + ub, dh[q]);
+                        if (p.drop_thresh != 0u) {           // gradient through this layer's output dropout (mask of nsd_dropout)
+                            const uint4 bits = dropout_bits((m * p.lddh + d * H + ub) >> 2, p.seed);
+                            const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dh[q][i] = bw[i] >= p.drop_thresh ? dh[q][i] * p.inv_keep : 0.f;
+                        }
                         ld4g(p.r + o, rr[q]); ld4g(p.z + o, zz[q]); ld4g(p.n + o, nn[q]); ld4g(p.hn + o, gn[q]);
                         if (has_prev) ld4g(p.hseq + ((size_t)tprev * B + b) * p.ldh + d * H + ub, hp[q]);
                     }
@@ -640,8 +664,31 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
                     if (b < B && ub < H) {
                         __nv_bfloat16* gi_row = p.dgi + m * p.ldg + d * 3 * H + ub;
                         st4_bf16(gi_row, drt[q]); st4_bf16(gi_row + H, dzt[q]); st4_bf16(gi_row + 2 * H, dnt[q]);
+                        if (p.db_ih) {                       // bias gradients: fp32 sums over (t, b) of dgi and dgh, this thread's cells
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                bsum[((0 * NP + q) * 4 + i) * WG_THREADS] += drt[q][i];
+                                bsum[((1 * NP + q) * 4 + i) * WG_THREADS] += dzt[q][i];
+                                bsum[((2 * NP + q) * 4 + i) * WG_THREADS] += dnt[q][i];
+                                bsum[((3 * NP + q) * 4 + i) * WG_THREADS] += dnt[q][i] * rr[q][i];
+                            }
+                        }
                     }
                 }
+            }
+        }
+        if (p.db_ih) {
+            // fold the 32 batch rows of this warpgroup; the two warpgroups then add into the zero-initialised outputs
+            // (two commutative additions per element: the result does not depend on their order)
+            wg_bar_sync(gg);
+            const int v = te >> 2, gate4 = v / (4 * NP), q = (v >> 2) % NP, i = v & 3;
+            const float* col = sm.bsum + (size_t)gg * 16 * NP * WG_THREADS + (size_t)v * WG_THREADS + uo4;
+            float sum = 0.f;
+            for (int r = 0; r < NG; ++r) sum += col[4 * r];
+            const int unit = uc0 + me * U + 4 * uo4 + 16 * q + i;
+            if (unit < H) {
+                if (gate4 < 3) atomicAdd(p.db_ih + d * 3 * H + gate4 * H + unit, sum);
+                if (gate4 != 2) atomicAdd(p.db_hh + d * 3 * H + min(gate4, 2) * H + unit, sum);
             }
         }
     }
@@ -723,10 +770,11 @@ size_t nsd_gru_tc_workspace(int B, int H, int D) {
 
 int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
                      int reverse0, float* hseq, void* hseq_bf16, int ldh, float* r, float* z, float* n, float* hn,
-                     void* workspace, size_t workspace_bytes, void* stream) {
+                     void* hdrop_bf16, float p_drop, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace nsd;
     using namespace nsd::rts;
     constexpr int CS = 4, U = 16;
+    NSD_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gru_fwd_bf16: p_drop=%f not in [0,1)", (double)p_drop);
     int rc = check_shape("gru_fwd_bf16", Tp, B, H, D, CS, U);
     if (rc) return rc;
     NSD_CHECK_ARG((r && z && n && hn) || (!r && !z && !n && !hn), "gru_fwd_bf16: save pointers must be all set or all NULL");
@@ -744,6 +792,7 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
+    p.hdrop = reinterpret_cast<__nv_bfloat16*>(hdrop_bf16); p.drop_thresh = dropout_threshold(p_drop); p.inv_keep = 1.0f / (1.0f - p_drop); p.seed = seed;
     const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
     rc = launch_cluster_coop(gru_fwd_ts_kernel, D * nper, CS, smem, tmH, p, s);
     trace_end("gru_fwd_bf16", tr, s, D * nper);
@@ -752,10 +801,13 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
 
 int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, const float* r, const float* z,
                      const float* n, const float* hn, const void* w_hhT_bf16, int Tp, int B, int H, int D, int reverse0,
-                     void* dgi_bf16, void* dgh_bf16, int ldg, void* workspace, size_t workspace_bytes, void* stream) {
+                     void* dgi_bf16, void* dgh_bf16, int ldg, float p_drop, uint64_t seed, float* db_ih, float* db_hh,
+                     void* workspace, size_t workspace_bytes, void* stream) {
     using namespace nsd;
     using namespace nsd::rts;
     constexpr int CS = 4, U = 32;
+    NSD_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gru_bwd_bf16: p_drop=%f not in [0,1)", (double)p_drop);
+    NSD_CHECK_ARG((db_ih == nullptr) == (db_hh == nullptr), "gru_bwd_bf16: db_ih and db_hh must both be set or both be NULL");
     int rc = check_shape("gru_bwd_bf16", Tp, B, H, D, CS, U);
     if (rc) return rc;
     NSD_CHECK_ARG((lddh % 4) == 0 && (ldh % 4) == 0 && (ldg % 8) == 0, "gru_bwd_bf16: leading dimensions must be multiples of 4 (f32) / 8 (bf16)");
@@ -772,7 +824,13 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     p.wT = reinterpret_cast<const __nv_bfloat16*>(w_hhT_bf16);
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
-    const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * U * NG * 2, U * NG * 4);
+    p.drop_thresh = p_drop > 0.f ? dropout_threshold(p_drop) : 0u; p.inv_keep = 1.0f / (1.0f - p_drop); p.seed = seed;
+    p.db_ih = db_ih; p.db_hh = db_hh;
+    if (db_ih) {
+        NSD_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)D * 3 * H, s));
+        NSD_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)D * 3 * H, s));
+    }
+    const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
     rc = launch_cluster_coop(gru_bwd_ts_kernel, D * nper, CS, smem, tmG, p, s);
     trace_end("gru_bwd_bf16", tr, s, D * nper);
     return rc;

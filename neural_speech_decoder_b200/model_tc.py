@@ -55,11 +55,13 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
         b_hh = torch.cat([w[3] for w in ws]) if D > 1 else ws[0][3]
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
         ops.gemm(False, True, M, D * 3 * H, in_l, inp, in_l, w_ih_bf, in_l, gi, D * 3 * H, bias=b_ih.contiguous())
-        hseq, hseq_bf, saves = ops.gru_fwd_bf16(gi, w_hh_bf, b_hh.contiguous(), Tp, B, H, D, False, need_grad)
+        if cfg["p_drop"] > 0 and l < L - 1:      # inter-layer dropout fused into the recurrence's epilogue
+            hseq, hseq_bf, saves, nxt = ops.gru_fwd_bf16(gi, w_hh_bf, b_hh.contiguous(), Tp, B, H, D, False, need_grad,
+                                                         cfg["p_drop"], cfg["seed"] + l)
+        else:
+            hseq, hseq_bf, saves = ops.gru_fwd_bf16(gi, w_hh_bf, b_hh.contiguous(), Tp, B, H, D, False, need_grad)
+            nxt = hseq_bf
         del gi
-        nxt = hseq_bf
-        if cfg["p_drop"] > 0 and l < L - 1:
-            nxt = ops.dropout(hseq_bf, cfg["p_drop"], cfg["seed"] + l)
         layers.append((inp, hseq, hseq_bf, saves, w_ih_bf, w_hhT_bf))
         inp = nxt
     C = fc_w.shape[0]
@@ -109,16 +111,14 @@ def decoder_backward_tc(ctx, dlogits):
         inp, hseq, hseq_bf, saves, w_ih_bf, w_hhT_bf = ctx.layers[l]
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
-        if cfg["p_drop"] > 0 and l < L - 1:
-            dh = ops.dropout(dh, cfg["p_drop"], cfg["seed"] + l)
-        dgi, dgh = ops.gru_bwd_bf16(dh, hseq, saves, w_hhT_bf, Tp, B, H, D, False)
         # one flat bucket per layer, laid out so that each GEMM writes its whole (both-direction) block at once
         v_wih, v_whh, v_bih, v_bhh = _flat_views([(D * 3 * H, in_l), (D * 3 * H, H), (D * 3 * H,), (D * 3 * H,)], dev, None,
                                                  zero=(Tp == 1))
+        drop = cfg["p_drop"] if (cfg["p_drop"] > 0 and l < L - 1) else 0.0
+        # BPTT with the output-dropout mask applied on load and the bias gradients (column sums) accumulated in-kernel
+        dgi, dgh = ops.gru_bwd_bf16(dh, hseq, saves, w_hhT_bf, Tp, B, H, D, False, drop, cfg["seed"] + l, v_bih, v_bhh)
         # wgrad W_ih: dW[D*3H, in_l] = dgi^T inp -- reduction over the T'*B rows, both operands M/N-major as stored
         ops.gemm(True, False, D * 3 * H, in_l, M, dgi, D * 3 * H, inp, in_l, v_wih, in_l)
-        ops.colsum(dgi, M, D * 3 * H, D * 3 * H, v_bih)
-        ops.colsum(dgh, M, D * 3 * H, D * 3 * H, v_bhh)
         if Tp > 1:
             for d in range(D):
                 # forward dir: dgh[t] pairs with h[t-1];  reverse dir: dgh[t] pairs with h[t+1]  (row-range views, no copies)

@@ -117,8 +117,8 @@ def gru_bwd_f32(dhseq, lddh, dh_off, hseq, ldh, h_off, saves, w_hh, Tp, B, H, re
          nbytes, stream())
 
 
-def gru_fwd_bf16(gi, w_hh_bf, b_hh, Tp, B, H, D, reverse0, want_saves):
-    """-> (hseq f32 [Tp*B, D*H], hseq bf16, saves (r,z,n,hn) each [D,Tp*B,H] or None)."""
+def gru_fwd_bf16(gi, w_hh_bf, b_hh, Tp, B, H, D, reverse0, want_saves, p_drop: float = 0.0, seed: int = 0):
+    """-> (hseq f32 [Tp*B, D*H], hseq bf16, saves (r,z,n,hn) each [D,Tp*B,H] or None[, dropped bf16 copy if p_drop > 0])."""
     dev = gi.device
     M = Tp * B
     hseq = torch.empty((M, D * H), device=dev, dtype=torch.float32)
@@ -126,13 +126,18 @@ def gru_fwd_bf16(gi, w_hh_bf, b_hh, Tp, B, H, D, reverse0, want_saves):
     sv = tuple(torch.empty((D, M, H), device=dev, dtype=torch.float32) for _ in range(4)) if want_saves else (None,) * 4
     nbytes = _lib.lib().nsd_gru_tc_workspace(B, H, D)
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    hdrop = torch.empty_like(hseq_bf) if p_drop > 0 else None
     call("nsd_gru_fwd_bf16", ptr(gi), gi.stride(0), ptr(w_hh_bf), ptr(b_hh), Tp, B, H, D, int(reverse0), ptr(hseq),
-         ptr(hseq_bf), D * H, ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), ptr(ws), nbytes, stream())
+         ptr(hseq_bf), D * H, ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), ptr(hdrop), float(p_drop), int(seed),
+         ptr(ws), nbytes, stream())
+    if p_drop > 0:
+        return hseq, hseq_bf, (sv if want_saves else None), hdrop
     return hseq, hseq_bf, (sv if want_saves else None)
 
 
-def gru_bwd_bf16(dhseq, hseq, saves, w_hhT_bf, Tp, B, H, D, reverse0):
-    """-> (dgi bf16 [Tp*B, D*3H] = [dr~,dz~,dn~], dgh bf16 = [dr~,dz~,dn~*r])."""
+def gru_bwd_bf16(dhseq, hseq, saves, w_hhT_bf, Tp, B, H, D, reverse0, p_drop: float = 0.0, seed: int = 0, db_ih=None, db_hh=None):
+    """-> (dgi bf16 [Tp*B, D*3H] = [dr~,dz~,dn~], dgh bf16 = [dr~,dz~,dn~*r]).  p_drop > 0 masks dhseq like
+    nsd_dropout(dhseq, p_drop, seed); db_ih / db_hh (f32 [D*3H]) receive the bias gradients."""
     dev = dhseq.device
     M = Tp * B
     dgi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.bfloat16)
@@ -141,7 +146,8 @@ def gru_bwd_bf16(dhseq, hseq, saves, w_hhT_bf, Tp, B, H, D, reverse0):
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     r, z, n, hn = saves
     call("nsd_gru_bwd_bf16", ptr(dhseq), dhseq.stride(0), ptr(hseq), hseq.stride(0), ptr(r), ptr(z), ptr(n), ptr(hn),
-         ptr(w_hhT_bf), Tp, B, H, D, int(reverse0), ptr(dgi), ptr(dgh), D * 3 * H, ptr(ws), nbytes, stream())
+         ptr(w_hhT_bf), Tp, B, H, D, int(reverse0), ptr(dgi), ptr(dgh), D * 3 * H, float(p_drop), int(seed), ptr(db_ih),
+         ptr(db_hh), ptr(ws), nbytes, stream())
     return dgi, dgh
 
 

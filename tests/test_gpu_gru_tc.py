@@ -113,3 +113,39 @@ def test_bf16_model_matches_reference_fixture(name):
         rel = np.linalg.norm(got - rs) / max(np.linalg.norm(rs), 1e-12)
         print(f"   grad {n}: rel L2 err {rel:.3e}")
         assert rel < 0.1, n
+
+
+@pytest.mark.parametrize("B,Tp,H,D", [(64, 5, 1024, 2), (40, 6, 128, 2), (7, 4, 64, 1)])
+def test_gru_tc_fused_dropout_and_bias_sums(B, Tp, H, D):
+    """The fused forms must equal the separate kernels: the dropped copy written by the forward epilogue == nsd_dropout
+    of the bf16 states (bit-exact), the BPTT with the mask applied on load == BPTT of nsd_dropout(dh) (bit-exact), and
+    the in-kernel bias gradients == fp32 column sums of dgi / dgh up to their bf16 rounding."""
+    torch.manual_seed(B + H)
+    M = Tp * B
+    gi = torch.randn(M, D * 3 * H, device=DEV)
+    w = (torch.randn(D * 3 * H, H, device=DEV) / np.sqrt(H)).to(torch.bfloat16)
+    b = torch.randn(D * 3 * H, device=DEV) * 0.1
+    p, seed = 0.4, 1234
+    hseq, hbf, sv, hdrop = ops.gru_fwd_bf16(gi, w, b, Tp, B, H, D, False, True, p, seed)
+    hseq2, hbf2, sv2 = ops.gru_fwd_bf16(gi, w, b, Tp, B, H, D, False, True)
+    assert torch.equal(hseq, hseq2) and torch.equal(hbf, hbf2)
+    assert torch.equal(hdrop, ops.dropout(hbf, p, seed))
+    keep = (hdrop != 0).float().mean().item()
+    assert abs(keep - 0.6) < 0.02
+
+    wT = torch.cat([w[d * 3 * H:(d + 1) * 3 * H].T.contiguous() for d in range(D)], 0)
+    dh = torch.randn(M, D * H, device=DEV)
+    db_ih = torch.full((D * 3 * H,), 7.0, device=DEV)      # must be overwritten, not accumulated into
+    db_hh = torch.full((D * 3 * H,), -3.0, device=DEV)
+    dgi, dgh = ops.gru_bwd_bf16(dh, hseq, sv, wT, Tp, B, H, D, False, p, seed, db_ih, db_hh)
+    dgi_ref, dgh_ref = ops.gru_bwd_bf16(ops.dropout(dh, p, seed), hseq, sv, wT, Tp, B, H, D, False)
+    assert torch.equal(dgi, dgi_ref) and torch.equal(dgh, dgh_ref)
+    for got, mat in ((db_ih, dgi), (db_hh, dgh)):
+        ref = mat.double().sum(0)
+        # each of the M summands carries a bf16 rounding error of at most 2^-9 relative in `mat`, none in `got`
+        tol = mat.double().abs().sum(0) * 2.0 ** -8 + 1e-6
+        assert bool(((got.double() - ref).abs() <= tol).all())
+    # run-to-run determinism of the two-warpgroup accumulation
+    db2_ih, db2_hh = torch.empty_like(db_ih), torch.empty_like(db_hh)
+    ops.gru_bwd_bf16(dh, hseq, sv, wT, Tp, B, H, D, False, p, seed, db2_ih, db2_hh)
+    assert torch.equal(db_ih, db2_ih) and torch.equal(db_hh, db2_hh)
