@@ -177,9 +177,11 @@ size_t nsd_edit_distance_workspace(int B, int max_len);
  * torch.optim.Adam semantics (trainer:163-169, 259): g = grad*grad_scale + weight_decay*p;
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps).
  * params/grads/exp_avg/exp_avg_sq are HOST arrays of n_tensors DEVICE pointers (f32, contiguous),
- * numel a HOST array.  One launch per 48 tensors.                                            */
+ * numel a HOST array.  One launch per 48 tensors.  shadow_bf16 (NULL, or a HOST array whose entries
+ * may be NULL): device pointer of a contiguous bf16 copy of the parameter, rewritten with the
+ * updated value in the same pass (the tensor-core operand copy the next forward reads).       */
 int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
-                  void* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                  void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus

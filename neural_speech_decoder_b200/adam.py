@@ -12,6 +12,11 @@ class FusedAdam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.grad_scale = grad_scale          # data parallel: 1/world_size folds the gradient average in
+        self.shadows = None                   # model_tc.Bf16Shadows: bf16 operand copies refreshed by the update kernel
+
+    def attach_shadows(self, shadows) -> None:
+        """Let the update kernel rewrite the model's bf16 weight copies in the same pass (saves the per-step casts)."""
+        self.shadows = shadows
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -22,6 +27,7 @@ class FusedAdam(torch.optim.Optimizer):
         for group in self.param_groups:
             ps, gs, ms, vs = [], [], [], []
             step = None
+            touched = []
             for p in group["params"]:
                 if p.grad is None:            # the reference's dead inpLayer* parameters never get one
                     continue
@@ -33,6 +39,7 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
+                touched.append(p)
                 step = st["step"] if step is None else step
                 if st["step"] != step:        # parameters that joined later: separate launch group
                     ops.adam_step([p], [p.grad.contiguous()], [st["exp_avg"]], [st["exp_avg_sq"]], group["lr"],
@@ -40,7 +47,15 @@ class FusedAdam(torch.optim.Optimizer):
                     continue
                 ps.append(p); gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
                 ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
+            sh = [self.shadows.slice_for(p) for p in ps] if self.shadows is not None else None
             if ps:
                 ops.adam_step(ps, gs, ms, vs, group["lr"], *group["betas"], group["eps"], group["weight_decay"], step,
-                              self.grad_scale)
+                              self.grad_scale, sh)
+            # the kernels write through raw pointers: tell autograd (and the shadow cache) that the parameters changed
+            if touched:
+                torch.autograd.graph.increment_version(touched)
+            if sh is not None:
+                for p, s_ in zip(ps, sh):
+                    if s_ is not None:
+                        self.shadows.mark_fresh(p)
         return loss

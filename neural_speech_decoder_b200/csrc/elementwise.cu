@@ -29,6 +29,7 @@ constexpr int ADAM_CHUNK = 16384;       // elements per CTA
 struct AdamTable {
     float* p[ADAM_MAX_TENSORS]; const float* g[ADAM_MAX_TENSORS]; float* m[ADAM_MAX_TENSORS]; float* v[ADAM_MAX_TENSORS];
     long long n[ADAM_MAX_TENSORS];
+    __nv_bfloat16* s[ADAM_MAX_TENSORS];     // optional bf16 shadow of the updated parameter (tensor-core operand copy) or null
     int chunk_start[ADAM_MAX_TENSORS + 1];   // first CTA of each tensor
     int count;
 };
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
     const long long end = min(n, base + ADAM_CHUNK);
     float* __restrict__ P = tab.p[ti]; const float* __restrict__ G = tab.g[ti];
     float* __restrict__ M = tab.m[ti]; float* __restrict__ V = tab.v[ti];
-    const bool vec = (((uintptr_t)P | (uintptr_t)G | (uintptr_t)M | (uintptr_t)V) & 15) == 0;
+    __nv_bfloat16* __restrict__ S = tab.s[ti];
+    const bool vec = ((((uintptr_t)P | (uintptr_t)G | (uintptr_t)M | (uintptr_t)V) & 15) | ((uintptr_t)S & 7)) == 0;
     if (vec) {
         const long long e4 = base + ((end - base) & ~3LL);
         for (long long i = base + 4LL * threadIdx.x; i < e4; i += 4LL * blockDim.x) {
@@ -63,10 +65,20 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
             adam_one(p.z, g.z, m.z, v.z, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
             adam_one(p.w, g.w, m.w, v.w, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
             *reinterpret_cast<float4*>(P + i) = p; *reinterpret_cast<float4*>(M + i) = m; *reinterpret_cast<float4*>(V + i) = v;
+            if (S) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+                *reinterpret_cast<uint2*>(S + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+            }
         }
-        for (long long i = e4 + threadIdx.x; i < end; i += blockDim.x) adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+        for (long long i = e4 + threadIdx.x; i < end; i += blockDim.x) {
+            adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            if (S) S[i] = __float2bfloat16_rn(P[i]);
+        }
     } else {
-        for (long long i = base + threadIdx.x; i < end; i += blockDim.x) adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+        for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+            adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            if (S) S[i] = __float2bfloat16_rn(P[i]);
+        }
     }
 }
 
@@ -75,7 +87,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
 extern "C" {
 
 int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
-                  void* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                  void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream) {
     using namespace nsd;
     NSD_CHECK_ARG(n_tensors >= 0 && step >= 1, "adam_step: bad n_tensors=%d step=%d", n_tensors, step);
@@ -90,6 +102,7 @@ int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, 
             tab.p[i] = (float*)params[t0 + i]; tab.g[i] = (const float*)grads[t0 + i];
             tab.m[i] = (float*)exp_avg[t0 + i]; tab.v[i] = (float*)exp_avg_sq[t0 + i];
             tab.n[i] = numel[t0 + i];
+            tab.s[i] = shadow_bf16 ? (__nv_bfloat16*)shadow_bf16[t0 + i] : nullptr;
             tab.chunk_start[i] = chunks;
             chunks += (int)cdivz((size_t)numel[t0 + i], ADAM_CHUNK);
         }

@@ -119,6 +119,8 @@ class GRUDecoder(nn.Module):
         self._step = 0
         self._err_flag: Optional[torch.Tensor] = None
         self.grad_sync = None       # parallel.GradSync when training data-parallel (set by trainer.train_step)
+        from .model_tc import Bf16Shadows
+        self._shadows = Bf16Shadows()   # bf16 operand copies of the weights (bf16 precision only), see FusedAdam.attach_shadows
 
     # ---------------------------------------------------------------- helpers
     def _gru_weights(self) -> List[torch.Tensor]:
@@ -151,7 +153,7 @@ class GRUDecoder(nn.Module):
         cfg = dict(K=self.kernelLen, S=self.strideLen, H=self.hidden_dim, L=self.layer_dim,
                    D=2 if self.bidirectional else 1, n_days=self.nDays, precision=self.precision,
                    p_drop=float(self.dropout) if self.training else 0.0, seed=0, err_flag=self._err_flag,
-                   grad_sync=self.grad_sync)
+                   grad_sync=self.grad_sync, shadows=self._shadows)
         if cfg["p_drop"] > 0:
             self._step += 1
             cfg["seed"] = (int(torch.initial_seed()) * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF

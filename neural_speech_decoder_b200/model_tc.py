@@ -15,6 +15,52 @@ import torch
 from . import ops
 
 
+class Bf16Shadows:
+    """bf16 operand copies of the fp32 master weights, kept across steps.  A copy is valid while the parameter's
+    (data_ptr, autograd version) is the one it was made from; anything that modifies a parameter in place (optimizers,
+    load_state_dict, broadcasts) bumps the version and the copy is re-made by the next forward.  FusedAdam, when attached,
+    rewrites the copies inside its update kernel and marks them fresh, so a training step does no weight casts at all."""
+
+    def __init__(self):
+        self.bufs = {}        # key -> stacked bf16 buffer [D*R, C]
+        self.tags = {}        # (key, d) -> (data_ptr, version) of the fp32 source
+        self.where = {}       # data_ptr of the fp32 source -> (key, d)
+
+    def stacked(self, key, ws):
+        """Up-to-date bf16 copy of the D fp32 matrices ``ws`` ([R, C] each) stacked by rows."""
+        D = len(ws)
+        R, Cn = ws[0].shape
+        buf = self.bufs.get(key)
+        if buf is None or tuple(buf.shape) != (D * R, Cn) or buf.device != ws[0].device:
+            buf = torch.empty((D * R, Cn), device=ws[0].device, dtype=torch.bfloat16)
+            self.bufs[key] = buf
+            for d in range(D):
+                self.tags.pop((key, d), None)
+        for d, w in enumerate(ws):
+            tag = (w.data_ptr(), w._version)
+            if self.tags.get((key, d)) != tag:
+                ops.cast_transpose_into(w.detach(), buf[d * R:(d + 1) * R], None)
+                self.tags[(key, d)] = tag
+                self.where[w.data_ptr()] = (key, d)
+        return buf
+
+    def slice_for(self, p):
+        loc = self.where.get(p.data_ptr())
+        if loc is None:
+            return None
+        key, d = loc
+        buf = self.bufs[key]
+        R = p.shape[0]
+        if buf.shape[1] != p.shape[1] or (d + 1) * R > buf.shape[0]:
+            return None
+        return buf[d * R:(d + 1) * R]
+
+    def mark_fresh(self, p) -> None:
+        loc = self.where.get(p.data_ptr())
+        if loc is not None:
+            self.tags[loc] = (p.data_ptr(), p._version)
+
+
 def _bf16_stacks(ws, want_t: bool, t_side_by_side: bool):
     """One pass over each direction's fp32 weight [R, C]: the bf16 copies stacked by rows [D*R, C] and, if asked, the
     bf16 transposes -- side by side [C, D*R] (W_ih^T for dgrad) or stacked by rows [D*C, R] (W_hh^T for BPTT)."""
@@ -49,8 +95,19 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
     for l in range(L):
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
-        w_ih_bf, _ = _bf16_stacks([w[0] for w in ws], False, True)                     # [D*3H, in_l]
-        w_hh_bf, w_hhT_bf = _bf16_stacks([w[1] for w in ws], need_grad, False)         # [D*3H, H], [D*H, 3H] (BPTT operand)
+        sh = cfg.get("shadows")
+        if sh is not None:
+            # gru_w holds the Parameters themselves: their version counters tell whether the kept copies are current
+            w_ih_bf = sh.stacked(("ih", l), [gru_w[(l * D + d) * 4] for d in range(D)])          # [D*3H, in_l]
+            w_hh_bf = sh.stacked(("hh", l), [gru_w[(l * D + d) * 4 + 1] for d in range(D)])      # [D*3H, H]
+            w_hhT_bf = None
+            if need_grad:                                                                        # [D*H, 3H] (BPTT operand)
+                w_hhT_bf = torch.empty((D * H, 3 * H), device=dev, dtype=torch.bfloat16)
+                for d in range(D):
+                    ops.cast_transpose_into(w_hh_bf[d * 3 * H:(d + 1) * 3 * H], None, w_hhT_bf[d * H:(d + 1) * H])
+        else:
+            w_ih_bf, _ = _bf16_stacks([w[0] for w in ws], False, True)                     # [D*3H, in_l]
+            w_hh_bf, w_hhT_bf = _bf16_stacks([w[1] for w in ws], need_grad, False)         # [D*3H, H], [D*H, 3H] (BPTT operand)
         b_ih = torch.cat([w[2] for w in ws]) if D > 1 else ws[0][2]
         b_hh = torch.cat([w[3] for w in ws]) if D > 1 else ws[0][3]
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
@@ -66,7 +123,7 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
         inp = nxt
     C = fc_w.shape[0]
     logits_tm = torch.empty((M, C), device=dev, dtype=torch.float32)
-    fc_w_bf = ops.cast_transpose(fc_w.detach(), True, False)[0]
+    fc_w_bf = sh.stacked(("fc", 0), [fc_w]) if cfg.get("shadows") is not None else ops.cast_transpose(fc_w.detach(), True, False)[0]
     ops.gemm(False, True, M, C, D * H, hseq_bf, D * H, fc_w_bf, D * H, logits_tm, C, bias=fc_b.detach().contiguous())
     logits = ops.swap01(logits_tm.view(Tp, B, C))
     if need_grad:

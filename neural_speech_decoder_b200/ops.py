@@ -181,15 +181,21 @@ def log_softmax(x):
     return out
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
-    """torch.optim.Adam (L2-in-gradient, not AdamW) on a list of f32 tensors in as few launches as possible."""
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadows=None):
+    """torch.optim.Adam (L2-in-gradient, not AdamW) on a list of f32 tensors in as few launches as possible.
+    ``shadows``: optional list (entries may be None) of contiguous bf16 tensors rewritten with the updated parameters."""
     import ctypes as C
     n = len(params)
     if n == 0:
         return
     arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
     numel = (C.c_int64 * n)(*[t.numel() for t in params])
-    call("nsd_adam_step", n, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq), numel, float(lr), float(beta1),
+    sh = None
+    if shadows is not None and any(s is not None for s in shadows):
+        for s_, p_ in zip(shadows, params):
+            assert s_ is None or (s_.is_contiguous() and s_.dtype == torch.bfloat16 and s_.numel() == p_.numel())
+        sh = (C.c_void_p * n)(*[None if s_ is None else s_.data_ptr() for s_ in shadows])
+    call("nsd_adam_step", n, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq), numel, sh, float(lr), float(beta1),
          float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), stream())
 
 

@@ -21,6 +21,8 @@ def make_optimizer(model: torch.nn.Module, args: dict):
     """trainer:163-175 (the non-AdamW branch, which the GRU configs use)."""
     opt = FusedAdam(model.parameters(), lr=args["lrStart"], betas=(0.9, 0.999), eps=0.1,
                     weight_decay=args.get("l2_decay", 0.0))
+    if getattr(model, "_shadows", None) is not None:
+        opt.attach_shadows(model._shadows)
     sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=args["lrEnd"] / args["lrStart"],
                                               total_iters=args["nBatch"])
     return opt, sched

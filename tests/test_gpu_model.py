@@ -155,3 +155,60 @@ def test_train_step_reduces_loss_and_eval_batch():
     m.eval()
     loss, dist, tot = nsd.eval_batch(m, *batch)
     assert tot == int(g["y_len"].sum()) and 0 <= dist <= tot + int(g["out_lens"].sum())
+
+
+def test_bf16_weight_shadows_follow_the_parameters():
+    """bf16 mode keeps bf16 operand copies of the weights across steps; FusedAdam rewrites them in its update kernel.
+    Training with the copies maintained by Adam must be bit-identical to training that re-casts every step, and any
+    other in-place change of a parameter (load_state_dict, manual edit) must invalidate the copy."""
+    from neural_speech_decoder_b200 import _lib
+    kw = dict(neural_dim=32, n_classes=10, hidden_dim=64, layer_dim=2, nDays=4, dropout=0.0, strideLen=4, kernelLen=16,
+              gaussianSmoothWidth=2.0, bidirectional=True)
+    X, y, X_len, y_len, day = make_batch(4, 72, n_feat=32, n_days=4, n_classes=10, seed=5, ragged=True, min_tgt=2, max_tgt=6,
+                                         kernel_len=16, stride_len=4)
+    batch = [t.to(DEV) for t in (X, y, X_len, y_len, day)]
+
+    def build_bf16():
+        nsd.set_default_precision("bf16")
+        try:
+            torch.manual_seed(0)
+            mm = nsd.GRUDecoder(device=DEV, **kw)
+        finally:
+            nsd.set_default_precision("fp32")
+        fill_trained_like_(mm, seed=3)
+        return mm.to(DEV)
+
+    runs = []
+    for attach in (True, False):
+        m = build_bf16()
+        m.train()
+        opt, sched = nsd.make_optimizer(m, dict(lrStart=0.02, lrEnd=0.02, nBatch=100, l2_decay=1e-5))
+        if not attach:
+            opt.attach_shadows(None)
+        losses = [nsd.train_step(m, opt, *batch, scheduler=sched).item() for _ in range(4)]
+        runs.append((losses, [p.detach().clone() for p in m.parameters()], m, opt))
+    assert runs[0][0] == runs[1][0]
+    assert all(torch.equal(a, b) for a, b in zip(runs[0][1], runs[1][1]))
+    # attached: a step does no weight casts (only the W_hh^T transposes of the bf16 copies and the dlogits cast)
+    m, opt = runs[0][2], runs[0][3]
+    _lib.profile_begin({"nsd_cast_transpose"})
+    nsd.train_step(m, opt, *batch)
+    with_shadows = sum(n for n, _ in _lib.profile_end().values())
+    m2, opt2 = runs[1][2], runs[1][3]
+    _lib.profile_begin({"nsd_cast_transpose"})
+    nsd.train_step(m2, opt2, *batch)
+    without = sum(n for n, _ in _lib.profile_end().values())
+    L, D = kw["layer_dim"], 2
+    assert without - with_shadows == 2 * L * D + 1                      # W_ih, W_hh per layer-direction and the output layer
+    # an in-place edit outside the optimizer invalidates the copy
+    m.eval()
+    X, day = batch[0], batch[4]
+    before = m.forward(X, day).detach().clone()
+    with torch.no_grad():
+        m.gru_decoder.weight_ih_l0.mul_(0.5)
+    after = m.forward(X, day).detach()
+    assert not torch.equal(before, after)
+    ref = build_bf16()
+    ref.load_state_dict(m.state_dict())
+    ref.eval()
+    assert torch.equal(ref.forward(X, day).detach(), after)
