@@ -62,7 +62,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;         // [ACC_STAGES] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int nk = (K + BK - 1) / BK;
@@ -86,13 +86,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer (one elected lane) =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const TileCoord tc = tile_coord(t, num_m, num_n);
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
+        // Warp-uniform control flow around elect.sync keeps descriptors / coordinates in uniform registers; a
+        // `lane == 0` branch makes the compiler wrap every UTMALDG / UTCHMMA in an R2UR waterfall loop.
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const TileCoord tc = tile_coord(t, num_m, num_n);
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], cfg::STAGE_BYTES);
                     if constexpr (!A_MN) tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, tc.m_blk * BM);
@@ -105,23 +107,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES + i * 8192, tc.n_blk * BN + 64 * i, kb * BK);
                     }
-                    if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one elected lane) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+        // ===================== MMA issuer (whole warp walks the ring, one elected lane issues) =====================
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < nk; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
+                if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
                     const uint64_t adesc = A_MN ? make_mnmajor_sw128_desc(sa, 8192) : make_kmajor_sw128_desc(sa);
                     const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(sa + cfg::A_BYTES, 8192) : make_kmajor_sw128_desc(sa + cfg::A_BYTES);
@@ -131,11 +134,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_bf16(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
                     umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
-                    if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == nk - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
                 }
-                umma_commit(&tmem_full[acc]);                         // accumulator complete -> epilogue
-                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===================== epilogue: TMEM -> registers -> global =====================

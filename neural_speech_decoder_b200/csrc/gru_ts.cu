@@ -85,11 +85,6 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
         }
     }
 }
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void red_release_add(unsigned int* p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
