@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
 
-One "step" = forward -> out_lens -> log-softmax + CTC -> backward -> (gradient all-reduce) -> Adam step on one
+One "step" = noise augmentation (trainer:194-201) -> forward -> out_lens -> log-softmax + CTC -> backward -> (gradient all-reduce) -> Adam step on one
 synthetic batch of the competition shape (256 features, 24 days, 41 classes; B=64 per GPU, T=500), i.e.
 neural_decoder_trainer.py:208-218, 242, 251-260.  Workload = BASELINE.json configs[1]: bidirectional 5x1024
 GRUDecoder, dropout 0.4, batch-sharded data parallel (weak scaling: 64 utterances per GPU).
@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "train utterances/sec (GRUDecoder, B=64, T=500)"
 UNIT = "utterances/s"
+NOISE = dict(white_noise_sd=0.8, constant_offset_sd=0.2)     # scripts/train_model.py:17-18 (whiteNoiseSD, constantOffsetSD)
 MODEL_KW = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, dropout=0.4, strideLen=4,
                 kernelLen=32, gaussianSmoothWidth=2.0)
 
@@ -47,13 +48,15 @@ def parse():
     ap.add_argument("--uni", action="store_true", help="unidirectional GRU (class default) instead of the training default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32")
     return ap.parse_args()
 
 
 def config_dict(a, n_gpus, impl_note=""):
     bi = not a.uni
     return {"workload": f"GRUDecoder {'bi' if bi else 'uni'}directional 5x1024, 256 feats, 24 days, k32/s4, 41 classes, "
-                        f"dropout 0.4; train step fwd+CTC+bwd+Adam; B={a.batch}/GPU T={a.T} (BASELINE configs[1])",
+                        f"dropout 0.4, white noise 0.8 + constant offset 0.2; train step augment+fwd+CTC+bwd+Adam; B={a.batch}/GPU T={a.T} (BASELINE configs[1])",
             "global_batch": a.batch * n_gpus, "T": a.T, "frames": (a.T - 32) // 4 + 1,
             "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
             "l2": "working set (0.54 GB weights + >1 GB activations per step) far exceeds the 126 MB L2; no flush needed"}
@@ -74,11 +77,11 @@ def cpu_port_run(a, sample_b, steps, warmup):
     opt = P.make_adam(m)
     batch = make_batch(sample_b, a.T, seed=1)
     for _ in range(warmup):
-        P.train_step(m, opt, *batch)
+        P.train_step(m, opt, *batch, **NOISE)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        P.train_step(m, opt, *batch)
+        P.train_step(m, opt, *batch, **NOISE)
         times.append(time.perf_counter() - t0)
     return sample_b * len(times) / sum(times), cores, sum(times) / len(times)
 
@@ -196,11 +199,11 @@ def run_ours(a):
     frames = (a.T - 32) // 4 + 1
 
     def step_resident():
-        return nsd.train_step(model, opt, *devb, scheduler=sched, grad_sync=gs)
+        return nsd.train_step(model, opt, *devb, scheduler=sched, grad_sync=gs, **NOISE)
 
     def step_e2e():
         b = [t.to(dev, non_blocking=True) for t in host]
-        return nsd.train_step(model, opt, *b, scheduler=sched, grad_sync=gs).item()
+        return nsd.train_step(model, opt, *b, scheduler=sched, grad_sync=gs, **NOISE).item()
 
     def barrier():
         if world > 1:
@@ -280,9 +283,53 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_infer(a):
+    """BASELINE configs[3]: unidirectional GRUDecoder inference, batch 1 and batch 32, T=500 bins (10 s of 20 ms bins):
+    eval-mode forward -> log-softmax -> greedy CTC decode on the device, host inputs, decoded ids read back.  Secondary
+    lines (not the headline contract): latency per call, per output frame (4 bins) and per 20 ms bin."""
+    import torch
+    import neural_speech_decoder_b200 as nsd
+    from neural_speech_decoder_b200.synthetic import make_batch
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    frames = (a.T - 32) // 4 + 1
+    for precision in ("bf16", "fp32"):
+        nsd.set_default_precision(precision)
+        torch.manual_seed(0)
+        model = nsd.GRUDecoder(device="cuda", bidirectional=False, **{**MODEL_KW, "dropout": 0.0}).to(dev).eval()
+        for B in (1, 32):
+            X, y, X_len, y_len, day = [t.pin_memory() for t in make_batch(B, a.T, seed=2)]
+
+            @torch.no_grad()
+            def call():
+                x, xl, dd = X.to(dev, non_blocking=True), X_len.to(dev, non_blocking=True), day.to(dev, non_blocking=True)
+                logits = model.forward(x, dd)
+                lens = nsd.out_lens(xl, model.kernelLen, model.strideLen)
+                dec, dec_len = nsd.greedy_decode(nsd.ctc.log_softmax_tbc(logits), lens)
+                return dec.cpu(), dec_len.cpu()
+
+            for _ in range(max(a.warmup, 3)):
+                call()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(a.steps):
+                t0 = time.perf_counter()
+                call()
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            med = ts[len(ts) // 2]
+            print(json.dumps({"metric": "inference latency, unidirectional GRUDecoder + greedy CTC decode (host in, decoded ids out)",
+                              "batch": B, "T_bins": a.T, "frames": frames, "dtype": precision, "ms_per_call": round(med * 1e3, 3),
+                              "us_per_output_frame": round(med * 1e6 / frames, 2), "us_per_20ms_bin": round(med * 1e6 / a.T, 2),
+                              "utterances_per_s": round(B / med, 1), "calls": a.steps, "impl": "ours", "data": "synthetic"}), flush=True)
+    nsd.set_default_precision("bf16")
+
+
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
+    if args.mode == "infer":
+        run_infer(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

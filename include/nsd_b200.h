@@ -55,11 +55,20 @@ int nsd_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   patches[j*B+b, c*K+kk] = z[b, j*S+kk, c]                         (time-major rows)
  * ys and z ([B,T,N] f32) are written for the backward; rows t >= (T'-1)*S+K are
  * left untouched.  err_flag (device-visible int32, may be mapped pinned host
- * memory, may be NULL) is set to 1 if a day index is outside [0,n_days).      */
+ * memory, may be NULL) is set to 1 if a day index is outside [0,n_days).
+ * Fused training augmentation (neural_decoder_trainer.py:194-201): when
+ * white_noise_sd / constant_offset_sd are non-zero, x is read as nsd_input_noise(x, ...) with the
+ * same seed would have written it -- no extra pass over X.  Distributional parity with the
+ * reference's torch.randn (counter-based Philox + Box-Muller here).                        */
 int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w, const float* day_b,
                      const float* taps, int ntaps, int B, int T, int N, int n_days, int kernel_len,
                      int stride_len, float* ys, float* z, void* patches, int patches_dtype,
-                     int* err_flag, void* stream);
+                     int* err_flag, float white_noise_sd, float constant_offset_sd, uint64_t noise_seed,
+                     void* stream);
+/* The augmentation on its own: out[b,t,c] = x[b,t,c] + white_noise_sd * n0[b,t,c] + constant_offset_sd * n1[b,c],
+ * n0, n1 standard normal, functions of (seed, element index) only.  x, out: [B,T,N] f32 contiguous (may alias). */
+int nsd_input_noise(const float* x, float* out, int B, int T, int N, float white_noise_sd, float constant_offset_sd,
+                    uint64_t seed, void* stream);
 
 /* Backward of K1 w.r.t. dayWeights / dayBias (X has no grad): col2im of dpatches,
  * softsign', per-utterance ys^T dpre, then a deterministic segment-reduce over

@@ -5,6 +5,7 @@ Public surface (mirrors the reference's):
     CTCLoss               torch.nn.CTCLoss as used at neural_decoder_trainer.py:139-141
     greedy_decode / phoneme_error_rate      trainer:313-333
     train_step / eval_batch                 trainer:181-260 / 286-333 (hot-loop lines only)
+    input_noise                             trainer:194-201 (white noise + constant offset; also fused into the front end)
 All compute is in ``libnsd_b200.so`` (include/nsd_b200.h); there is no CPU or PyTorch fallback.
 """
 from ._lib import NsdError, lib  # noqa: F401
@@ -12,5 +13,6 @@ from .model import GRUDecoder, set_default_precision  # noqa: F401
 from .ctc import (CTCLoss, ctc_loss_from_logits, greedy_decode, decoded_to_lists, edit_distances,  # noqa: F401
                   phoneme_error_rate, out_lens)
 from .trainer import train_step, eval_batch, make_optimizer  # noqa: F401
+from .ops import input_noise  # noqa: F401   trainer:194-201 as one kernel
 
 __version__ = "0.1.0"

@@ -25,7 +25,8 @@ SIGNATURES = {
     "nsd_last_error": (C.c_char_p, []),
     "nsd_launch_count": (C.c_ulonglong, []),
     "nsd_device_info": (i32, [C.POINTER(i32)] * 3),
-    "nsd_frontend_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "nsd_frontend_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, f32, f32, u64, vp]),
+    "nsd_input_noise": (i32, [vp, vp, i32, i32, i32, f32, f32, u64, vp]),
     "nsd_frontend_bwd": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]),
     "nsd_frontend_bwd_workspace": (sz, [i32, i32]),
     "nsd_gemm_f32": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, f32, vp]),

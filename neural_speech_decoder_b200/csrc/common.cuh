@@ -76,6 +76,37 @@ __device__ __forceinline__ uint4 dropout_bits(size_t q, uint64_t seed) {
 }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)fminf(4294967295.0f, p * 4294967296.0f); }
 
+// In-loop training augmentation of the reference (neural_decoder_trainer.py:194-201): X += N(0,1)*whiteNoiseSD (per element)
+// and X += N(0,1)*constantOffsetSD (per utterance and channel, constant over time).  Counter-based: the four standard
+// normals of elements 4q .. 4q+3 of a stream depend only on (seed, stream, q) -- Philox bits through Box-Muller -- so the
+// fused form inside K1 and the stand-alone kernel produce identical values wherever and however often an element is read.
+__device__ __forceinline__ float4 normal4(size_t q, uint64_t seed, uint32_t stream) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), stream, 0x6e6f6973u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u0 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float m0 = sqrtf(-2.0f * __logf(u0)), m1 = sqrtf(-2.0f * __logf(u2));
+    float s0, c0, s1, c1;
+    __sincosf(6.2831853071795865f * u1, &s0, &c0);
+    __sincosf(6.2831853071795865f * u3, &s1, &c1);
+    return make_float4(m0 * c0, m0 * s0, m1 * c1, m1 * s1);
+}
+__device__ __forceinline__ float normal1(size_t e, uint64_t seed, uint32_t stream) {
+    const float4 v = normal4(e >> 2, seed, stream);
+    const int i = (int)(e & 3);
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+// x[b,t,c] + white_sd * n0[(b*T+t)*N+c] + offset_sd * n1[b*N+c]   (N % 4 == 0 variant for four consecutive channels)
+__device__ __forceinline__ float4 add_input_noise4(float4 v, size_t e, size_t eo, float white_sd, float offset_sd, uint64_t seed) {
+    if (white_sd != 0.f) { const float4 n = normal4(e >> 2, seed, 0u); v.x = fmaf(white_sd, n.x, v.x); v.y = fmaf(white_sd, n.y, v.y); v.z = fmaf(white_sd, n.z, v.z); v.w = fmaf(white_sd, n.w, v.w); }
+    if (offset_sd != 0.f) { const float4 n = normal4(eo >> 2, seed, 1u); v.x = fmaf(offset_sd, n.x, v.x); v.y = fmaf(offset_sd, n.y, v.y); v.z = fmaf(offset_sd, n.z, v.z); v.w = fmaf(offset_sd, n.w, v.w); }
+    return v;
+}
+__device__ __forceinline__ float add_input_noise1(float v, size_t e, size_t eo, float white_sd, float offset_sd, uint64_t seed) {
+    if (white_sd != 0.f) v = fmaf(white_sd, normal1(e, seed, 0u), v);
+    if (offset_sd != 0.f) v = fmaf(offset_sd, normal1(eo, seed, 1u), v);
+    return v;
+}
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }

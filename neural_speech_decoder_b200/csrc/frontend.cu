@@ -6,6 +6,8 @@
 // last K+TT rows of z in a shared-memory ring and emits every frame whose window is complete.
 // X is read once (plus a (ntaps-1)-row halo per block), ys/z are written once for the backward,
 // patches are written once with 16-byte stores in time-major row order (m = j*B + b).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nsd {
@@ -18,6 +20,7 @@ struct FrontendFwdParams {
     const float* x; const int64_t* day_idx; const float* day_w; const float* day_b; const float* taps;
     float* ys; float* z; void* patches; int* err_flag;
     int ntaps, B, T, N, n_days, K, S, Tp, frames_per_seg, ring;
+    float white_sd, offset_sd; unsigned long long noise_seed;   // fused training augmentation (trainer:194-201); 0 = off
 };
 
 template <typename OutT>
@@ -37,6 +40,7 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
     const int j1 = min(p.Tp, j0 + p.frames_per_seg);
     if (j0 >= j1) return;
     const int tid = threadIdx.x;
+    const bool noisy = (p.white_sd != 0.f) || (p.offset_sd != 0.f);
 
     long long day = p.day_idx[b];
     if (day < 0 || day >= p.n_days) {          // reference: index_select raises IndexError (model.py:89)
@@ -62,14 +66,22 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
                 int rr = i / n4, c4 = i - rr * n4;
                 int t = rb - left + rr;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t >= 0 && t < T && rr < rows + ntaps - 1) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)t * N) + c4);
+                if (t >= 0 && t < T && rr < rows + ntaps - 1) {
+                    v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)t * N) + c4);
+                    if (noisy) v = add_input_noise4(v, ((size_t)b * T + t) * N + 4 * c4, (size_t)b * N + 4 * c4, p.white_sd, p.offset_sd, p.noise_seed);
+                }
                 reinterpret_cast<float4*>(xs + (size_t)rr * N)[c4] = v;
             }
         } else {
             for (int i = tid; i < xrows * N; i += FE_THREADS) {
                 int rr = i / N, c = i - rr * N;
                 int t = rb - left + rr;
-                xs[i] = (t >= 0 && t < T) ? __ldg(xb + (size_t)t * N + c) : 0.f;
+                float v = 0.f;
+                if (t >= 0 && t < T) {
+                    v = __ldg(xb + (size_t)t * N + c);
+                    if (noisy) v = add_input_noise1(v, ((size_t)b * T + t) * N + c, (size_t)b * N + c, p.white_sd, p.offset_sd, p.noise_seed);
+                }
+                xs[i] = v;
             }
         }
         __syncthreads();
@@ -290,6 +302,24 @@ __global__ void day_segment_reduce_kernel(const float* __restrict__ pw, const fl
     }
 }
 
+// stand-alone form of the augmentation (same values as the fused path): out = x + white + offset
+__global__ void input_noise_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int T, int N, float white_sd, float offset_sd,
+                                   unsigned long long seed) {
+    const size_t total = (size_t)B * T * N;
+    if ((N & 3) == 0) {
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total / 4; q += (size_t)gridDim.x * blockDim.x) {
+            const size_t e = 4 * q, b = e / ((size_t)T * N), c = e % N;
+            float4 v = reinterpret_cast<const float4*>(x)[q];
+            reinterpret_cast<float4*>(out)[q] = add_input_noise4(v, e, b * N + c, white_sd, offset_sd, seed);
+        }
+    } else {
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+            const size_t b = e / ((size_t)T * N), c = e % N;
+            out[e] = add_input_noise1(x[e], e, b * N + c, white_sd, offset_sd, seed);
+        }
+    }
+}
+
 static int pick_segments(int B, int Tp, int sms, int S, int K) {
     // minimise waves/segments: time ~ ceil(B*nseg/sms)/nseg, halo recompute grows with nseg
     int best = 1;
@@ -310,7 +340,7 @@ extern "C" {
 int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w, const float* day_b,
                      const float* taps, int ntaps, int B, int T, int N, int n_days, int kernel_len,
                      int stride_len, float* ys, float* z, void* patches, int patches_dtype, int* err_flag,
-                     void* stream) {
+                     float white_noise_sd, float constant_offset_sd, uint64_t noise_seed, void* stream) {
     using namespace nsd;
     NSD_CHECK_ARG(B > 0 && T > 0 && N > 0 && n_days > 0, "frontend_fwd: bad sizes B=%d T=%d N=%d", B, T, N);
     NSD_CHECK_ARG(ntaps >= 1 && ntaps <= 64, "frontend_fwd: ntaps=%d not in [1,64]", ntaps);
@@ -320,6 +350,7 @@ int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w,
     FrontendFwdParams p;
     p.x = x; p.day_idx = day_idx; p.day_w = day_w; p.day_b = day_b; p.taps = taps;
     p.ys = ys; p.z = z; p.patches = patches; p.err_flag = err_flag;
+    p.white_sd = white_noise_sd; p.offset_sd = constant_offset_sd; p.noise_seed = noise_seed;
     p.ntaps = ntaps; p.B = B; p.T = T; p.N = N; p.n_days = n_days; p.K = kernel_len; p.S = stride_len;
     p.Tp = (T - kernel_len) / stride_len + 1;
     const int nseg = pick_segments(B, p.Tp, sm_count(), stride_len, kernel_len);
@@ -336,6 +367,19 @@ int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w,
         NSD_CUDA(cudaFuncSetAttribute(frontend_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         frontend_fwd_kernel<__nv_bfloat16><<<grid, FE_THREADS, smem, s>>>(p);
     }
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+int nsd_input_noise(const float* x, float* out, int B, int T, int N, float white_noise_sd, float constant_offset_sd,
+                    uint64_t seed, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(B >= 0 && T >= 0 && N > 0 && x && out, "input_noise: bad arguments");
+    const size_t total = (size_t)B * T * N;
+    if (total == 0) return NSD_OK;
+    NSD_CHECK_ARG((N & 3) != 0 || ((((uintptr_t)x | (uintptr_t)out) & 15) == 0), "input_noise: x/out must be 16-byte aligned");
+    const int blocks = (int)std::min<size_t>(cdivz(cdivz(total, 4), 256), (size_t)sm_count() * 16);
+    input_noise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, B, T, N, white_noise_sd, constant_offset_sd, seed);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

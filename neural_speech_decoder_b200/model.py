@@ -119,6 +119,9 @@ class GRUDecoder(nn.Module):
         self._step = 0
         self._err_flag: Optional[torch.Tensor] = None
         self.grad_sync = None       # parallel.GradSync when training data-parallel (set by trainer.train_step)
+        # (whiteNoiseSD, constantOffsetSD) of the trainer's in-loop augmentation (trainer:194-201), applied inside K1 while
+        # the module is in train mode; None = the caller adds its own noise (or none), as in the reference
+        self.input_noise = None
         from .model_tc import Bf16Shadows
         self._shadows = Bf16Shadows()   # bf16 operand copies of the weights (bf16 precision only), see FusedAdam.attach_shadows
 
@@ -154,9 +157,11 @@ class GRUDecoder(nn.Module):
                    D=2 if self.bidirectional else 1, n_days=self.nDays, precision=self.precision,
                    p_drop=float(self.dropout) if self.training else 0.0, seed=0, err_flag=self._err_flag,
                    grad_sync=self.grad_sync, shadows=self._shadows)
-        if cfg["p_drop"] > 0:
+        noisy = self.training and self.input_noise is not None and any(float(v) != 0.0 for v in self.input_noise)
+        if cfg["p_drop"] > 0 or noisy:
             self._step += 1
             cfg["seed"] = (int(torch.initial_seed()) * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF
+        cfg["noise"] = (float(self.input_noise[0]), float(self.input_noise[1]), cfg["seed"] ^ 0x5DEECE66D) if noisy else None
         taps = self.gaussianSmoother.weight[0, 0].contiguous()
         return _DecoderFunction.apply(cfg, neuralInput, dayIdx, taps, self.dayWeights, self.dayBias,
                                       self.fc_decoder_out.weight, self.fc_decoder_out.bias, *self._gru_weights())
@@ -204,7 +209,7 @@ class _DecoderFunction(torch.autograd.Function):
         day_idx = day_idx.to(device=dev, dtype=torch.int64).contiguous()
         need_grad = any(t.requires_grad for t in (day_w, day_b, fc_w, fc_b) + tuple(gru_w))
         patches, ys, z = ops.frontend_fwd(x, day_idx, day_w.detach().contiguous(), day_b.detach().contiguous(), taps,
-                                          K, S, torch.float32, cfg["err_flag"])
+                                          K, S, torch.float32, cfg["err_flag"], cfg.get("noise"))
         inp = patches
         layers = []
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)

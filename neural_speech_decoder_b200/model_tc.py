@@ -88,7 +88,7 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
     day_idx = day_idx.to(device=dev, dtype=torch.int64).contiguous()
     need_grad = any(t.requires_grad for t in (day_w, day_b, fc_w, fc_b) + tuple(gru_w))
     patches, ys, z = ops.frontend_fwd(x, day_idx, day_w.detach().contiguous(), day_b.detach().contiguous(), taps,
-                                      K, S, torch.bfloat16, cfg["err_flag"])
+                                      K, S, torch.bfloat16, cfg["err_flag"], cfg.get("noise"))
     inp = patches                                            # bf16 [M, in_l]
     layers = []
     hseq = None

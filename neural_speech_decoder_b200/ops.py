@@ -21,8 +21,9 @@ def n_frames(T: int, kernel_len: int, stride_len: int) -> int:
 
 
 # ------------------------------------------------------------------ K1
-def frontend_fwd(x, day_idx, day_w, day_b, taps, kernel_len, stride_len, out_dtype, err_flag=None):
-    """-> (patches [T'*B, N*K] time-major, ys [B,T,N], z [B,T,N])."""
+def frontend_fwd(x, day_idx, day_w, day_b, taps, kernel_len, stride_len, out_dtype, err_flag=None, noise=None):
+    """-> (patches [T'*B, N*K] time-major, ys [B,T,N], z [B,T,N]).  ``noise`` = (whiteNoiseSD, constantOffsetSD, seed)
+    fuses the trainer's in-loop augmentation (trainer:194-201) into the read of x."""
     require_cuda(x, "neuralInput")
     B, T, N = x.shape
     Tp = n_frames(T, kernel_len, stride_len)
@@ -33,8 +34,20 @@ def frontend_fwd(x, day_idx, day_w, day_b, taps, kernel_len, stride_len, out_dty
     patches = torch.empty((Tp * B, N * kernel_len), device=x.device, dtype=out_dtype)
     call("nsd_frontend_fwd", ptr(x), ptr(day_idx), ptr(day_w), ptr(day_b), ptr(taps), taps.numel(), B, T, N,
          day_w.shape[0], kernel_len, stride_len, ptr(ys), ptr(z), ptr(patches), dtype_code(out_dtype),
-         ptr(err_flag), stream())
+         ptr(err_flag), float(noise[0]) if noise else 0.0, float(noise[1]) if noise else 0.0, int(noise[2]) if noise else 0,
+         stream())
     return patches, ys, z
+
+
+def input_noise(x, white_noise_sd: float, constant_offset_sd: float, seed: int, out=None):
+    """x + N(0,1)*whiteNoiseSD + N(0,1)[B,1,N]*constantOffsetSD (trainer:194-201) in one pass; the values the fused
+    front end uses for the same seed."""
+    require_cuda(x, "X")
+    assert x.dim() == 3 and x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    B, T, N = x.shape
+    call("nsd_input_noise", ptr(x), ptr(out), B, T, N, float(white_noise_sd), float(constant_offset_sd), int(seed), stream())
+    return out
 
 
 def frontend_bwd(dpatches, ys, z, day_idx, n_days, kernel_len, stride_len):

@@ -28,10 +28,14 @@ def make_optimizer(model: torch.nn.Module, args: dict):
     return opt, sched
 
 
-def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, grad_sync=None) -> torch.Tensor:
+def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, grad_sync=None,
+               white_noise_sd: float = 0.0, constant_offset_sd: float = 0.0) -> torch.Tensor:
     """One optimisation step; returns the (device) loss scalar.  ``grad_sync`` is the data-parallel hook
-    (parallel.GradSync): it all-reduces gradients bucket by bucket while the backward is still running."""
+    (parallel.GradSync): it all-reduces gradients bucket by bucket while the backward is still running.
+    ``white_noise_sd`` / ``constant_offset_sd`` (args["whiteNoiseSD"], args["constantOffsetSD"]): the in-loop
+    augmentation of trainer:194-201, generated inside the front-end kernel instead of in extra passes over X."""
     model.grad_sync = grad_sync
+    model.input_noise = (white_noise_sd, constant_offset_sd) if (white_noise_sd or constant_offset_sd) else None
     pred = model.forward(X, dayIdx)                                         # trainer:208
     lens = _ctc.out_lens(X_len, model.kernelLen, model.strideLen)           # trainer:209
     loss = _ctc.ctc_loss_from_logits(pred, y, lens, y_len, blank=0, reduction="mean")   # trainer:210-218, 242

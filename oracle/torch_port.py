@@ -81,7 +81,11 @@ def make_adam(model, lr=0.02, l2=1e-5):
     return torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=0.1, weight_decay=l2)   # trainer:163-169
 
 
-def train_step(model, opt, X, y, X_len, y_len, dayIdx):
+def train_step(model, opt, X, y, X_len, y_len, dayIdx, white_noise_sd: float = 0.0, constant_offset_sd: float = 0.0):
+    if white_noise_sd > 0:                                                           # trainer:194-196
+        X = X + torch.randn(X.shape) * white_noise_sd
+    if constant_offset_sd > 0:                                                       # trainer:198-201
+        X = X + torch.randn([X.shape[0], 1, X.shape[2]]) * constant_offset_sd
     pred = model(X, dayIdx)                                                          # trainer:208
     out_lens = ((X_len - model.kernelLen) / model.strideLen).to(torch.int32)         # trainer:209
     log_probs = pred.log_softmax(2).permute(1, 0, 2)                                 # trainer:210

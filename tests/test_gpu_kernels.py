@@ -275,3 +275,56 @@ def test_fused_adam_matches_torch_adam():
         o_ref.step(); o_mine.step()
     for a, b in zip(ref, mine):
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
+
+
+def test_input_noise_moments_and_fused_front_end():
+    """trainer:194-201: X += randn*whiteNoiseSD; X += randn([B,1,N])*constantOffsetSD.  Distributional parity (own
+    counter-based generator): moments of the two components; the copy fused into K1 must equal K1 of the explicitly
+    noised input bit for bit."""
+    import neural_speech_decoder_b200 as nsd
+    B, T, N = 8, 300, 256
+    x = torch.zeros(B, T, N, device=DEV)
+    w = ops.input_noise(x, 0.8, 0.0, 11)
+    assert abs(w.mean().item()) < 5e-3 and abs(w.std().item() - 0.8) < 5e-3
+    kurt = ((w / w.std()) ** 4).mean().item()
+    assert abs(kurt - 3.0) < 0.05                                       # Gaussian, not uniform
+    assert abs(torch.corrcoef(torch.stack([w[:, :-1].reshape(-1), w[:, 1:].reshape(-1)]))[0, 1].item()) < 5e-3
+    o = ops.input_noise(x, 0.0, 0.2, 11)
+    assert torch.equal(o, o[:, :1].expand(-1, T, -1).contiguous())      # constant over time
+    off = o[:, 0]
+    assert abs(off.mean().item()) < 2e-2 and abs(off.std().item() - 0.2) < 2e-2
+    assert not torch.equal(ops.input_noise(x, 0.8, 0.2, 11), ops.input_noise(x, 0.8, 0.2, 12))
+    both = ops.input_noise(x, 0.8, 0.2, 11)
+    assert torch.allclose(both, w + o, atol=1e-6)
+    # fused into the front end
+    torch.manual_seed(0)
+    xr = torch.randn(B, T, N, device=DEV)
+    day = torch.randint(0, 4, (B,), device=DEV)
+    dw = (torch.eye(N, device=DEV) + 0.05 * torch.randn(4, N, N, device=DEV)).contiguous()
+    db = 0.1 * torch.randn(4, 1, N, device=DEV)
+    taps = nsd.model.gaussian_kernel_1d(20, 2.0).to(DEV)
+    for dt in (torch.float32, torch.bfloat16):
+        fused = ops.frontend_fwd(xr, day, dw, db, taps, 32, 4, dt, None, (0.8, 0.2, 77))
+        plain = ops.frontend_fwd(ops.input_noise(xr, 0.8, 0.2, 77), day, dw, db, taps, 32, 4, dt)
+        for a, b in zip(fused, plain):
+            assert torch.equal(a, b)
+    # odd channel count takes the scalar path
+    xo = torch.randn(3, 50, 30, device=DEV)
+    no = ops.input_noise(torch.zeros_like(xo), 1.0, 0.0, 5)
+    assert abs(no.std().item() - 1.0) < 0.05
+
+
+def test_train_step_with_fused_noise_runs():
+    import neural_speech_decoder_b200 as nsd
+    from neural_speech_decoder_b200.synthetic import make_batch
+    kw = dict(neural_dim=32, n_classes=10, hidden_dim=64, layer_dim=2, nDays=4, dropout=0.2, strideLen=4, kernelLen=16,
+              gaussianSmoothWidth=2.0, bidirectional=True)
+    torch.manual_seed(0)
+    m = nsd.GRUDecoder(device=DEV, **kw).to(DEV).train()
+    batch = [t.to(DEV) for t in make_batch(4, 72, n_feat=32, n_days=4, n_classes=10, seed=5, min_tgt=2, max_tgt=6, kernel_len=16, stride_len=4)]
+    opt, sched = nsd.make_optimizer(m, dict(lrStart=0.02, lrEnd=0.02, nBatch=100, l2_decay=1e-5))
+    a = nsd.train_step(m, opt, *batch, white_noise_sd=0.8, constant_offset_sd=0.2).item()
+    assert np.isfinite(a)
+    m.eval()                                                            # eval: no augmentation even if configured
+    X, day = batch[0], batch[4]
+    assert torch.equal(m.forward(X, day), m.forward(X, day))
