@@ -23,17 +23,42 @@ struct FrontendFwdParams {
     float white_sd, offset_sd; unsigned long long noise_seed;   // fused training augmentation (trainer:194-201); 0 = off
 };
 
-template <typename OutT>
+// ---- warp-level tensor-core pieces of the bf16 front end (the 256x256 day affine is a tiny GEMM fused between HBM-bound
+// stages: mma.sync m16n8k16 on register-resident weight fragments, not a tcgen05 pipeline)
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+// NTW = 0: fp32 FFMA day affine (the fp32 parity path, any N).  NTW = N/64 > 0: bf16 tensor-core day affine, N = 64*NTW:
+// warp w owns output channels [8*NTW*w, 8*NTW*(w+1)) and keeps its slice of dayWeights[day] as mma B fragments in
+// registers for the whole CTA; the smoothed block is the A operand (bf16, shared memory), fp32 accumulate.
+template <typename OutT, int NTW>
 __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwdParams p) {
     extern __shared__ __align__(16) float smem[];
     const int N = p.N, K = p.K, S = p.S, T = p.T, ntaps = p.ntaps;
     const int left = (ntaps - 1) / 2;
     const int xrows = FE_TT + ntaps - 1;
     const int NP = N + 1;
+    constexpr int KS = NTW * 4;                             // k-steps of 16 input channels (N / 16)
+    constexpr int NA = NTW * 64 + 8;                        // padded row length (bf16) of the A tile: conflict-free ldmatrix
     float* taps_s = smem;                                   // [64]
     float* xs = smem + 64;                                  // [xrows][N]
-    float* ysT = xs + (size_t)xrows * N;                    // [N][FE_TTP]
-    float* zring = ysT + (size_t)N * FE_TTP;                // [ring][N+1]
+    float* ysT = xs + (size_t)xrows * N;                    // SIMT: [N][FE_TTP] f32;  TC: [FE_TT][NA] bf16
+    float* zring = ysT + (NTW > 0 ? (size_t)FE_TT * NA / 2 : (size_t)N * FE_TTP);   // [ring][N+1]
+    __nv_bfloat16* ysA = reinterpret_cast<__nv_bfloat16*>(ysT);
 
     const int b = blockIdx.x;
     const int j0 = blockIdx.y * p.frames_per_seg;
@@ -50,6 +75,24 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
     const float* W = p.day_w + (size_t)day * N * N;
     const float* bias = p.day_b + (size_t)day * N;
     if (tid < ntaps) taps_s[tid] = p.taps[tid];
+
+    const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, fc = lane & 3;     // mma fragment coordinates
+    uint32_t wfrag[NTW > 0 ? NTW : 1][NTW > 0 ? KS : 1][2];
+    float bfrag[NTW > 0 ? NTW : 1][2];
+    if constexpr (NTW > 0) {
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) {
+            const int n = (warp * NTW + j) * 8 + fg;                               // B[k = d][n]: this lane's output channel
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const float* w0 = W + (size_t)(16 * ks + 2 * fc) * N + n;
+                wfrag[j][ks][0] = pack2_bf16(__ldg(w0), __ldg(w0 + N));
+                wfrag[j][ks][1] = pack2_bf16(__ldg(w0 + 8 * (size_t)N), __ldg(w0 + 9 * (size_t)N));
+            }
+            bfrag[j][0] = __ldg(bias + (warp * NTW + j) * 8 + 2 * fc);
+            bfrag[j][1] = __ldg(bias + (warp * NTW + j) * 8 + 2 * fc + 1);
+        }
+    }
 
     const int R0 = j0 * S, R1 = (j1 - 1) * S + K;   // z rows this CTA needs
     const float* xb = p.x + (size_t)b * T * N;
@@ -93,11 +136,44 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
                     for (int k = 0; k < ntaps; ++k) acc = fmaf(taps_s[k], xs[(size_t)(tt + k) * N + c], acc);
                     ysb[(size_t)(rb + tt) * N + c] = acc;
                 }
-                ysT[(size_t)c * FE_TTP + tt] = acc;
+                if constexpr (NTW > 0) ysA[(size_t)tt * NA + c] = __float2bfloat16_rn(acc);
+                else ysT[(size_t)c * FE_TTP + tt] = acc;
             }
         }
         __syncthreads();
         // 3. day affine + softsign: pre[t][k] = sum_d ys[t][d] W[d][k] + bias[k]
+        if constexpr (NTW > 0) {
+            float acc[2][NTW][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) { acc[mt][j][0] = acc[mt][j][2] = bfrag[j][0]; acc[mt][j][1] = acc[mt][j][3] = bfrag[j][1]; }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    uint32_t a[4];
+                    ldmatrix_x4(a, ysA + (size_t)(16 * mt + (lane & 7) + 8 * ((lane >> 3) & 1)) * NA + 16 * ks + 8 * (lane >> 4));
+#pragma unroll
+                    for (int j = 0; j < NTW; ++j) mma_bf16_16816(acc[mt][j], a, wfrag[j][ks][0], wfrag[j][ks][1]);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int j = 0; j < NTW; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = 16 * mt + fg + 8 * h, col = (warp * NTW + j) * 8 + 2 * fc;
+                        if (i < rows) {
+                            const float a0 = acc[mt][j][2 * h], a1 = acc[mt][j][2 * h + 1];
+                            const float v0 = a0 / (1.0f + fabsf(a0)), v1 = a1 / (1.0f + fabsf(a1));
+                            float* zr = zring + (size_t)((rb + i) % p.ring) * NP + col;
+                            zr[0] = v0; zr[1] = v1;
+                            *reinterpret_cast<float2*>(zb + (size_t)(rb + i) * N + col) = make_float2(v0, v1);
+                        }
+                    }
+        } else
         for (int kc = tid; kc < N; kc += FE_THREADS) {
             float acc[FE_TT];
             const float bv = __ldg(bias + kc);
@@ -286,6 +362,152 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_kernel(FrontendBwd
     }
 }
 
+// Tensor-core form of the backward for the bf16 model path (dpatches bf16, N = 128 * MT): same col2im ring and softsign',
+// but the per-utterance ys^T dpre (the 2*T*N*N FLOPs that made the FFMA kernel instruction-bound) runs on mma.sync m16n8k16
+// with bf16 operands and fp32 accumulators held in registers for the whole utterance: warp w owns rows d in
+// [16*MT*w, 16*MT*(w+1)) of dW, all FB_CN = 128 columns of the CTA's column block.
+template <int MT>
+__global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_tc_kernel(FrontendBwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int N = 128 * MT, NYS = N + 8, NDP = FB_CN + 8;
+    const int K = p.K, S = p.S, T = p.T, KP = p.KP, B = p.B;
+    const int b = blockIdx.x;
+    const int c0 = blockIdx.y * FB_CN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kl = tid & (FB_CN - 1);   // column within the chunk
+    const int half = tid >> 7;          // which 8 of a chunk's 16 rows this thread turns into dpre
+    const int RP = FB_CN + 1;
+    float* ring = smem;                                                           // [ring][FB_CN+1]
+    float* stage = ring + (((size_t)p.ring * RP + 3) & ~(size_t)3);               // [FB_G][FB_CN][KP], 16-byte aligned
+    __nv_bfloat16* ys_s = reinterpret_cast<__nv_bfloat16*>(stage + (size_t)FB_G * FB_CN * KP);   // [16][N+8]
+    __nv_bfloat16* dp_s = ys_s + 16 * NYS;                                        // [16][FB_CN+8]
+    float* bsum = reinterpret_cast<float*>(dp_s + 16 * NDP);                      // [FB_CN]
+
+    for (int i = tid; i < p.ring * RP; i += FB_THREADS) ring[i] = 0.f;
+    const float* ysb = p.ys + (size_t)b * T * N;
+    const float* zb = p.z + (size_t)b * T * N;
+    const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(p.dp);
+    const int F = N * K;
+
+    float acc[MT][FB_CN / 8][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < FB_CN / 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    float bacc = 0.f;
+    __syncthreads();
+
+    auto finalize = [&](int r_begin, int r_end) {
+        for (int rc = r_begin; rc < r_end; rc += 16) {
+            const int nr = min(16, r_end - rc);
+            // A^T tile: 16 rows of ys as bf16 (zero rows past nr)
+            for (int i = tid; i < 16 * (N / 4); i += FB_THREADS) {
+                const int rr = i / (N / 4), c4 = i - rr * (N / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rr < nr) v = __ldg(reinterpret_cast<const float4*>(ysb + (size_t)(rc + rr) * N) + c4);
+                *reinterpret_cast<uint2*>(ys_s + (size_t)rr * NYS + 4 * c4) = make_uint2(pack2_bf16(v.x, v.y), pack2_bf16(v.z, v.w));
+            }
+            // B tile: dpre = col2im(dpatches) * softsign'(z), this thread's column, 8 of the 16 rows
+            {
+                float zz[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int rr = 8 * half + q;
+                    zz[q] = (rr < nr) ? __ldg(zb + (size_t)(rc + rr) * N + c0 + kl) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int rr = 8 * half + q;
+                    float dpre = 0.f;
+                    if (rr < nr) {
+                        const float sg = 1.0f - fabsf(zz[q]);
+                        dpre = ring[(size_t)((rc + rr) % p.ring) * RP + kl] * sg * sg;
+                    }
+                    bacc += dpre;
+                    dp_s[(size_t)rr * NDP + kl] = __float2bfloat16_rn(dpre);
+                }
+            }
+            __syncthreads();
+            {
+                uint32_t a[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    ldmatrix_x4_trans(a[mt], ys_s + (size_t)((lane & 7) + 8 * (lane >> 4)) * NYS + (warp * MT + mt) * 16 + 8 * ((lane >> 3) & 1));
+#pragma unroll
+                for (int np = 0; np < FB_CN / 16; ++np) {
+                    uint32_t bq[4];
+                    ldmatrix_x4_trans(bq, dp_s + (size_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * NDP + 16 * np + 8 * (lane >> 4));
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_bf16_16816(acc[mt][2 * np], a[mt], bq[0], bq[1]);
+                        mma_bf16_16816(acc[mt][2 * np + 1], a[mt], bq[2], bq[3]);
+                    }
+                }
+            }
+            // consumed rows go back to zero for their next use
+            for (int i = tid; i < nr * FB_CN; i += FB_THREADS)
+                ring[(size_t)((rc + i / FB_CN) % p.ring) * RP + (i % FB_CN)] = 0.f;
+            __syncthreads();
+        }
+    };
+
+    for (int jg = 0; jg < p.Tp; jg += FB_G) {
+        const int ng = min(FB_G, p.Tp - jg);
+        // a. stage this CTA's slice of ng gradient rows (coalesced 16-byte loads when K % 8 == 0)
+        for (int g = 0; g < ng; ++g) {
+            const __nv_bfloat16* row = dp + ((size_t)(jg + g) * B + b) * F + (size_t)c0 * K;
+            float* st = stage + (size_t)g * FB_CN * KP;
+            if ((K & 7) == 0) {
+                for (int i = tid; i < FB_CN * K / 8; i += FB_THREADS) {
+                    const int e = 8 * i, cl = e / K, kk = e - cl * K;
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(row) + i);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    float* d = st + cl * KP + kk;
+                    const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+                    *reinterpret_cast<float4*>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    *reinterpret_cast<float4*>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+                }
+            } else {
+                for (int i = tid; i < FB_CN * K; i += FB_THREADS) {
+                    const int cl = i / K, kk = i - cl * K;
+                    st[cl * KP + kk] = __bfloat162float(row[i]);
+                }
+            }
+        }
+        __syncthreads();
+        // b. scatter-add into the ring; a thread owns (cl, phase) so no two threads touch one cell
+        for (int pi = tid; pi < FB_CN * S; pi += FB_THREADS) {
+            const int cl = pi / S, ph = pi - cl * S;
+            for (int g = 0; g < ng; ++g) {
+                const float* st = stage + (size_t)g * FB_CN * KP + cl * KP;
+                const int rbase = (jg + g) * S;
+                for (int kk = ph; kk < K; kk += S) ring[(size_t)((rbase + kk) % p.ring) * RP + cl] += st[kk];
+            }
+        }
+        __syncthreads();
+        // c. rows below the next group's first row are complete
+        const bool last = (jg + ng >= p.Tp);
+        finalize(jg * S, last ? (p.Tp - 1) * S + K : (jg + ng) * S);
+    }
+    // this utterance's partial dW block / db: C fragment (row = lane/4 (+8), cols 2*(lane%4), +1)
+    float* pw = p.partial_w + (size_t)b * N * N;
+    const int fg = lane >> 2, fc = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < FB_CN / 8; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int d = (warp * MT + mt) * 16 + fg + 8 * h;
+                *reinterpret_cast<float2*>(pw + (size_t)d * N + c0 + 8 * nt + 2 * fc) = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
+            }
+    if (half == 1) bsum[kl] = bacc;
+    __syncthreads();
+    if (half == 0) p.partial_b[(size_t)b * N + c0 + kl] = bacc + bsum[kl];
+}
+
 // out[d][e] = sum_{b : day[b]==d} partial[b][e], utterances visited in index order (deterministic).
 __global__ void day_segment_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
                                           const int64_t* __restrict__ day_idx, int B, int NN, int N, int n_days,
@@ -356,17 +578,25 @@ int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w,
     const int nseg = pick_segments(B, p.Tp, sm_count(), stride_len, kernel_len);
     p.frames_per_seg = cdiv(p.Tp, nseg);
     p.ring = kernel_len + FE_TT;
-    size_t smem = sizeof(float) * (64 + (size_t)(FE_TT + ntaps - 1) * N + (size_t)N * FE_TTP + (size_t)p.ring * (N + 1));
+    // bf16 patches (the tensor-core model path) with 64 | N <= 256: day affine on mma.sync; otherwise the exact fp32 FFMA form
+    const int ntw = (patches_dtype == NSD_BF16 && N % 64 == 0 && N <= 256) ? N / 64 : 0;
+    size_t smem = sizeof(float) * (64 + (size_t)(FE_TT + ntaps - 1) * N + (size_t)p.ring * (N + 1) +
+                                   (ntw ? (size_t)FE_TT * (N + 8) / 2 : (size_t)N * FE_TTP));
     NSD_CHECK_ARG(smem <= 227 * 1024, "frontend_fwd: N=%d kernelLen=%d need %zu B shared memory", N, kernel_len, smem);
     dim3 grid(B, cdiv(p.Tp, p.frames_per_seg));
     cudaStream_t s = (cudaStream_t)stream;
-    if (patches_dtype == NSD_F32) {
-        NSD_CUDA(cudaFuncSetAttribute(frontend_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        frontend_fwd_kernel<float><<<grid, FE_THREADS, smem, s>>>(p);
-    } else {
-        NSD_CUDA(cudaFuncSetAttribute(frontend_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        frontend_fwd_kernel<__nv_bfloat16><<<grid, FE_THREADS, smem, s>>>(p);
-    }
+    auto go = [&](auto kern) -> int {
+        NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, FE_THREADS, smem, s>>>(p);
+        return NSD_OK;
+    };
+    int rc;
+    if (patches_dtype == NSD_F32) rc = go(frontend_fwd_kernel<float, 0>);
+    else if (ntw == 4) rc = go(frontend_fwd_kernel<__nv_bfloat16, 4>);
+    else if (ntw == 2) rc = go(frontend_fwd_kernel<__nv_bfloat16, 2>);
+    else if (ntw == 1) rc = go(frontend_fwd_kernel<__nv_bfloat16, 1>);
+    else rc = go(frontend_fwd_kernel<__nv_bfloat16, 0>);
+    if (rc) return rc;
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -404,16 +634,32 @@ int nsd_frontend_bwd(const void* dpatches, int dpatches_dtype, const float* ys, 
     p.Tp = (T - kernel_len) / stride_len + 1;
     p.KP = ((kernel_len + 3) / 4) * 4 + 4;
     p.ring = (FB_G - 1) * stride_len + kernel_len;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int mt = (dpatches_dtype == NSD_BF16 && (N == 128 || N == 256)) ? N / 128 : 0;
+    if (mt) {
+        // bf16 model path: per-utterance ys^T dpre on tensor cores
+        size_t smem = sizeof(float) * ((((size_t)p.ring * (FB_CN + 1) + 3) & ~(size_t)3) + (size_t)FB_G * FB_CN * p.KP + FB_CN) +
+                      sizeof(__nv_bfloat16) * (16 * (size_t)(N + 8) + 16 * (size_t)(FB_CN + 8));
+        NSD_CHECK_ARG(smem <= 227 * 1024, "frontend_bwd: N=%d kernelLen=%d need %zu B shared memory", N, kernel_len, smem);
+        dim3 grid(B, N / FB_CN);
+        if (mt == 2) {
+            NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            frontend_bwd_tc_kernel<2><<<grid, FB_THREADS, smem, s>>>(p);
+        } else {
+            NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            frontend_bwd_tc_kernel<1><<<grid, FB_THREADS, smem, s>>>(p);
+        }
+    } else {
     size_t smem = sizeof(float) * ((size_t)p.ring * (FB_CN + 1) + (size_t)FB_RCH * N + (size_t)FB_G * FB_CN * p.KP);
     NSD_CHECK_ARG(smem <= 227 * 1024, "frontend_bwd: N=%d kernelLen=%d need %zu B shared memory", N, kernel_len, smem);
     dim3 grid(B, cdiv(N, FB_CN));
-    cudaStream_t s = (cudaStream_t)stream;
     if (dpatches_dtype == NSD_F32) {
         NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         frontend_bwd_kernel<float><<<grid, FB_THREADS, smem, s>>>(p);
     } else {
         NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         frontend_bwd_kernel<__nv_bfloat16><<<grid, FB_THREADS, smem, s>>>(p);
+    }
     }
     NSD_LAUNCH_CHECK();
     const int per = N * N + N;

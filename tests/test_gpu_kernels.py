@@ -328,3 +328,44 @@ def test_train_step_with_fused_noise_runs():
     m.eval()                                                            # eval: no augmentation even if configured
     X, day = batch[0], batch[4]
     assert torch.equal(m.forward(X, day), m.forward(X, day))
+
+
+@pytest.mark.parametrize("B,T,N,K,S,nd", [(5, 203, 256, 32, 4, 24), (3, 100, 128, 16, 4, 4), (2, 64, 64, 32, 4, 3), (4, 75, 256, 14, 4, 5)])
+def test_frontend_tensor_core_path(B, T, N, K, S, nd):
+    """bf16 model path of K1: the day affine (forward) and ys^T dpre (backward) run on mma.sync with bf16 operands and
+    fp32 accumulation.  Tolerances are bf16's (stated separately from the fp32 path above): z within 1e-2 absolute of the
+    fp64 oracle (|z| < 1), patches == bf16(z) exactly (the unfold stays pure data movement), dW/db within 2 % of max|dW|."""
+    rng = np.random.default_rng(N + T)
+    x = rng.standard_normal((B, T, N)).astype(np.float32)
+    W = (np.eye(N)[None] + 0.05 * rng.standard_normal((nd, N, N))).astype(np.float32)
+    bias = (0.1 * rng.standard_normal((nd, 1, N))).astype(np.float32)
+    day = rng.integers(0, nd, size=B).astype(np.int64)
+    day[-1] = day[0]
+    taps = O.gaussian_taps(2.0)
+    p_ref, saved = O.frontend_fwd(x.astype(np.float64), taps.astype(np.float64), W.astype(np.float64), bias.astype(np.float64), day, K, S)
+    patches, ys, z = ops.frontend_fwd(cu(x), cu(day), cu(W), cu(bias), cu(taps), K, S, torch.bfloat16)
+    Tp = O.n_frames(T, K, S)
+    used = (Tp - 1) * S + K
+    np.testing.assert_allclose(ys.cpu().numpy()[:, :used], saved["ys"][:, :used], rtol=1e-5, atol=2e-6)     # smoothing stays fp32
+    zerr = np.abs(z.cpu().numpy()[:, :used] - saved["z"][:, :used]).max()
+    print(f"tc front end N={N}: max |z - oracle| = {zerr:.2e}")
+    assert zerr < 1e-2
+    zk = torch.from_numpy(O.unfold(z.cpu().numpy().copy(), K, S)).to(torch.bfloat16)
+    assert torch.equal(patches.view(Tp, B, N * K).permute(1, 0, 2).cpu(), zk)
+
+    dp = rng.standard_normal((B, Tp, N * K)).astype(np.float32)
+    dp_bf = torch.from_numpy(np.ascontiguousarray(dp.transpose(1, 0, 2)).reshape(Tp * B, N * K)).to(torch.bfloat16).to(DEV)
+    dp_r = dp_bf.float().cpu().numpy().reshape(Tp, B, N * K).transpose(1, 0, 2).astype(np.float64)
+    saved_k = dict(saved)
+    zk64 = z.cpu().numpy().astype(np.float64)
+    saved_k["ys"], saved_k["z"] = ys.cpu().numpy().astype(np.float64), zk64
+    saved_k["pre"] = zk64 / (1.0 - np.abs(zk64))               # the backward is checked against the kernel's own forward state
+    dW_ref, db_ref = O.frontend_bwd(dp_r, saved_k, W.astype(np.float64), day, T, K, S)
+    dW, db = ops.frontend_bwd(dp_bf, ys, z, cu(day), nd, K, S)
+    scale = np.abs(dW_ref).max()
+    e_w = np.abs(dW.cpu().numpy() - dW_ref).max() / scale
+    e_b = np.abs(db.cpu().numpy() - db_ref).max() / max(np.abs(db_ref).max(), 1e-9)
+    print(f"tc front end N={N}: dW err / max|dW| = {e_w:.2e}, db err / max|db| = {e_b:.2e}")
+    assert e_w < 2e-2 and e_b < 2e-3                            # db is accumulated in fp32 from fp32 dpre
+    dW2, db2 = ops.frontend_bwd(dp_bf, ys, z, cu(day), nd, K, S)
+    assert torch.equal(dW, dW2) and torch.equal(db, db2)        # deterministic
