@@ -228,6 +228,22 @@ int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int cols, 
     return NSD_OK;
 }
 
+// 3-D view [cols/64 chunks][rows][64] of the same row-major matrix: ONE box {64, box_rows, box_chunks} lands as box_chunks
+// consecutive K-major 128B-swizzled [box_rows x 64] tiles, i.e. a whole multi-chunk UMMA operand per TMA instruction.
+int make_bf16_map_chunked(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows, int box_chunks) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("gemm_bf16: cuTensorMapEncodeTiled entry point not available"); return NSD_ERR_CUDA; }
+    cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)rows, (cuuint64_t)(cols / BK)};
+    cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)BK * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (chunked) failed (%d) rows=%lld cols=%d ld=%d", (int)r, rows, cols, ld); return NSD_ERR_CUDA; }
+    return NSD_OK;
+}
+
 int make_bf16_map_mn(CUtensorMap* map, const void* base, long long k_rows, int mn_cols, int ld) {
     return make_bf16_map(map, base, k_rows, mn_cols, ld, BK);      // inner dim = mn (64-wide box), outer = k (64 rows)
 }

@@ -108,6 +108,7 @@ struct Common {
     int nper;                               // CTAs per direction
     int G;                                  // batch groups of NG rows
     int ktot, kper;                         // reduction length (H forward, 3H BPTT) and its share per CTA (multiple of 16)
+    int chunked;                            // 1: K shares are whole 64-wide chunks -> single 3-D TMA box per operand
     int cs, upz, nzone;                         // units per zone (= per cluster) and zones per direction
     unsigned int* counters;                 // [D][G][nzone] step counters, CNT_STRIDE apart: CS arrivals per step
     long long* trace;                       // debug (NSD_GRU_TRACE=1)
@@ -215,7 +216,7 @@ __device__ __forceinline__ void load_a_row(uint32_t taddr_row, const __nv_bfloat
 // barriers are needed: passing the grid barrier of (s, g) implies that this CTA published (s-1, g), i.e. that its
 // MMAs and its epilogue for the previous use of the same buffers are finished.
 template <int NT>
-__device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, int warp, int lane, uint32_t tmem_base,
+__device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, const CUtensorMap* tmB3, int warp, int lane, uint32_t tmem_base,
                                               const Common& c, int d, int my_zone, int k_lo, int k_hi, int nslab, int nbox, int nbox_max,
                                               int b_col0, bool bptt) {
     const bool rev = (d == 1) || (c.reverse0 != 0);
@@ -246,8 +247,14 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                     if (lane == 0 && nbox > 0) mbar_expect_tx(&sm.full[gg], (uint32_t)(nbox * BOX_BYTES));
                     __syncwarp();
                     if (lane == 0 && g == 0) stamp(c, sm.trace, s, 0);
-                    if (lane < nbox) {
-                        asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy writes (acquired above) -> TMA reads
+                    if (c.chunked) {
+                        // K share aligned to 64-wide chunks: the whole operand (nbox swizzled tiles) in one TMA instruction
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes (acquired above) -> TMA reads
+                            tma_load_3d(tmB3, &sm.full[gg], sm.b + (size_t)(gg * nbox_max) * BOX_BYTES, 0, t_src * c.B + g * NG, (b_col0 + k_lo) / BK);
+                        }
+                    } else if (lane < nbox) {
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
                         tma_load_2d(tmB, &sm.full[gg], sm.b + (size_t)(gg * nbox_max + lane) * BOX_BYTES, b_col0 + k_lo + lane * BK, t_src * c.B + g * NG);
                     } else if (lane == 0) {
                         mbar_arrive(&sm.full[gg]);
@@ -383,7 +390,7 @@ struct FwdParams {
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
+gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmH3, const FwdParams p) {
     constexpr int CS = 4, NT = 2, NGATE = 3, U = 16;
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
     extern __shared__ uint8_t smem_raw[];
@@ -415,7 +422,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT>(sm, &tmH, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * H, false);
+        control_warps<NT>(sm, &tmH, &tmH3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * H, false);
     } else {
         // ------------------------------------------------------------ epilogue warpgroup gg: batch groups of parity gg
         const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
@@ -528,7 +535,7 @@ struct BwdParams {
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
+gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG3, const BwdParams p) {
     constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16;       // NP passes of (batch row, 4 units) per thread
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
     extern __shared__ uint8_t smem_raw[];
@@ -561,7 +568,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT>(sm, &tmG, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * 3 * H, true);
+        control_warps<NT>(sm, &tmG, &tmG3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * 3 * H, true);
     } else {
         const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
         const int bl = te >> 2, uo4 = te & 3;
@@ -692,7 +699,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
 
 // ---------------------------------------------------------------- host side
 template <typename Kern, typename P>
-static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const P& p, cudaStream_t s) {
+static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1, const P& p, cudaStream_t s) {
     NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -705,7 +712,7 @@ static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const C
     int max_clusters = 0;
     NSD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters * cs < grid) { set_error("gru_ts: %d CTAs in clusters of %d cannot be co-resident (max %d clusters)", grid, cs, max_clusters); return NSD_ERR_INVALID; }
-    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, p));
+    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, p));
     count_launch(1);
     return NSD_OK;
 }
@@ -783,13 +790,17 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     FwdParams p;
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, round_up(cdiv(H, CS), UMMA_K), CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    const int kper = round_up(cdiv(H, CS), UMMA_K);
+    const int chunked = (kper % BK == 0 && H % BK == 0) ? 1 : 0;
+    CUtensorMap tmH3 = tmH;
+    if (chunked) { rc = make_bf16_map_chunked(&tmH3, hseq_bf16, (long long)Tp * B, D * H, ldh, NG, kper / BK); if (rc) return rc; }
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, kper, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
     p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.hdrop = reinterpret_cast<__nv_bfloat16*>(hdrop_bf16); p.drop_thresh = dropout_threshold(p_drop); p.inv_keep = 1.0f / (1.0f - p_drop); p.seed = seed;
     const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
-    rc = launch_cluster_coop(gru_fwd_ts_kernel, D * nper, CS, smem, tmH, p, s);
+    rc = launch_cluster_coop(gru_fwd_ts_kernel, D * nper, CS, smem, tmH, tmH3, p, s);
     trace_end("gru_fwd_bf16", tr, s, D * nper);
     return rc;
 }
@@ -815,7 +826,11 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     BwdParams p;
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, round_up(cdiv(3 * H, CS), UMMA_K), CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    const int kper = round_up(cdiv(3 * H, CS), UMMA_K);
+    const int chunked = (kper % BK == 0) ? 1 : 0;
+    CUtensorMap tmG3 = tmG;
+    if (chunked) { rc = make_bf16_map_chunked(&tmG3, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG, kper / BK); if (rc) return rc; }
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, kper, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
     p.wT = reinterpret_cast<const __nv_bfloat16*>(w_hhT_bf16);
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
@@ -826,7 +841,7 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
         NSD_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)D * 3 * H, s));
     }
     const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
-    rc = launch_cluster_coop(gru_bwd_ts_kernel, D * nper, CS, smem, tmG, p, s);
+    rc = launch_cluster_coop(gru_bwd_ts_kernel, D * nper, CS, smem, tmG, tmG3, p, s);
     trace_end("gru_bwd_bf16", tr, s, D * nper);
     return rc;
 }

@@ -14,6 +14,8 @@ constexpr long long SPIN_CYCLES = 6000000000LL;   // ~3 s: a broken pipeline tra
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle, OOB reads as 0
 int make_bf16_map(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows);
+// same matrix viewed as [cols/64][rows][64]: one box = box_chunks K-major swizzled [box_rows x 64] tiles back to back
+int make_bf16_map_chunked(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_rows, int box_chunks);
 // same, for an MN-major operand stored [K rows, MN cols] (ld elements per row): box = [64 k-rows, 64 mn-cols]
 int make_bf16_map_mn(CUtensorMap* map, const void* base, long long k_rows, int mn_cols, int ld);
 
@@ -59,6 +61,11 @@ __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
