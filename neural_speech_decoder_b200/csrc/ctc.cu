@@ -2,7 +2,7 @@
 //
 // K4 replaces log_softmax(2).permute(1,0,2) + torch.nn.CTCLoss(blank=0, reduction="mean",
 // zero_infinity=True) + its backward (reference neural_decoder_trainer.py:139-141, 210, 213-218, 242, 252).
-// One CTA (two warps) per utterance: warp 0 runs the alpha recursion forward in time while warp 1 runs
+// One CTA per utterance: warp 0 runs the alpha recursion forward in time while warp 1 runs
 // the beta recursion backward in time over the blank-extended label lattice in log space; both warps
 // then form the occupancy sums and the gradient.  Every reduction has a fixed order, so the result is
 // bit-reproducible run to run.  Lengths and targets stay on the device (the reference syncs them to host).
@@ -12,7 +12,8 @@
 
 namespace nsd {
 
-constexpr int CTC_THREADS = 64;
+constexpr int CTC_THREADS = 256;     // warps 0/1 run the alpha/beta recursions; all 8 share the per-frame work before and after
+constexpr int CTC_WARPS = CTC_THREADS / 32;
 #define NSD_NEG_INF (-INFINITY)
 
 __device__ __forceinline__ float lse2f(float a, float b) {
@@ -46,8 +47,8 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(CtcParams p) {
     int* nxt = ext + SP;                                              // [SP]   next lattice slot with the same label (or -1)
     int* isfirst = nxt + SP;                                          // [SP]   1 if no earlier slot carries the same label
     float* rowbuf = reinterpret_cast<float*>(isfirst + SP);           // [2 warps][2][SP+2]  alpha / beta ping-pong
-    float* vbuf = rowbuf + 2 * 2 * (SP + 2);                          // [2 warps][SP]
-    float* occ = vbuf + 2 * SP;                                       // [2 warps][C]
+    float* vbuf = rowbuf + 2 * 2 * (SP + 2);                          // [CTC_WARPS][SP]
+    float* occ = vbuf + CTC_WARPS * SP;                               // [CTC_WARPS][C]
     __shared__ float s_nll;
     __shared__ int s_last;
 
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(CtcParams p) {
 
     // phase 1: warp 0 -> alpha (t ascending), warp 1 -> beta (t descending)
     if (il > 0) {
-        float* buf = rowbuf + warp * 2 * (SP + 2);
+        float* buf = rowbuf + (warp & 1) * 2 * (SP + 2);
         if (warp == 0) {
             float* prev = buf + 2;                 // two -inf guard cells in front for s-1, s-2
             float* cur = buf + (SP + 2) + 2;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(CtcParams p) {
                 __syncwarp();
                 float* tmp = prev; prev = cur; cur = tmp;
             }
-        } else if (p.grad != nullptr) {
+        } else if (warp == 1 && p.grad != nullptr) {
             float* prev = buf;                     // two -inf guard cells after the row for s+1, s+2
             float* cur = buf + (SP + 2);
             for (int s = lane; s < S + 2; s += 32) {
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(CtcParams p) {
 
     float* myv = vbuf + warp * SP;
     float* myocc = occ + warp * C;
-    for (int t = warp; t < T && p.grad != nullptr; t += 2) {
+    for (int t = warp; t < T && p.grad != nullptr; t += CTC_WARPS) {
         float* g = p.grad + (int64_t)t * p.st + (int64_t)b * p.sb;
         if (t >= il || !feasible) {
             for (int c = lane; c < C; c += 32) g[(int64_t)c * p.sc] = 0.f;
@@ -332,7 +333,7 @@ int nsd_ctc_loss(const float* act, int64_t st, int64_t sb, int64_t sc, int is_lo
     p.beta = p.alpha + (size_t)B * T * p.SP;
     cudaStream_t s = (cudaStream_t)stream;
     NSD_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s));
-    const size_t smem = sizeof(int) * 3 * p.SP + sizeof(float) * (4 * (size_t)(p.SP + 2) + 2 * (size_t)p.SP + 2 * (size_t)C);
+    const size_t smem = sizeof(int) * 3 * p.SP + sizeof(float) * (4 * (size_t)(p.SP + 2) + CTC_WARPS * (size_t)p.SP + CTC_WARPS * (size_t)C);
     NSD_CHECK_ARG(smem <= 200 * 1024, "ctc_loss: max_tgt=%d C=%d need %zu B shared memory", max_tgt, C, smem);
     if (smem > 48 * 1024) NSD_CUDA(cudaFuncSetAttribute(ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctc_kernel<<<B, CTC_THREADS, smem, s>>>(p);
