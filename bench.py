@@ -263,9 +263,17 @@ def run_ours(a):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = gemm_flops_per_step(a, frames) * a.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    traffic, traffic_note = None, "no ncu capture found under profiles/"
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        traffic = tj["dram_bytes"]
+        traffic_note = (f"ncu --set full, {tj['launch']}: dram read+write {tj['dram_bytes'] / 1e6:.0f} MB vs "
+                        f"{tj['algorithmic_bytes'] / 1e6:.0f} MB algorithmic operand+result bytes of that launch")
+    except Exception:
+        pass
     roofline = {"kernel": "K2 time-batched GEMMs (nsd_gemm_%s)" % a.precision, "bound": "tensor",
                 "achieved": round(ach, 2) if ach else None, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(ach / peak_tf, 4) if ach else None, "traffic": None,
+                "frac": round(ach / peak_tf, 4) if ach else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches_per_step": gemm_calls // max(1, a.steps), "share_of_step": round(gemm_ms / ms, 4)}
     h2d = sum(t.numel() * t.element_size() for t in host)

@@ -39,5 +39,24 @@ def rep(src, dst):
                 if base in KEYS:
                     f.write(f"{base:80s} {r[i]:>16s} {units[i]}\n")
 
+def traffic(src, dst):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first kernel in an `ncu --set full` report -> small JSON that
+    bench.py quotes as roofline.traffic (the layer-0 W_ih forward GEMM, the largest launch of the step)."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, r = rows[0], rows[1], rows[2]
+    def val(key):
+        i = [j for j, h in enumerate(hdr) if h.endswith(key)][0]
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        return float(r[i].replace(",", "")) * mult
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    json.dump({"kernel": r[hdr.index("Kernel Name")][:80], "launch": "layer-0 W_ih forward 7552x6144x8192 (largest K2 launch of the step)",
+               "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr,
+               "algorithmic_bytes": 7552 * 8192 * 2 + 6144 * 8192 * 2 + 7552 * 6144 * 4,
+               "duration_us": val("gpu__time_duration.sum") / (1e3 if units[[j for j, h in enumerate(hdr) if h.endswith("gpu__time_duration.sum")][0]] == "ns" else 1),
+               "source": src}, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "rep": rep, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
