@@ -48,13 +48,13 @@ def traffic(src, dst):
     hdr, units, r = rows[0], rows[1], rows[2]
     def val(key):
         i = [j for j, h in enumerate(hdr) if h.endswith(key)][0]
-        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}[units[i]]
         return float(r[i].replace(",", "")) * mult
     rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
     json.dump({"kernel": r[hdr.index("Kernel Name")][:80], "launch": "layer-0 W_ih forward 7552x6144x8192 (largest K2 launch of the step)",
                "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr,
                "algorithmic_bytes": 7552 * 8192 * 2 + 6144 * 8192 * 2 + 7552 * 6144 * 4,
-               "duration_us": val("gpu__time_duration.sum") / (1e3 if units[[j for j, h in enumerate(hdr) if h.endswith("gpu__time_duration.sum")][0]] == "ns" else 1),
+               "duration_us": val("gpu__time_duration.sum"),
                "source": src}, open(dst, "w"), indent=1)
 
 
