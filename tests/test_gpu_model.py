@@ -212,3 +212,21 @@ def test_bf16_weight_shadows_follow_the_parameters():
     ref.load_state_dict(m.state_dict())
     ref.eval()
     assert torch.equal(ref.forward(X, day).detach(), after)
+
+
+def test_batch_prefetcher_yields_identical_batches_in_order():
+    """trainer:185-191 replacement: batches staged on a copy stream arrive complete and in order."""
+    host = []
+    for i in range(5):
+        X, y, X_len, y_len, day = make_batch(3, 64 + 4 * i, n_feat=32, n_days=4, n_classes=10, seed=i, kernel_len=16, stride_len=4)
+        host.append(tuple(t.pin_memory() for t in (X, y, X_len, y_len, day)))
+    got = []
+    for dev_batch in nsd.BatchPrefetcher(iter(host), DEV):
+        assert all(t.is_cuda for t in dev_batch)
+        got.append(tuple(t.clone() for t in dev_batch))
+    torch.cuda.synchronize()
+    assert len(got) == 5
+    for h, g in zip(host, got):
+        assert all(torch.equal(a, b.cpu()) for a, b in zip(h, g))
+    with pytest.raises(RuntimeError):
+        nsd.BatchPrefetcher(iter(host), "cpu")
