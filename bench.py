@@ -48,8 +48,9 @@ def parse():
     ap.add_argument("--uni", action="store_true", help="unidirectional GRU (class default) instead of the training default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
-    ap.add_argument("--mode", default="train", choices=["train", "infer"],
-                    help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32")
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "stream"],
+                    help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32; "
+                         "stream: the same model fed 4 bins (80 ms) at a time through StreamingDecoder")
     return ap.parse_args()
 
 
@@ -359,9 +360,46 @@ def run_infer(a):
     nsd.set_default_precision("bf16")
 
 
+def run_stream(a):
+    """BASELINE configs[3], streaming form: 4 new 20 ms bins per call (one output frame), host bins in, argmax id out.
+    Reported per call = per 80 ms of signal; per-bin = /4.  Real-time factor = 80 ms / latency."""
+    import torch
+    import neural_speech_decoder_b200 as nsd
+    from neural_speech_decoder_b200.synthetic import make_batch
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    nsd.set_default_precision("bf16")
+    torch.manual_seed(0)
+    model = nsd.GRUDecoder(device="cuda", bidirectional=False, **{**MODEL_KW, "dropout": 0.0}).to(dev).eval()
+    for B in (1, 32):
+        X, y, X_len, y_len, day = make_batch(B, a.T, seed=2)
+        X = X.pin_memory()
+        sd = nsd.StreamingDecoder(model, B, day)
+        lat = []
+        for rep in range(2):                                    # first pass warms up
+            sd.reset()
+            lat = []
+            for pos in range(0, a.T, 4):
+                t0 = time.perf_counter()
+                o = sd.push(X[:, pos:pos + 4].to(dev, non_blocking=True))
+                ids = o.argmax(-1).cpu() if o is not None else None
+                if ids is None:
+                    torch.cuda.synchronize()
+                lat.append(time.perf_counter() - t0)
+            sd.finish()
+        steady = sorted(lat[len(lat) // 4:])
+        med, p99 = steady[len(steady) // 2], steady[int(len(steady) * 0.99) - 1]
+        print(json.dumps({"metric": "streaming inference latency per 4-bin (80 ms) push, unidirectional GRUDecoder, greedy id out",
+                          "batch": B, "dtype": "bf16", "us_per_push_median": round(med * 1e6, 1), "us_per_push_p99": round(p99 * 1e6, 1),
+                          "us_per_20ms_bin": round(med * 1e6 / 4, 1), "real_time_factor": round(0.080 / med, 1),
+                          "lookahead_bins": 10, "pushes": len(steady), "impl": "ours", "data": "synthetic"}), flush=True)
+
+
 if __name__ == "__main__":
     args = parse()
-    if args.mode == "infer":
+    if args.mode == "stream":
+        run_stream(args)
+    elif args.mode == "infer":
         run_infer(args)
     elif args.impl == "reference":
         run_reference(args)

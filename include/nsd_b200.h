@@ -131,10 +131,14 @@ size_t nsd_gru_bwd_workspace(int B, int H);
  * with direction d at column d*H (the bf16 copy is what the CTAs exchange between steps and the next layer's GEMM
  * operand); r,z,n,hn are [D][T'*B][H] (all NULL to skip).  Requires H % 64 == 0.  workspace: nsd_gru_tc_workspace.
  * Fused inter-layer dropout (model.py:55): if hdrop_bf16 != NULL it receives nsd_dropout(hseq_bf16, p_drop, seed)
- * (same mask, same rounding) as a second [T'*B, ldh] bf16 tensor -- the next layer's input in train mode. */
+ * (same mask, same rounding) as a second [T'*B, ldh] bf16 tensor -- the next layer's input in train mode.
+ * Initial state (streaming inference; D == 1, reverse0 == 0 only): h0 != NULL is [B, ldh] f32 and
+ * hseq_bf16 must then hold T'*B + B rows whose FIRST B rows are bf16(h0); the states h_0..h_{T'-1} are written after
+ * them.  h0 == NULL is the reference's zero initial state (model.py:104-117). */
 int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
                      int reverse0, float* hseq, void* hseq_bf16, int ldh, float* r, float* z, float* n, float* hn,
-                     void* hdrop_bf16, float p_drop, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
+                     void* hdrop_bf16, float p_drop, uint64_t seed, const float* h0, void* workspace, size_t workspace_bytes,
+                     void* stream);
 /* BPTT of the above.  w_hhT_bf16 is the bf16 TRANSPOSE of each direction's W_hh stacked to [D*H, 3H].  Writes
  * dgi_bf16 = [dr~,dz~,dn~] and dgh_bf16 = [dr~,dz~,dn~*r], both [T'*B, ldg] bf16 with direction d at column d*3H.
  * p_drop > 0: dhseq is the gradient w.r.t. the DROPPED output (mask of nsd_dropout(., p_drop, seed) over the

@@ -39,7 +39,7 @@ SIGNATURES = {
     "nsd_gru_fwd_f32": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]),
     "nsd_gru_bwd_f32": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp, vp, sz, vp]),
     "nsd_gru_bwd_workspace": (sz, [i32, i32]),
-    "nsd_gru_fwd_bf16": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, f32, u64, vp, sz, vp]),
+    "nsd_gru_fwd_bf16": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, f32, u64, vp, vp, sz, vp]),
     "nsd_gru_bwd_bf16": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, f32, u64, vp, vp, vp, sz, vp]),
     "nsd_gru_tc_workspace": (sz, [i32, i32, i32]),
     "nsd_dropout": (i32, [vp, vp, i32, sz, f32, u64, vp]),

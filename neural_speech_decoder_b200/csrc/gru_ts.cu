@@ -108,6 +108,8 @@ struct Common {
     int nper;                               // CTAs per direction
     int G;                                  // batch groups of NG rows
     int ktot, kper;                         // reduction length (H forward, 3H BPTT) and its share per CTA (multiple of 16)
+    int s0, row_off;                        // first step with a recurrent term (0 when an initial state is given, else 1); rows the
+                                            // exchanged-state tensor is shifted by (B when its first B rows hold the initial state)
     int chunked;                            // 1: K shares are whole 64-wide chunks -> single 3-D TMA box per operand
     int cs, upz, nzone;                         // units per zone (= per cluster) and zones per direction
     unsigned int* counters;                 // [D][G][nzone] step counters, CNT_STRIDE apart: CS arrivals per step
@@ -232,7 +234,7 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
         }
         const bool poller = lane < nbox || lane == 31;
         for (int g0 = 0; g0 < c.G; g0 += 2) {
-            for (int s = 1; s < c.Tp; ++s) {
+            for (int s = c.s0; s < c.Tp; ++s) {
                 int t_src;
                 if (!bptt) { const int t = rev ? (c.Tp - 1 - s) : s; t_src = rev ? t + 1 : t - 1; }
                 else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
@@ -251,11 +253,11 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                         // K share aligned to 64-wide chunks: the whole operand (nbox swizzled tiles) in one TMA instruction
                         if (lane == 0) {
                             asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes (acquired above) -> TMA reads
-                            tma_load_3d(tmB3, &sm.full[gg], sm.b + (size_t)(gg * nbox_max) * BOX_BYTES, 0, t_src * c.B + g * NG, (b_col0 + k_lo) / BK);
+                            tma_load_3d(tmB3, &sm.full[gg], sm.b + (size_t)(gg * nbox_max) * BOX_BYTES, 0, t_src * c.B + g * NG + c.row_off, (b_col0 + k_lo) / BK);
                         }
                     } else if (lane < nbox) {
                         asm volatile("fence.proxy.async.global;" ::: "memory");
-                        tma_load_2d(tmB, &sm.full[gg], sm.b + (size_t)(gg * nbox_max + lane) * BOX_BYTES, b_col0 + k_lo + lane * BK, t_src * c.B + g * NG);
+                        tma_load_2d(tmB, &sm.full[gg], sm.b + (size_t)(gg * nbox_max + lane) * BOX_BYTES, b_col0 + k_lo + lane * BK, t_src * c.B + g * NG + c.row_off);
                     } else if (lane == 0) {
                         mbar_arrive(&sm.full[gg]);
                     }
@@ -269,7 +271,7 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
         constexpr uint32_t idesc = make_idesc_bf16(128, NG);
         uint32_t n[2] = {0u, 0u};
         for (int g0 = 0; g0 < c.G; g0 += 2) {
-            for (int s = 1; s < c.Tp; ++s) {
+            for (int s = c.s0; s < c.Tp; ++s) {
                 for (int gg = 0; gg < 2 && g0 + gg < c.G; ++gg) {
                     mbar_wait(&sm.full[gg], n[gg] & 1);
                     ++n[gg];
@@ -386,6 +388,7 @@ struct FwdParams {
     const float* b_hh;                    // [D*3H]
     float* hseq; __nv_bfloat16* hseq_bf; int ldh;    // [Tp*B, D*H]; the bf16 copy is what the other CTAs TMA-load
     float* r; float* z; float* n; float* hn;         // [D][Tp*B][H] or null
+    const float* h0;                                 // [B, ldh] initial state (fp32) or null; its bf16 copy = first B rows of hseq_bf
     __nv_bfloat16* hdrop; uint32_t drop_thresh; float inv_keep; uint64_t seed;   // fused inter-layer dropout output (or null)
 };
 
@@ -440,6 +443,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             const int b = grp * NG + bl;
             const bool row_ok = b < B;
             float k_h[4] = {0.f, 0.f, 0.f, 0.f};          // h_{t-1} of this thread's (row, 4 units), fp32, in registers
+            if (p.h0 != nullptr && row_ok) ld4g(p.h0 + (size_t)b * p.ldh + d * H + ub, k_h);
             for (int s = 0; s < c.Tp; ++s) {
                 const int t = rev ? (c.Tp - 1 - s) : s;
                 const size_t m = (size_t)t * B + b;
@@ -459,7 +463,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                 for (int g = 0; g < 3; ++g)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
-                if (s > 0) {
+                if (s >= c.s0) {
                     if (te == 0) mbar_expect_tx(&sm.inbox_bar[gg], (uint32_t)MSGS);
                     mbar_wait(&sm.tmem_full[gg], it & 1);
                     tcgen05_fence_after();
@@ -491,7 +495,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                         k_h[i] = fmaf(zz[i], k_h[i] - nn[i], nn[i]);        // (1-z)*n + z*h_prev
                     }
                     // the bf16 state is what the other CTAs wait for: store it first, publish, then write the rest
-                    st4_bf16(p.hseq_bf + m * p.ldh + d * H + ub, k_h);
+                    st4_bf16(p.hseq_bf + (m + c.row_off) * p.ldh + d * H + ub, k_h);
                 }
                 if (te == 0 && grp == 0) stamp(c, sm.trace, s, 6);
                 wg_bar_sync(gg);                             // (the consumer fences generic->async proxy after its acquire)
@@ -772,7 +776,7 @@ size_t nsd_gru_tc_workspace(int B, int H, int D) {
 
 int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
                      int reverse0, float* hseq, void* hseq_bf16, int ldh, float* r, float* z, float* n, float* hn,
-                     void* hdrop_bf16, float p_drop, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
+                     void* hdrop_bf16, float p_drop, uint64_t seed, const float* h0, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace nsd;
     using namespace nsd::rts;
     constexpr int CS = 4, U = 16;
@@ -785,7 +789,8 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     cudaStream_t s = (cudaStream_t)stream;
     NSD_CUDA(cudaMemsetAsync(workspace, 0, nsd_gru_tc_workspace(B, H, D), s));
     CUtensorMap tmH;
-    rc = make_bf16_map(&tmH, hseq_bf16, (long long)Tp * B, D * H, ldh, NG);
+    const int row_off = h0 ? B : 0;       // with an initial state, hseq_bf16 has Tp*B + B rows: [bf16(h0) | h_0 .. h_{Tp-1}]
+    rc = make_bf16_map(&tmH, hseq_bf16, (long long)Tp * B + row_off, D * H, ldh, NG);
     if (rc) return rc;
     FwdParams p;
     long long* tr = trace_begin();
@@ -793,8 +798,9 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     const int kper = round_up(cdiv(H, CS), UMMA_K);
     const int chunked = (kper % BK == 0 && H % BK == 0) ? 1 : 0;
     CUtensorMap tmH3 = tmH;
-    if (chunked) { rc = make_bf16_map_chunked(&tmH3, hseq_bf16, (long long)Tp * B, D * H, ldh, NG, kper / BK); if (rc) return rc; }
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, kper, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    if (chunked) { rc = make_bf16_map_chunked(&tmH3, hseq_bf16, (long long)Tp * B + row_off, D * H, ldh, NG, kper / BK); if (rc) return rc; }
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, kper, h0 ? 0 : 1, row_off, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    p.h0 = h0;
     p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
@@ -830,7 +836,7 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     const int chunked = (kper % BK == 0) ? 1 : 0;
     CUtensorMap tmG3 = tmG;
     if (chunked) { rc = make_bf16_map_chunked(&tmG3, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG, kper / BK); if (rc) return rc; }
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, kper, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, kper, 1, 0, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
     p.wT = reinterpret_cast<const __nv_bfloat16*>(w_hhT_bf16);
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;

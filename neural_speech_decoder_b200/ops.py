@@ -130,19 +130,26 @@ def gru_bwd_f32(dhseq, lddh, dh_off, hseq, ldh, h_off, saves, w_hh, Tp, B, H, re
          nbytes, stream())
 
 
-def gru_fwd_bf16(gi, w_hh_bf, b_hh, Tp, B, H, D, reverse0, want_saves, p_drop: float = 0.0, seed: int = 0):
-    """-> (hseq f32 [Tp*B, D*H], hseq bf16, saves (r,z,n,hn) each [D,Tp*B,H] or None[, dropped bf16 copy if p_drop > 0])."""
+def gru_fwd_bf16(gi, w_hh_bf, b_hh, Tp, B, H, D, reverse0, want_saves, p_drop: float = 0.0, seed: int = 0, h0=None):
+    """-> (hseq f32 [Tp*B, D*H], hseq bf16, saves (r,z,n,hn) each [D,Tp*B,H] or None[, dropped bf16 copy if p_drop > 0]).
+    ``h0`` ([B, H] f32, one forward direction only): initial state instead of the reference's zeros (streaming)."""
     dev = gi.device
     M = Tp * B
     hseq = torch.empty((M, D * H), device=dev, dtype=torch.float32)
-    hseq_bf = torch.empty((M, D * H), device=dev, dtype=torch.bfloat16)
+    if h0 is not None:
+        assert D == 1 and not reverse0 and h0.shape == (B, H) and h0.dtype == torch.float32 and h0.is_contiguous()
+        full_bf = torch.empty((M + B, H), device=dev, dtype=torch.bfloat16)
+        call("nsd_cast", ptr(h0), dtype_code(h0.dtype), ptr(full_bf), dtype_code(torch.bfloat16), h0.numel(), stream())
+        hseq_bf = full_bf[B:]
+    else:
+        full_bf = hseq_bf = torch.empty((M, D * H), device=dev, dtype=torch.bfloat16)
     sv = tuple(torch.empty((D, M, H), device=dev, dtype=torch.float32) for _ in range(4)) if want_saves else (None,) * 4
     nbytes = _lib.lib().nsd_gru_tc_workspace(B, H, D)
     ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
     hdrop = torch.empty_like(hseq_bf) if p_drop > 0 else None
     call("nsd_gru_fwd_bf16", ptr(gi), gi.stride(0), ptr(w_hh_bf), ptr(b_hh), Tp, B, H, D, int(reverse0), ptr(hseq),
-         ptr(hseq_bf), D * H, ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), ptr(hdrop), float(p_drop), int(seed),
-         ptr(ws), nbytes, stream())
+         ptr(full_bf), D * H, ptr(sv[0]), ptr(sv[1]), ptr(sv[2]), ptr(sv[3]), ptr(hdrop), float(p_drop), int(seed),
+         ptr(h0), ptr(ws), nbytes, stream())
     if p_drop > 0:
         return hseq, hseq_bf, (sv if want_saves else None), hdrop
     return hseq, hseq_bf, (sv if want_saves else None)
