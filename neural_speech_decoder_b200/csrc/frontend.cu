@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
                         if (i < rows) {
                             const float a0 = acc[mt][j][2 * h], a1 = acc[mt][j][2 * h + 1];
                             const float v0 = a0 / (1.0f + fabsf(a0)), v1 = a1 / (1.0f + fabsf(a1));
-                            float* zr = zring + (size_t)((rb + i) % p.ring) * NP + col;
+                            float* zr = zring + (size_t)((rb + i) & (p.ring - 1)) * NP + col;
                             zr[0] = v0; zr[1] = v1;
                             *reinterpret_cast<float2*>(zb + (size_t)(rb + i) * N + col) = make_float2(v0, v1);
                         }
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
             for (int i = 0; i < FE_TT; ++i) {
                 if (i < rows) {
                     float v = acc[i] / (1.0f + fabsf(acc[i]));
-                    zring[(size_t)((rb + i) % p.ring) * NP + kc] = v;
+                    zring[(size_t)((rb + i) & (p.ring - 1)) * NP + kc] = v;
                     zb[(size_t)(rb + i) * N + kc] = v;
                 }
             }
@@ -208,16 +208,22 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
         const int F = N * K;
         if ((K & 3) == 0) {
             const int f4n = F >> 2;
+            // thread-invariant patch coordinates when the thread stride (4 * FE_THREADS features) is a multiple of K
+            const bool fixed_kk = ((4 * FE_THREADS) % K) == 0;
+            const int c_first = (4 * tid) / K, kk_first = (4 * tid) - c_first * K, c_step = (4 * FE_THREADS) / K;
+            const int rmask = p.ring - 1;
             for (int j = jnext; j < jend; ++j) {
                 OutT* orow = reinterpret_cast<OutT*>(p.patches) + ((size_t)j * p.B + b) * F;
-                for (int q = tid; q < f4n; q += FE_THREADS) {
-                    int f = q << 2;
-                    int c = f / K, kk = f - c * K;
-                    int r = j * S + kk;
-                    float v0 = zring[(size_t)((r + 0) % p.ring) * NP + c];
-                    float v1 = zring[(size_t)((r + 1) % p.ring) * NP + c];
-                    float v2 = zring[(size_t)((r + 2) % p.ring) * NP + c];
-                    float v3 = zring[(size_t)((r + 3) % p.ring) * NP + c];
+                int c = c_first;
+                for (int q = tid; q < f4n; q += FE_THREADS, c += c_step) {
+                    int kk = kk_first;
+                    if (!fixed_kk) { const int f = q << 2; c = f / K; kk = f - c * K; }
+                    const int r = j * S + kk;
+                    const float* zc = zring + c;
+                    float v0 = zc[(size_t)((r + 0) & rmask) * NP];
+                    float v1 = zc[(size_t)((r + 1) & rmask) * NP];
+                    float v2 = zc[(size_t)((r + 2) & rmask) * NP];
+                    float v3 = zc[(size_t)((r + 3) & rmask) * NP];
                     if constexpr (sizeof(OutT) == 4) {
                         reinterpret_cast<float4*>(orow)[q] = make_float4(v0, v1, v2, v3);
                     } else {
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
                 OutT* orow = reinterpret_cast<OutT*>(p.patches) + ((size_t)j * p.B + b) * F;
                 for (int f = tid; f < F; f += FE_THREADS) {
                     int c = f / K, kk = f - c * K;
-                    orow[f] = from_f32<OutT>(zring[(size_t)((j * S + kk) % p.ring) * NP + c]);
+                    orow[f] = from_f32<OutT>(zring[(size_t)((j * S + kk) & (p.ring - 1)) * NP + c]);
                 }
             }
         }
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_kernel(FrontendBwd
                 if (kl < cn) {
                     for (int rr = 0; rr < nr; ++rr) {
                         const int t = rc + rr;
-                        float dz = ring[(size_t)(t % p.ring) * RP + kl];
+                        float dz = ring[(size_t)(t & (p.ring - 1)) * RP + kl];
                         float zz = __ldg(zb + (size_t)t * N + c0 + kl);
                         float s = 1.0f - fabsf(zz);
                         float dpre = dz * s * s;
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_kernel(FrontendBwd
                 __syncthreads();
                 // consumed rows go back to zero for their next use
                 for (int i = tid; i < nr * FB_CN; i += FB_THREADS)
-                    ring[(size_t)((rc + i / FB_CN) % p.ring) * RP + (i % FB_CN)] = 0.f;
+                    ring[(size_t)((rc + i / FB_CN) & (p.ring - 1)) * RP + (i % FB_CN)] = 0.f;
                 __syncthreads();
             }
         };
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_kernel(FrontendBwd
                 for (int g = 0; g < ng; ++g) {
                     const float* st = stage + (size_t)g * FB_CN * KP + cl * KP;
                     const int rbase = (jg + g) * S;
-                    for (int kk = ph; kk < K; kk += S) ring[(size_t)((rbase + kk) % p.ring) * RP + cl] += st[kk];
+                    for (int kk = ph; kk < K; kk += S) ring[(size_t)((rbase + kk) & (p.ring - 1)) * RP + cl] += st[kk];
                 }
             }
             __syncthreads();
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_tc_kernel(Frontend
                     float dpre = 0.f;
                     if (rr < nr) {
                         const float sg = 1.0f - fabsf(zz[q]);
-                        dpre = ring[(size_t)((rc + rr) % p.ring) * RP + kl] * sg * sg;
+                        dpre = ring[(size_t)((rc + rr) & (p.ring - 1)) * RP + kl] * sg * sg;
                     }
                     bacc += dpre;
                     dp_s[(size_t)rr * NDP + kl] = __float2bfloat16_rn(dpre);
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_tc_kernel(Frontend
             }
             // consumed rows go back to zero for their next use
             for (int i = tid; i < nr * FB_CN; i += FB_THREADS)
-                ring[(size_t)((rc + i / FB_CN) % p.ring) * RP + (i % FB_CN)] = 0.f;
+                ring[(size_t)((rc + i / FB_CN) & (p.ring - 1)) * RP + (i % FB_CN)] = 0.f;
             __syncthreads();
         }
     };
@@ -483,7 +489,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_tc_kernel(Frontend
             for (int g = 0; g < ng; ++g) {
                 const float* st = stage + (size_t)g * FB_CN * KP + cl * KP;
                 const int rbase = (jg + g) * S;
-                for (int kk = ph; kk < K; kk += S) ring[(size_t)((rbase + kk) % p.ring) * RP + cl] += st[kk];
+                for (int kk = ph; kk < K; kk += S) ring[(size_t)((rbase + kk) & (p.ring - 1)) * RP + cl] += st[kk];
             }
         }
         __syncthreads();
@@ -577,7 +583,8 @@ int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w,
     p.Tp = (T - kernel_len) / stride_len + 1;
     const int nseg = pick_segments(B, p.Tp, sm_count(), stride_len, kernel_len);
     p.frames_per_seg = cdiv(p.Tp, nseg);
-    p.ring = kernel_len + FE_TT;
+    p.ring = 1;
+    while (p.ring < kernel_len + FE_TT) p.ring <<= 1;      // power of two: ring rows are addressed with a mask
     // bf16 patches (the tensor-core model path) with 64 | N <= 256: day affine on mma.sync; otherwise the exact fp32 FFMA form
     const int ntw = (patches_dtype == NSD_BF16 && N % 64 == 0 && N <= 256) ? N / 64 : 0;
     size_t smem = sizeof(float) * (64 + (size_t)(FE_TT + ntaps - 1) * N + (size_t)p.ring * (N + 1) +
@@ -633,7 +640,8 @@ int nsd_frontend_bwd(const void* dpatches, int dpatches_dtype, const float* ys, 
     p.B = B; p.T = T; p.N = N; p.K = kernel_len; p.S = stride_len;
     p.Tp = (T - kernel_len) / stride_len + 1;
     p.KP = ((kernel_len + 3) / 4) * 4 + 4;
-    p.ring = (FB_G - 1) * stride_len + kernel_len;
+    p.ring = 1;
+    while (p.ring < (FB_G - 1) * stride_len + kernel_len) p.ring <<= 1;   // power of two: ring rows are addressed with a mask
     cudaStream_t s = (cudaStream_t)stream;
     const int mt = (dpatches_dtype == NSD_BF16 && (N == 128 || N == 256)) ? N / 128 : 0;
     if (mt) {
