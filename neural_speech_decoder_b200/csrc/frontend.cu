@@ -94,6 +94,11 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
         }
     }
 
+    // constant-offset noise of this thread's channel quad (valid when the staging loop's stride keeps the quad fixed)
+    const bool off_fixed = ((N & 3) == 0) && (FE_THREADS % (N >> 2)) == 0;
+    float4 off4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (noisy && off_fixed && p.offset_sd != 0.f) off4 = normal4(((size_t)b * N + 4 * (tid % (N >> 2))) >> 2, p.noise_seed, 1u);
+
     const int R0 = j0 * S, R1 = (j1 - 1) * S + K;   // z rows this CTA needs
     const float* xb = p.x + (size_t)b * T * N;
     float* ysb = p.ys + (size_t)b * T * N;
@@ -111,7 +116,16 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t >= 0 && t < T && rr < rows + ntaps - 1) {
                     v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)t * N) + c4);
-                    if (noisy) v = add_input_noise4(v, ((size_t)b * T + t) * N + 4 * c4, (size_t)b * N + 4 * c4, p.white_sd, p.offset_sd, p.noise_seed);
+                    if (noisy) {
+                        // same operations, in the same order, as add_input_noise4 (the stand-alone kernel); the per-utterance
+                        // offset does not depend on t: when the thread's channel quad is loop-invariant it is generated once
+                        if (p.white_sd != 0.f) v = add_input_noise4(v, ((size_t)b * T + t) * N + 4 * c4, 0, p.white_sd, 0.f, p.noise_seed);
+                        if (p.offset_sd != 0.f) {
+                            const float4 o = off_fixed ? off4 : normal4(((size_t)b * N + 4 * c4) >> 2, p.noise_seed, 1u);
+                            v.x = fmaf(p.offset_sd, o.x, v.x); v.y = fmaf(p.offset_sd, o.y, v.y);
+                            v.z = fmaf(p.offset_sd, o.z, v.z); v.w = fmaf(p.offset_sd, o.w, v.w);
+                        }
+                    }
                 }
                 reinterpret_cast<float4*>(xs + (size_t)rr * N)[c4] = v;
             }
