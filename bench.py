@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--T", type=int, default=500)
     ap.add_argument("--uni", action="store_true", help="unidirectional GRU (class default) instead of the training default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --batch is the GLOBAL batch, split evenly over the GPUs (default: weak, --batch per GPU)")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
     ap.add_argument("--mode", default="train", choices=["train", "infer", "stream"],
                     help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32; "
@@ -180,6 +181,10 @@ def run_ours(a):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    if a.strong:
+        if a.batch % world:
+            raise SystemExit(f"--strong: global batch {a.batch} is not divisible by {world} GPUs")
+        a.batch //= world                                  # per-GPU share of the fixed global batch
     import neural_speech_decoder_b200 as nsd
     from neural_speech_decoder_b200 import _lib
     from neural_speech_decoder_b200.parallel import GradSync
@@ -305,7 +310,7 @@ def run_ours(a):
                            "note": "both directions, all batch groups; 5 layers x %d sequential timesteps" % frames})
     h2d = sum(t.numel() * t.element_size() for t in host)
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "strong" if a.strong else "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic", "config": config_dict(a, world), "clocks": clocks,
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "roofline": roofline, "rooflines_other": others, "loss": float(lv)}

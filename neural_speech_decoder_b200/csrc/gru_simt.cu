@@ -181,6 +181,11 @@ __global__ void __launch_bounds__(GR_THREADS) gru_bwd_f32_kernel(GruBwdParams p)
                 for (int j0 = 0; j0 < H3; j0 += GR_KC) {
                     // the chunk [j0, j0+KC) lies in dgi columns (< 2H) and/or in dghn (>= 2H): stage piecewise
                     __syncthreads();
+                    if ((2 * H) % GR_KC == 0) {
+                        // the chunk lies wholly in the dgi columns (< 2H) or wholly in dghn: vectorised row staging
+                        if (j0 < 2 * H) stage_rows(ds, p.dgi + (size_t)tnext * B * p.ldgi, p.ldgi, b0, B, j0, 2 * H, tid);
+                        else stage_rows(ds, p.dghn + (size_t)tnext * B * H, H, b0, B, j0 - 2 * H, H, tid);
+                    } else
                     for (int i = tid; i < GR_BT * GR_KC; i += GR_THREADS) {
                         const int row = i / GR_KC, jj = i - row * GR_KC;
                         const int b = b0 + row, j = j0 + jj;
