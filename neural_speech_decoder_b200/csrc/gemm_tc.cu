@@ -17,9 +17,15 @@ namespace tc {
 constexpr int BM = 128;          // UMMA M (cta_group::1, all 128 TMEM lanes)
 constexpr int THREADS = 256;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int ACC_STAGES = 2;
+#ifndef NSD_ST256
+#define NSD_ST256 4
+#endif
+#ifndef NSD_ST2
+#define NSD_ST2 7
+#endif
 
 template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (BN == 256) ? NSD_ST256 : (BN == 128 ? 6 : 8);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -245,6 +251,234 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// =====================================================================================================================
+// Pair form (cta_group::2): the two CTAs of a cluster compute ONE 256 x 256 tile with a single stream of
+// tcgen05.mma.cta_group::2 instructions issued by the leader (cluster rank 0).  Each CTA stages its own 128 rows of A and
+// its own HALF of B (128 of the 256 n-rows) -- 32 KB per k-block instead of 48 KB -- so the ring is 6 stages deep instead
+// of 4: with 128x256 tiles the 4-stage ring cannot cover a TMA round trip at the rate the tensor pipe drains it (measured:
+// 3 stages cost 6-21 %).  Accumulator rows 0-127 live in the leader's TMEM, rows 128-255 in the peer's; each CTA's epilogue
+// drains its own half.  Barriers: full[s] in the leader, completed by BOTH CTAs' TMA loads (cta_group::2 TMA form, barrier
+// addressed in the leader's shared memory); empty[s] / tmem_full[a] in both CTAs (multicast commit); tmem_empty[a] in the leader (8 arrivals:
+// four epilogue warps of each CTA).
+struct Cfg2 {
+    static constexpr int BN = 256, STAGES = NSD_ST2;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 512;
+};
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// TMA into MY shared memory that completes a barrier which may live in the PAIR's other CTA (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {        // barrier that a peer CTA arrives on
+    if (mbar_try_wait_cl(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned int spins = 0;
+    while (!mbar_try_wait_cl(bar, parity)) {
+        if ((++spins & 0xFFFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
+            printf("nsd gemm_tc2: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+template <typename OutT, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C, int ldc,
+                const float* __restrict__ bias, float beta, int M, int N, int K) {
+    using cfg = Cfg2;
+    constexpr int BN = cfg::BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                             // [STAGES]  leader only: both CTAs' TMA -> MMA
+    uint64_t* peer_full = bars + cfg::STAGES;              // (unused slots)
+    (void)peer_full;
+    uint64_t* empty_bar = bars + 2 * cfg::STAGES;          // [STAGES]  MMA (multicast commit) -> my TMA
+    uint64_t* tmem_full = bars + 3 * cfg::STAGES;          // [ACC_STAGES] MMA (multicast commit) -> my epilogue
+    uint64_t* tmem_empty = tmem_full + ACC_STAGES;         // [ACC_STAGES] leader only: both epilogues -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int crank = (int)cluster_ctarank();
+    const bool leader = crank == 0;
+    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int nk = (K + BK - 1) / BK;
+    const int num_mw = (num_m + 1) / 2;
+    const int num_tiles = num_mw * num_n;
+    const int w_first = (int)cluster_id_x(), w_step = (int)nclusters_x();
+    auto coord_of = [&](int t) { TileCoord tc = tile_coord(t, num_mw, num_n, 8); tc.m_blk = tc.m_blk * 2 + crank; return tc; };
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: my 128 rows of A, my half of B =====================
+        // Both CTAs' loads complete the LEADER's full barrier (the one MMA issuer waits on one barrier per stage); the
+        // leader expects the bytes of both.
+        int stage = 0; uint32_t phase = 0;
+        for (int t = w_first; t < num_tiles; t += w_step) {
+            const TileCoord tc = coord_of(t);
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait_cl(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
+                    const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0u);
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * cfg::STAGE_BYTES);
+                    if constexpr (!A_MN) tma_load_2d_pair(&tmA, fb, sa, kb * BK, tc.m_blk * BM);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i) tma_load_2d_pair(&tmA, fb, sa + i * 8192, tc.m_blk * BM + 64 * i, kb * BK);
+                    }
+                    const int n0 = tc.n_blk * BN + crank * (BN / 2);
+                    if constexpr (!B_MN) tma_load_2d_pair(&tmB, fb, sa + cfg::A_BYTES, kb * BK, n0);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < BN / 128; ++i) tma_load_2d_pair(&tmB, fb, sa + cfg::A_BYTES + i * 8192, n0 + 64 * i, kb * BK);
+                    }
+                }
+                __syncwarp();
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===================== MMA issuer (leader only): one instruction stream drives both SMs =====================
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = w_first; t < num_tiles; t += w_step) {
+                mbar_wait_cl(&tmem_empty[acc], acc_phase ^ 1);       // both epilogues have drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait_cl(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + stage * cfg::STAGE_BYTES);
+                        const uint64_t adesc = A_MN ? make_mnmajor_sw128_desc(sa, 8192) : make_kmajor_sw128_desc(sa);
+                        const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(sa + cfg::A_BYTES, 8192) : make_kmajor_sw128_desc(sa + cfg::A_BYTES);
+                        constexpr uint64_t a_step = A_MN ? (2048 >> 4) : (32 >> 4), b_step = B_MN ? (2048 >> 4) : (32 >> 4);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma2_bf16(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
+                        umma2_commit_mc(&empty_bar[stage]);                  // both CTAs may refill this stage
+                        if (kb == nk - 1) umma2_commit_mc(&tmem_full[acc]);  // both epilogues may drain
+                    }
+                    __syncwarp();
+                    if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: my 128 rows of the 256-row tile =====================
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        const bool vec_ok = ((ldc % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        for (int t = w_first; t < num_tiles; t += w_step) {
+            const TileCoord tc = coord_of(t);
+            mbar_wait_cl(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = tc.m_blk * BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = tc.n_blk * BN + c0;
+                if (col0 >= N) break;                                 // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                if (row < M) {
+                    OutT* crow = C + (size_t)row * ldc + col0;
+                    if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
+                            if (bias) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+                                v0 += bv.x; v1 += bv.y; v2 += bv.z; v3 += bv.w;
+                            }
+                            if (beta != 0.f) {
+                                v0 = fmaf(beta, to_f32<OutT>(crow[i]), v0); v1 = fmaf(beta, to_f32<OutT>(crow[i + 1]), v1);
+                                v2 = fmaf(beta, to_f32<OutT>(crow[i + 2]), v2); v3 = fmaf(beta, to_f32<OutT>(crow[i + 3]), v3);
+                            }
+                            store4<OutT>(crow + i, v0, v1, v2, v3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (col0 + i < N) {
+                                float v = __uint_as_float(r[i]);
+                                if (bias) v += __ldg(bias + col0 + i);
+                                if (beta != 0.f) v = fmaf(beta, to_f32<OutT>(crow[i]), v);
+                                crow[i] = from_f32<OutT>(v);
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(&tmem_empty[acc]), 0u));      // the leader's barrier (also for the leader itself)
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // the pair's commits / remote arrivals target each other's shared memory
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled get_encode() {
     static PFN_cuTensorMapEncodeTiled fn = nullptr;
@@ -313,8 +547,40 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc
     return NSD_OK;
 }
 
+template <typename OutT, bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta, int M, int N, int K, cudaStream_t s) {
+    using cfg = Cfg2;
+    auto kern = gemm_tc2_kernel<OutT, A_MN, B_MN>;
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
+        attr_set = true;
+    }
+    const int items = cdiv(cdiv(M, BM), 2) * cdiv(N, cfg::BN);     // 256 x 256 tiles
+    const int grid = std::min(items, sm_count() / 2) * 2;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+    NSD_CUDA(cudaLaunchKernelEx(&lc, kern, ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K));
+    count_launch(1);
+    return NSD_OK;
+}
+
 }  // namespace tc
 }  // namespace nsd
+
+template <typename OutT>
+static int dispatch_layout2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta,
+                            int M, int N, int K, cudaStream_t s) {
+    using namespace nsd::tc;
+    if (!a_mn && !b_mn) return launch2<OutT, false, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (!a_mn && b_mn) return launch2<OutT, false, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (a_mn && b_mn) return launch2<OutT, true, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    return launch2<OutT, true, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+}
 
 template <int BN, typename OutT, int CL>
 static int dispatch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta,
@@ -352,6 +618,8 @@ extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const 
     rc = b_mn ? make_bf16_map_mn(&tb, B, K, N, ldb) : make_bf16_map(&tb, B, N, K, ldb, pair ? BN / 2 : BN);
     if (rc) return rc;
     const bool f32 = c_dtype == NSD_F32;
+    static const bool pair_mma = [] { const char* e = getenv("NSD_GEMM_PAIR"); return !(e && e[0] == '0'); }();      // debug: NSD_GEMM_PAIR=0 -> multicast form
+    if (pair && pair_mma) return f32 ? dispatch_layout2<float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout2<__nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
     if (pair) return f32 ? dispatch_layout<256, float, 2>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<256, __nv_bfloat16, 2>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
     if (BN == 256) return f32 ? dispatch_layout<256, float, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<256, __nv_bfloat16, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
     if (BN == 128) return f32 ? dispatch_layout<128, float, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<128, __nv_bfloat16, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
