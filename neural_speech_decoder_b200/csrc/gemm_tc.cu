@@ -3,10 +3,10 @@
 // Hand-written sm_100a kernel: TMA (cp.async.bulk.tensor, 128-byte swizzle) stages K-major A / B tiles through a
 // shared-memory ring, ONE elected thread issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16) with the
 // accumulator in tensor memory, and four epilogue warps drain TMEM with tcgen05.ld while the next tile's MMAs
-// run into the second accumulator stage.  Persistent: one CTA per SM walks a grouped tile order.
+// run into the second accumulator stage.  Persistent: one CTA per SM walks a grouped tile order.  Wide problems (N >= 192,
+// M > 128) run the PAIR form further down: clusters of two CTAs, tcgen05.mma.cta_group::2 on 256 x 256 tiles.
 // It backs the time-batched W_ih projections of nn.GRU (reference model.py:50-57, 119), their dgrad / wgrad and
-// the time-batched W_hh wgrad.  Both operands must be K-major ("NT"); the callers keep transposed bf16 copies
-// (nsd_cast_transpose) where the natural layout is not.
+// the time-batched W_hh wgrad.  Operands may be K-major or MN-major (both are native UMMA layouts).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -17,15 +17,9 @@ namespace tc {
 constexpr int BM = 128;          // UMMA M (cta_group::1, all 128 TMEM lanes)
 constexpr int THREADS = 256;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int ACC_STAGES = 2;
-#ifndef NSD_ST256
-#define NSD_ST256 4
-#endif
-#ifndef NSD_ST2
-#define NSD_ST2 7
-#endif
 
 template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? NSD_ST256 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -56,11 +50,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
     *reinterpret_cast<uint2*>(p) = u;
 }
 
-// CL = 2: a cluster of two CTAs works on two vertically adjacent tiles (m-blocks 2i, 2i+1; same n-block) in lockstep and
-// shares the B operand: each CTA fetches HALF of the B tile and TMA-multicasts it into both CTAs' shared memory, so a CTA
-// pulls 32 KB instead of 48 KB per k-block from L2 (148 SMs x 48 KB per 0.4 us is ~16 TB/s of L2 reads -- the bound the
-// single-CTA form runs into).  A stage may be refilled only when BOTH CTAs' MMAs have drained it: the MMA warps commit to
-// the empty barrier of both CTAs (multicast commit, barrier count 2).
+// cluster helpers of the pair form below
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t nclusters_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
@@ -68,17 +58,7 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-
-template <int BN, typename OutT, bool A_MN, bool B_MN, int CL>
+template <int BN, typename OutT, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C, int ldc,
                const float* __restrict__ bias, float beta, int M, int N, int K) {
@@ -94,21 +74,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
     const int nk = (K + BK - 1) / BK;
-    // work items: tiles (CL = 1) or vertical tile pairs (CL = 2) walked by CTAs / clusters; crank picks the pair's member
-    const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
-    const int num_mw = (num_m + CL - 1) / CL;
-    const int num_tiles = num_mw * num_n;
-    const int w_first = (CL == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
-    const int w_step = (CL == 2) ? (int)nclusters_x() : (int)gridDim.x;
-    auto coord_of = [&](int t) { TileCoord tc = tile_coord(t, num_mw, num_n, 16 / CL); tc.m_blk = tc.m_blk * CL + crank; return tc; };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
+        for (int i = 0; i < cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -118,7 +92,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tcgen05_fence_before();
     __syncthreads();
-    if constexpr (CL == 2) cluster_sync_all();      // the peer's barriers exist before anything is multicast into them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -127,8 +100,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Warp-uniform control flow around elect.sync keeps descriptors / coordinates in uniform registers; a
         // `lane == 0` branch makes the compiler wrap every UTMALDG / UTCHMMA in an R2UR waterfall loop.
         int stage = 0; uint32_t phase = 0;
-        for (int t = w_first; t < num_tiles; t += w_step) {
-            const TileCoord tc = coord_of(t);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const TileCoord tc = tile_coord(t, num_m, num_n);
             for (int kb = 0; kb < nk; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -139,17 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < BM / 64; ++i) tma_load_2d(&tmA, &full_bar[stage], sa + i * 8192, tc.m_blk * BM + 64 * i, kb * BK);
                     }
-                    if constexpr (CL == 2) {
-                        // my half of the B tile, multicast into both CTAs of the cluster (same offsets, same barrier)
-                        if constexpr (!B_MN) tma_load_2d_mc(&tmB, &full_bar[stage], sa + cfg::A_BYTES + crank * (cfg::B_BYTES / 2), kb * BK, tc.n_blk * BN + crank * (BN / 2), (uint16_t)3);
-                        else {
-#pragma unroll
-                            for (int i = 0; i < BN / 128; ++i) {
-                                const int ch = crank * (BN / 128) + i;
-                                tma_load_2d_mc(&tmB, &full_bar[stage], sa + cfg::A_BYTES + ch * 8192, tc.n_blk * BN + 64 * ch, kb * BK, (uint16_t)3);
-                            }
-                        }
-                    } else if constexpr (!B_MN) tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tc.n_blk * BN);
+                    if constexpr (!B_MN) tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES, kb * BK, tc.n_blk * BN);
                     else {
 #pragma unroll
                         for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, &full_bar[stage], sa + cfg::A_BYTES + i * 8192, tc.n_blk * BN + 64 * i, kb * BK);
@@ -164,7 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = w_first; t < num_tiles; t += w_step) {
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -180,8 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_bf16(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
-                    if constexpr (CL == 2) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in BOTH CTAs: the peer multicasts into it
-                    else umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
+                    umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
                     if (kb == nk - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
                 }
                 __syncwarp();
@@ -194,8 +156,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                                       // TMEM lane quadrant this warp may read
         int acc = 0; uint32_t acc_phase = 0;
         const bool vec_ok = ((ldc % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-        for (int t = w_first; t < num_tiles; t += w_step) {
-            const TileCoord tc = coord_of(t);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const TileCoord tc = tile_coord(t, num_m, num_n);
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int row = tc.m_blk * BM + q * 32 + lane;
@@ -244,7 +206,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tcgen05_fence_before();
     __syncthreads();
-    if constexpr (CL == 2) cluster_sync_all();      // the peer's last commits / multicasts target my shared memory
     if (warp == 2) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(cfg::TMEM_COLS) : "memory");
@@ -261,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // addressed in the leader's shared memory); empty[s] / tmem_full[a] in both CTAs (multicast commit); tmem_empty[a] in the leader (8 arrivals:
 // four epilogue warps of each CTA).
 struct Cfg2 {
-    static constexpr int BN = 256, STAGES = NSD_ST2;
+    static constexpr int BN = 256, STAGES = 7;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 512;
@@ -322,10 +283,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
     uint64_t* full_bar = bars;                             // [STAGES]  leader only: both CTAs' TMA -> MMA
-    uint64_t* peer_full = bars + cfg::STAGES;              // (unused slots)
-    (void)peer_full;
-    uint64_t* empty_bar = bars + 2 * cfg::STAGES;          // [STAGES]  MMA (multicast commit) -> my TMA
-    uint64_t* tmem_full = bars + 3 * cfg::STAGES;          // [ACC_STAGES] MMA (multicast commit) -> my epilogue
+    uint64_t* empty_bar = bars + cfg::STAGES;              // [STAGES]  MMA (multicast commit) -> my TMA
+    uint64_t* tmem_full = bars + 2 * cfg::STAGES;          // [ACC_STAGES] MMA (multicast commit) -> my epilogue
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;         // [ACC_STAGES] leader only: both epilogues -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
@@ -525,25 +484,19 @@ int make_bf16_map_mn(CUtensorMap* map, const void* base, long long k_rows, int m
     return make_bf16_map(map, base, k_rows, mn_cols, ld, BK);      // inner dim = mn (64-wide box), outer = k (64 rows)
 }
 
-template <int BN, typename OutT, bool A_MN, bool B_MN, int CL>
+template <int BN, typename OutT, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta, int M, int N, int K, cudaStream_t s) {
     using cfg = Cfg<BN>;
-    auto kern = gemm_tc_kernel<BN, OutT, A_MN, B_MN, CL>;
+    auto kern = gemm_tc_kernel<BN, OutT, A_MN, B_MN>;
     static bool attr_set = false;       // per instantiation
     if (!attr_set) {
         NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
         attr_set = true;
     }
-    const int items = cdiv(cdiv(M, BM), CL) * cdiv(N, BN);         // tiles, or vertical tile pairs
-    const int grid = std::min(items, sm_count() / CL) * CL;
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(grid); lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    lc.attrs = attr; lc.numAttrs = 1;
-    NSD_CUDA(cudaLaunchKernelEx(&lc, kern, ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K));
-    count_launch(1);
+    const int tiles = cdiv(M, BM) * cdiv(N, BN);
+    const int grid = std::min(tiles, sm_count());
+    kern<<<grid, THREADS, cfg::SMEM, s>>>(ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K);
+    NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 
@@ -582,14 +535,14 @@ static int dispatch_layout2(bool a_mn, bool b_mn, const CUtensorMap& ta, const C
     return launch2<OutT, true, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
 }
 
-template <int BN, typename OutT, int CL>
+template <int BN, typename OutT>
 static int dispatch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta,
                            int M, int N, int K, cudaStream_t s) {
     using namespace nsd::tc;
-    if (!a_mn && !b_mn) return launch<BN, OutT, false, false, CL>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (!a_mn && b_mn) return launch<BN, OutT, false, true, CL>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (a_mn && b_mn) return launch<BN, OutT, true, true, CL>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    return launch<BN, OutT, true, false, CL>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (!a_mn && !b_mn) return launch<BN, OutT, false, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (!a_mn && b_mn) return launch<BN, OutT, false, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (a_mn && b_mn) return launch<BN, OutT, true, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    return launch<BN, OutT, true, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
 }
 
 extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
@@ -612,16 +565,14 @@ extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const 
     CUtensorMap ta, tb;
     int rc = a_mn ? make_bf16_map_mn(&ta, A, K, M, lda) : make_bf16_map(&ta, A, M, K, lda, BM);
     if (rc) return rc;
-    // wide tiles with at least one vertical pair: clusters of two CTAs sharing (multicasting) the B tile
-    static const bool no_cluster = [] { const char* e = getenv("NSD_GEMM_NOCLUSTER"); return e && e[0] == '1'; }();
-    const bool pair = (BN == 256) && (M > BM) && !no_cluster;
+    // wide tiles with at least one vertical pair: the cta_group::2 form (256 x 256 tile over an SM pair)
+    static const bool no_pair = [] { const char* e = getenv("NSD_GEMM_PAIR"); return e && e[0] == '0'; }();      // debug: single-CTA form only
+    const bool pair = (BN == 256) && (M > BM) && !no_pair && sm_count() >= 2;
     rc = b_mn ? make_bf16_map_mn(&tb, B, K, N, ldb) : make_bf16_map(&tb, B, N, K, ldb, pair ? BN / 2 : BN);
     if (rc) return rc;
     const bool f32 = c_dtype == NSD_F32;
-    static const bool pair_mma = [] { const char* e = getenv("NSD_GEMM_PAIR"); return !(e && e[0] == '0'); }();      // debug: NSD_GEMM_PAIR=0 -> multicast form
-    if (pair && pair_mma) return f32 ? dispatch_layout2<float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout2<__nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (pair) return f32 ? dispatch_layout<256, float, 2>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<256, __nv_bfloat16, 2>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (BN == 256) return f32 ? dispatch_layout<256, float, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<256, __nv_bfloat16, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (BN == 128) return f32 ? dispatch_layout<128, float, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<128, __nv_bfloat16, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
-    return f32 ? dispatch_layout<64, float, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<64, __nv_bfloat16, 1>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (pair) return f32 ? dispatch_layout2<float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout2<__nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (BN == 256) return f32 ? dispatch_layout<256, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<256, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (BN == 128) return f32 ? dispatch_layout<128, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<128, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+    return f32 ? dispatch_layout<64, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<64, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
 }

@@ -11,11 +11,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!.*gru_).
 echo "launch list rc=$?"
 # dominant kernel: the K2 GEMM.  Skip the warm-up steps' GEMM launches (3 steps x 28) and take the first three of a timed step
 # (layer-0 W_ih forward 7552x6144x8192, layer-1, layer-2).
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 84 -c 3 -f -o gpurun_out/prof_gemm \
+ncu --set full --clock-control none --import-source on -k "regex:gemm_tc2?_kernel" -s 84 -c 3 -f -o gpurun_out/prof_gemm \
     $CMD > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture rc=$?"
 # K1 / Adam / CTC: one launch each, for the HBM-bound rooflines
-ncu --set full --clock-control none --import-source on -k 'regex:frontend_fwd_kernel|frontend_bwd_kernel|adam_kernel|ctc_kernel' -s 12 -c 4 -f \
+ncu --set full --clock-control none --import-source on -k 'regex:frontend_fwd_kernel|frontend_bwd_tc_kernel|adam_kernel|ctc_kernel' -s 12 -c 4 -f \
     -o gpurun_out/prof_misc $CMD > gpurun_out/ncu_misc.log 2>&1
 echo "misc capture rc=$?"
 ls -la gpurun_out/
