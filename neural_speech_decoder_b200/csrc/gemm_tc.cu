@@ -9,6 +9,8 @@
 // the time-batched W_hh wgrad.  Operands may be K-major or MN-major (both are native UMMA layouts).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace nsd {
@@ -38,6 +40,12 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int
     return {first_m + within % gsz, within / gsz};
 }
 
+// eight consecutive fp32 results as ONE 256-bit store (a full 32-byte sector per thread: the thread-per-row epilogue otherwise
+// half-fills every sector it touches and backs up the LSU queue -- ncu: lg_throttle on the K = 2048 GEMMs)
+__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 template <typename OutT> __device__ __forceinline__ void store4(OutT* p, float a, float b, float c, float d);
 template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
@@ -156,6 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                                       // TMEM lane quadrant this warp may read
         int acc = 0; uint32_t acc_phase = 0;
         const bool vec_ok = ((ldc % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const bool vec8_ok = ((ldc % 8) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0);
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const TileCoord tc = tile_coord(t, num_m, num_n);
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -170,7 +179,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
                 if (row < M) {
                     OutT* crow = C + (size_t)row * ldc + col0;
-                    if (vec_ok && col0 + 32 <= N) {
+                    if (std::is_same<OutT, float>::value && vec8_ok && beta == 0.f && col0 + 32 <= N) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
+                            if (bias) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i + 4));
+                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                            }
+                            store8_f32(reinterpret_cast<float*>(crow) + i, v);
+                        }
+                    } else if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
@@ -381,6 +402,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
         const bool vec_ok = ((ldc % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const bool vec8_ok = ((ldc % 8) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0);
         for (int t = w_first; t < num_tiles; t += w_step) {
             const TileCoord tc = coord_of(t);
             mbar_wait_cl(&tmem_full[acc], acc_phase);
@@ -395,7 +417,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
                 if (row < M) {
                     OutT* crow = C + (size_t)row * ldc + col0;
-                    if (vec_ok && col0 + 32 <= N) {
+                    if (std::is_same<OutT, float>::value && vec8_ok && beta == 0.f && col0 + 32 <= N) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
+                            if (bias) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i + 4));
+                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                            }
+                            store8_f32(reinterpret_cast<float*>(crow) + i, v);
+                        }
+                    } else if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
