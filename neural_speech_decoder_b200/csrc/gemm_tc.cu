@@ -46,6 +46,18 @@ __device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const uint32_t (&r)[32], int i, const float* bias_at) {
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float lo = __uint_as_float(r[i + 2 * e]), hi = __uint_as_float(r[i + 2 * e + 1]);
+        if (bias_at) { lo += __ldg(bias_at + 2 * e); hi += __ldg(bias_at + 2 * e + 1); }
+        const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+        w[e] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
 template <typename OutT> __device__ __forceinline__ void store4(OutT* p, float a, float b, float c, float d);
 template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
@@ -191,6 +203,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             store8_f32(reinterpret_cast<float*>(crow) + i, v);
                         }
+                    } else if (std::is_same<OutT, __nv_bfloat16>::value && vec8_ok && (ldc % 16) == 0 && beta == 0.f && col0 + 32 <= N) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 16)
+                            store16_bf16(reinterpret_cast<__nv_bfloat16*>(crow) + i, r, i, bias ? bias + col0 + i : nullptr);
                     } else if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
@@ -429,6 +445,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                             store8_f32(reinterpret_cast<float*>(crow) + i, v);
                         }
+                    } else if (std::is_same<OutT, __nv_bfloat16>::value && vec8_ok && (ldc % 16) == 0 && beta == 0.f && col0 + 32 <= N) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 16)
+                            store16_bf16(reinterpret_cast<__nv_bfloat16*>(crow) + i, r, i, bias ? bias + col0 + i : nullptr);
                     } else if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
