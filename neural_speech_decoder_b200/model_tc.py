@@ -61,24 +61,6 @@ class Bf16Shadows:
             self.tags[loc] = (p.data_ptr(), p._version)
 
 
-def _bf16_stacks(ws, want_t: bool, t_side_by_side: bool):
-    """One pass over each direction's fp32 weight [R, C]: the bf16 copies stacked by rows [D*R, C] and, if asked, the
-    bf16 transposes -- side by side [C, D*R] (W_ih^T for dgrad) or stacked by rows [D*C, R] (W_hh^T for BPTT)."""
-    D = len(ws)
-    R, Cn = ws[0].shape
-    dev = ws[0].device
-    out = torch.empty((D * R, Cn), device=dev, dtype=torch.bfloat16)
-    outT = None
-    if want_t:
-        outT = torch.empty((Cn, D * R) if t_side_by_side else (D * Cn, R), device=dev, dtype=torch.bfloat16)
-    for d, w in enumerate(ws):
-        tv = None
-        if want_t:
-            tv = outT[:, d * R:(d + 1) * R] if t_side_by_side else outT[d * Cn:(d + 1) * Cn]
-        ops.cast_transpose_into(w, out[d * R:(d + 1) * R], tv)
-    return out, outT
-
-
 def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gru_w):
     K, S, H, L, D = cfg["K"], cfg["S"], cfg["H"], cfg["L"], cfg["D"]
     dev = x.device
@@ -90,24 +72,20 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
     patches, ys, z = ops.frontend_fwd(x, day_idx, day_w.detach().contiguous(), day_b.detach().contiguous(), taps,
                                       K, S, torch.bfloat16, cfg["err_flag"], cfg.get("noise"))
     inp = patches                                            # bf16 [M, in_l]
+    sh = cfg.get("shadows") or Bf16Shadows()                 # the module's cache of bf16 weight copies (a throw-away one otherwise)
     layers = []
     hseq = None
     for l in range(L):
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
-        sh = cfg.get("shadows")
-        if sh is not None:
-            # gru_w holds the Parameters themselves: their version counters tell whether the kept copies are current
-            w_ih_bf = sh.stacked(("ih", l), [gru_w[(l * D + d) * 4] for d in range(D)])          # [D*3H, in_l]
-            w_hh_bf = sh.stacked(("hh", l), [gru_w[(l * D + d) * 4 + 1] for d in range(D)])      # [D*3H, H]
-            w_hhT_bf = None
-            if need_grad:                                                                        # [D*H, 3H] (BPTT operand)
-                w_hhT_bf = torch.empty((D * H, 3 * H), device=dev, dtype=torch.bfloat16)
-                for d in range(D):
-                    ops.cast_transpose_into(w_hh_bf[d * 3 * H:(d + 1) * 3 * H], None, w_hhT_bf[d * H:(d + 1) * H])
-        else:
-            w_ih_bf, _ = _bf16_stacks([w[0] for w in ws], False, True)                     # [D*3H, in_l]
-            w_hh_bf, w_hhT_bf = _bf16_stacks([w[1] for w in ws], need_grad, False)         # [D*3H, H], [D*H, 3H] (BPTT operand)
+        # gru_w holds the Parameters themselves: their version counters tell whether the kept bf16 copies are current
+        w_ih_bf = sh.stacked(("ih", l), [gru_w[(l * D + d) * 4] for d in range(D)])          # [D*3H, in_l]
+        w_hh_bf = sh.stacked(("hh", l), [gru_w[(l * D + d) * 4 + 1] for d in range(D)])      # [D*3H, H]
+        w_hhT_bf = None
+        if need_grad:                                                                        # [D*H, 3H] (BPTT operand)
+            w_hhT_bf = torch.empty((D * H, 3 * H), device=dev, dtype=torch.bfloat16)
+            for d in range(D):
+                ops.cast_transpose_into(w_hh_bf[d * 3 * H:(d + 1) * 3 * H], None, w_hhT_bf[d * H:(d + 1) * H])
         b_ih = torch.cat([w[2] for w in ws]) if D > 1 else ws[0][2]
         b_hh = torch.cat([w[3] for w in ws]) if D > 1 else ws[0][3]
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
@@ -123,7 +101,7 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
         inp = nxt
     C = fc_w.shape[0]
     logits_tm = torch.empty((M, C), device=dev, dtype=torch.float32)
-    fc_w_bf = sh.stacked(("fc", 0), [fc_w]) if cfg.get("shadows") is not None else ops.cast_transpose(fc_w.detach(), True, False)[0]
+    fc_w_bf = sh.stacked(("fc", 0), [fc_w])
     ops.gemm(False, True, M, C, D * H, hseq_bf, D * H, fc_w_bf, D * H, logits_tm, C, bias=fc_b.detach().contiguous())
     logits = ops.swap01(logits_tm.view(Tp, B, C))
     if need_grad:
