@@ -18,6 +18,21 @@ from . import ops
 from ._lib import NsdError
 
 
+def complete_frames(n_bins: int, kernel_len: int, stride_len: int, lookahead: int) -> int:
+    """Number of output frames that can be emitted once ``n_bins`` bins have arrived: frame j reads smoothed bins
+    [S*j, S*j+K) and the smoothing reads ``lookahead`` raw bins past each of them."""
+    if n_bins < kernel_len + lookahead:
+        return 0
+    return (n_bins - kernel_len - lookahead) // stride_len + 1
+
+
+def window_for(j0: int, stride_len: int, halo: int):
+    """(first raw bin, number of leading frames to discard) of the window that recomputes frames from j0 on with
+    ``halo`` bins (a multiple of the stride, >= the smoothing's left reach) of true history in front."""
+    r0 = max(0, stride_len * j0 - halo)
+    return r0, (stride_len * j0 - r0) // stride_len
+
+
 class StreamingDecoder:
     def __init__(self, model, batch_size: int, dayIdx: torch.Tensor):
         if model.bidirectional:
@@ -52,9 +67,8 @@ class StreamingDecoder:
         """Frames j0..j1 (inclusive) from bins [r0, r1): r0 re-reads ``halo`` bins of left context so that the frames
         we keep see the true smoothing history; frames computed from the window's padded edges are discarded."""
         m, B, K, S = self.m, self.B, self.K, self.S
-        r0 = max(0, S * j0 - self.halo)
+        r0, skip = window_for(j0, S, self.halo)
         x = self.hist[:, r0 - self.hist_start:r1 - self.hist_start].contiguous()
-        skip = (S * j0 - r0) // S
         k = j1 - j0 + 1
         taps = m.gaussianSmoother.weight[0, 0].contiguous()
         patches, _, _ = ops.frontend_fwd(x, self.day, m.dayWeights.detach().contiguous(), m.dayBias.detach().contiguous(), taps,
@@ -96,7 +110,7 @@ class StreamingDecoder:
         self.hist = torch.cat([self.hist, bins.to(self.dev, torch.float32)], dim=1)
         self.n_bins += bins.shape[1]
         # frame j needs smoothed bins up to S*j+K-1, i.e. raw bins up to S*j+K-1+right
-        j1 = (self.n_bins - self.K - self.right) // self.S
+        j1 = complete_frames(self.n_bins, self.K, self.S, self.right) - 1
         if j1 < self.next_frame:
             return None
         out = self._emit(self.next_frame, j1, self.S * j1 + self.K + self.right)

@@ -99,3 +99,21 @@ def test_fused_adam_rejects_cpu_parameters():
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError):
         nsd.adam.FusedAdam([p], lr=0.1).step()
+
+
+def test_streaming_frame_arithmetic():
+    """StreamingDecoder's host logic (no GPU): which frames are complete after n bins, and which window recomputes them.
+    Checked against the definitions: frame j reads smoothed bins [S*j, S*j+K); smoothed bin t reads raw bins
+    [t-left, t+right] (augmentations.py:91: 20 taps, padding 'same' -> left 9, right 10)."""
+    from neural_speech_decoder_b200.streaming import complete_frames, window_for
+    for K, S, left, right in ((32, 4, 9, 10), (14, 2, 9, 10), (16, 4, 4, 5), (7, 3, 9, 10)):
+        halo = -(-left // S) * S
+        for n in range(0, 120):
+            brute = 0
+            while S * brute + K - 1 + right <= n - 1:      # last raw bin frame `brute` needs has arrived
+                brute += 1
+            assert complete_frames(n, K, S, right) == brute
+        for j0 in range(0, 40):
+            r0, skip = window_for(j0, S, halo)
+            assert r0 % S == 0 and r0 + skip * S == S * j0           # the kept frames start exactly at frame j0
+            assert r0 == 0 or S * j0 - r0 >= left                    # ... with the smoothing's full left reach in the window
