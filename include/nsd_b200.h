@@ -91,6 +91,11 @@ int nsd_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, in
                  int ldb, float* C, int ldc, const float* bias, float beta, void* stream);
 int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const void* A, int lda, const void* B,
                   int ldb, void* C, int ldc, int c_dtype, const float* bias, float beta, void* stream);
+/* Two GEMMs of identical shape and layout in ONE launch (operands A0/B0 -> C0 and A1/B1 -> C1, shared leading
+ * dimensions; no bias, no beta): the two directions' time-batched W_hh weight gradients each fill only 65 % of the
+ * GPU on their own.  Shapes the paired tensor-core form does not take fall back to two nsd_gemm_bf16 calls. */
+int nsd_gemm_bf16_x2(int transa, int transb, int M, int N, int K, const void* A0, const void* A1, int lda, const void* B0,
+                     const void* B1, int ldb, void* C0, void* C1, int ldc, int c_dtype, void* stream);
 
 /* column sums: out[n] = sum_m a[m*lda + n]  (bias gradients); two fixed-order stages, workspace nsd_colsum_workspace(N). */
 int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, void* workspace, size_t workspace_bytes,

@@ -31,6 +31,7 @@ SIGNATURES = {
     "nsd_frontend_bwd_workspace": (sz, [i32, i32]),
     "nsd_gemm_f32": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, f32, vp]),
     "nsd_gemm_bf16": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, f32, vp]),
+    "nsd_gemm_bf16_x2": (i32, [i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, vp]),
     "nsd_colsum": (i32, [vp, i32, i32, i32, i32, vp, vp, sz, vp]),
     "nsd_colsum_workspace": (sz, [i32]),
     "nsd_cast": (i32, [vp, i32, vp, i32, sz, vp]),

@@ -258,10 +258,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // drains its own half.  Barriers: full[s] in the leader, completed by BOTH CTAs' TMA loads (cta_group::2 TMA form, barrier
 // addressed in the leader's shared memory); empty[s] / tmem_full[a] in both CTAs (multicast commit); tmem_empty[a] in the leader (8 arrivals:
 // four epilogue warps of each CTA).
-struct Cfg2 {
-    static constexpr int BN = 256, STAGES = 7;
+// BN2 = 256 (default) or 128: the narrower tile halves the quantum of work, which pays when the 256-wide tiling leaves the
+// last round of clusters mostly idle (picked per problem by pair_tile_width()).
+template <int BN2> struct Cfg2 {
+    static constexpr int BN = BN2, STAGES = (BN2 == 256) ? 7 : 9;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 512;
+    static constexpr int TMEM_COLS = ACC_STAGES * BN;      // 512 or 256
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 512;
 };
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
@@ -310,11 +312,15 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {  
     }
 }
 
-template <typename OutT, bool A_MN, bool B_MN>
+// Up to TWO problems of identical shape in one launch (nprob = 2: operands tmA2 / tmB2, result C2): the two directions'
+// W_hh weight gradients are 48 tile pairs each on 74 clusters -- together, with 128-wide tiles, they fill 2.6 rounds
+// instead of leaving a third of the GPU idle twice.
+template <typename OutT, bool A_MN, bool B_MN, int BN2>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C, int ldc,
-                const float* __restrict__ bias, float beta, int M, int N, int K) {
-    using cfg = Cfg2;
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, OutT* __restrict__ C, OutT* __restrict__ C2,
+                int ldc, const float* __restrict__ bias, float beta, int M, int N, int K, int nprob) {
+    using cfg = Cfg2<BN2>;
     constexpr int BN = cfg::BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -331,13 +337,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int nk = (K + BK - 1) / BK;
     const int num_mw = (num_m + 1) / 2;
-    const int num_tiles = num_mw * num_n;
+    const int per_prob = num_mw * num_n;
+    const int num_tiles = per_prob * nprob;
     const int w_first = (int)cluster_id_x(), w_step = (int)nclusters_x();
-    auto coord_of = [&](int t) { TileCoord tc = tile_coord(t, num_mw, num_n, 8); tc.m_blk = tc.m_blk * 2 + crank; return tc; };
+    auto coord_of = [&](int t) { TileCoord tc = tile_coord(t % per_prob, num_mw, num_n, 8); tc.m_blk = tc.m_blk * 2 + crank; return tc; };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (nprob > 1) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -361,22 +372,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int stage = 0; uint32_t phase = 0;
         for (int t = w_first; t < num_tiles; t += w_step) {
             const TileCoord tc = coord_of(t);
+            const CUtensorMap* mA = (t >= per_prob) ? &tmA2 : &tmA;
+            const CUtensorMap* mB = (t >= per_prob) ? &tmB2 : &tmB;
             for (int kb = 0; kb < nk; ++kb) {
                 mbar_wait_cl(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * cfg::STAGE_BYTES;
                     const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0u);
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * cfg::STAGE_BYTES);
-                    if constexpr (!A_MN) tma_load_2d_pair(&tmA, fb, sa, kb * BK, tc.m_blk * BM);
+                    if constexpr (!A_MN) tma_load_2d_pair(mA, fb, sa, kb * BK, tc.m_blk * BM);
                     else {
 #pragma unroll
-                        for (int i = 0; i < BM / 64; ++i) tma_load_2d_pair(&tmA, fb, sa + i * 8192, tc.m_blk * BM + 64 * i, kb * BK);
+                        for (int i = 0; i < BM / 64; ++i) tma_load_2d_pair(mA, fb, sa + i * 8192, tc.m_blk * BM + 64 * i, kb * BK);
                     }
                     const int n0 = tc.n_blk * BN + crank * (BN / 2);
-                    if constexpr (!B_MN) tma_load_2d_pair(&tmB, fb, sa + cfg::A_BYTES, kb * BK, n0);
+                    if constexpr (!B_MN) tma_load_2d_pair(mB, fb, sa + cfg::A_BYTES, kb * BK, n0);
                     else {
 #pragma unroll
-                        for (int i = 0; i < BN / 128; ++i) tma_load_2d_pair(&tmB, fb, sa + cfg::A_BYTES + i * 8192, n0 + 64 * i, kb * BK);
+                        for (int i = 0; i < BN / 128; ++i) tma_load_2d_pair(mB, fb, sa + cfg::A_BYTES + i * 8192, n0 + 64 * i, kb * BK);
                     }
                 }
                 __syncwarp();
@@ -417,8 +430,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===================== epilogue: my 128 rows of the 256-row tile =====================
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
-        const bool vec_ok = ((ldc % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-        const bool vec8_ok = ((ldc % 8) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0);
+        const uintptr_t cbits = reinterpret_cast<uintptr_t>(C) | (nprob > 1 ? reinterpret_cast<uintptr_t>(C2) : 0);
+        const bool vec_ok = ((ldc % 4) == 0) && ((cbits & 15) == 0);
+        const bool vec8_ok = ((ldc % 8) == 0) && ((cbits & 31) == 0);
         for (int t = w_first; t < num_tiles; t += w_step) {
             const TileCoord tc = coord_of(t);
             mbar_wait_cl(&tmem_full[acc], acc_phase);
@@ -432,7 +446,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
                 if (row < M) {
-                    OutT* crow = C + (size_t)row * ldc + col0;
+                    OutT* crow = ((t >= per_prob) ? C2 : C) + (size_t)row * ldc + col0;
                     if (std::is_same<OutT, float>::value && vec8_ok && beta == 0.f && col0 + 32 <= N) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
@@ -554,16 +568,17 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc
     return NSD_OK;
 }
 
-template <typename OutT, bool A_MN, bool B_MN>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta, int M, int N, int K, cudaStream_t s) {
-    using cfg = Cfg2;
-    auto kern = gemm_tc2_kernel<OutT, A_MN, B_MN>;
+template <typename OutT, bool A_MN, bool B_MN, int BN2>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2, void* C, void* C2, int ldc,
+                   const float* bias, float beta, int M, int N, int K, int nprob, cudaStream_t s) {
+    using cfg = Cfg2<BN2>;
+    auto kern = gemm_tc2_kernel<OutT, A_MN, B_MN, BN2>;
     static bool attr_set = false;       // per instantiation
     if (!attr_set) {
         NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
         attr_set = true;
     }
-    const int items = cdiv(cdiv(M, BM), 2) * cdiv(N, cfg::BN);     // 256 x 256 tiles
+    const int items = cdiv(cdiv(M, BM), 2) * cdiv(N, cfg::BN) * nprob;     // 256 x BN tiles
     const int grid = std::min(items, sm_count() / 2) * 2;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = s;
@@ -571,22 +586,38 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ld
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     lc.attrs = attr; lc.numAttrs = 1;
-    NSD_CUDA(cudaLaunchKernelEx(&lc, kern, ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K));
+    NSD_CUDA(cudaLaunchKernelEx(&lc, kern, ta, tb, ta2, tb2, reinterpret_cast<OutT*>(C), reinterpret_cast<OutT*>(C2), ldc, bias, beta, M, N, K, nprob));
     count_launch(1);
     return NSD_OK;
+}
+
+// tile width of the pair form: the one whose last round of clusters wastes less
+static int pair_tile_width(int M, int N, int nprob) {
+    const int clusters = std::max(1, sm_count() / 2);
+    const long long mp = cdiv(cdiv(M, BM), 2);
+    const long long c256 = cdivz((size_t)(mp * cdiv(N, 256) * nprob), (size_t)clusters) * 256;
+    const long long c128 = cdivz((size_t)(mp * cdiv(N, 128) * nprob), (size_t)clusters) * 128;
+    return (c128 < c256) ? 128 : 256;
 }
 
 }  // namespace tc
 }  // namespace nsd
 
-template <typename OutT>
-static int dispatch_layout2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc, const float* bias, float beta,
-                            int M, int N, int K, cudaStream_t s) {
+template <typename OutT, int BN2>
+static int dispatch_layout2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                            void* C, void* C2, int ldc, const float* bias, float beta, int M, int N, int K, int nprob, cudaStream_t s) {
     using namespace nsd::tc;
-    if (!a_mn && !b_mn) return launch2<OutT, false, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (!a_mn && b_mn) return launch2<OutT, false, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    if (a_mn && b_mn) return launch2<OutT, true, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
-    return launch2<OutT, true, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (!a_mn && !b_mn) return launch2<OutT, false, false, BN2>(ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s);
+    if (!a_mn && b_mn) return launch2<OutT, false, true, BN2>(ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s);
+    if (a_mn && b_mn) return launch2<OutT, true, true, BN2>(ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s);
+    return launch2<OutT, true, false, BN2>(ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s);
+}
+static int dispatch_pair(int bn2, bool f32, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                         void* C, void* C2, int ldc, const float* bias, float beta, int M, int N, int K, int nprob, cudaStream_t s) {
+    if (bn2 == 256) return f32 ? dispatch_layout2<float, 256>(a_mn, b_mn, ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s)
+                               : dispatch_layout2<__nv_bfloat16, 256>(a_mn, b_mn, ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s);
+    return f32 ? dispatch_layout2<float, 128>(a_mn, b_mn, ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s)
+               : dispatch_layout2<__nv_bfloat16, 128>(a_mn, b_mn, ta, tb, ta2, tb2, C, C2, ldc, bias, beta, M, N, K, nprob, s);
 }
 
 template <int BN, typename OutT>
@@ -622,11 +653,39 @@ extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const 
     // wide tiles with at least one vertical pair: the cta_group::2 form (256 x 256 tile over an SM pair)
     static const bool no_pair = [] { const char* e = getenv("NSD_GEMM_PAIR"); return e && e[0] == '0'; }();      // debug: single-CTA form only
     const bool pair = (BN == 256) && (M > BM) && !no_pair && sm_count() >= 2;
-    rc = b_mn ? make_bf16_map_mn(&tb, B, K, N, ldb) : make_bf16_map(&tb, B, N, K, ldb, pair ? BN / 2 : BN);
+    const int bn2 = pair ? pair_tile_width(M, N, 1) : 0;
+    rc = b_mn ? make_bf16_map_mn(&tb, B, K, N, ldb) : make_bf16_map(&tb, B, N, K, ldb, pair ? bn2 / 2 : BN);
     if (rc) return rc;
     const bool f32 = c_dtype == NSD_F32;
-    if (pair) return f32 ? dispatch_layout2<float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout2<__nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+    if (pair) return dispatch_pair(bn2, f32, a_mn, b_mn, ta, tb, ta, tb, C, C, ldc, bias, beta, M, N, K, 1, s);
     if (BN == 256) return f32 ? dispatch_layout<256, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<256, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
     if (BN == 128) return f32 ? dispatch_layout<128, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<128, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
     return f32 ? dispatch_layout<64, float>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s) : dispatch_layout<64, __nv_bfloat16>(a_mn, b_mn, ta, tb, C, ldc, bias, beta, M, N, K, s);
+}
+
+extern "C" int nsd_gemm_bf16_x2(int transa, int transb, int M, int N, int K, const void* A0, const void* A1, int lda, const void* B0, const void* B1,
+                                int ldb, void* C0, void* C1, int ldc, int c_dtype, void* stream) {
+    using namespace nsd;
+    using namespace nsd::tc;
+    NSD_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_bf16_x2: bad sizes M=%d N=%d K=%d", M, N, K);
+    if (M == 0 || N == 0) return NSD_OK;
+    NSD_CHECK_ARG(A0 && A1 && B0 && B1 && C0 && C1, "gemm_bf16_x2: null pointer");
+    static const bool no_pair = [] { const char* e = getenv("NSD_GEMM_PAIR"); return e && e[0] == '0'; }();
+    if (N < 192 || M <= BM || no_pair || sm_count() < 2) {          // shapes the pair form does not take: two plain launches
+        int rc = nsd_gemm_bf16(transa, transb, M, N, K, A0, lda, B0, ldb, C0, ldc, c_dtype, nullptr, 0.f, stream);
+        return rc ? rc : nsd_gemm_bf16(transa, transb, M, N, K, A1, lda, B1, ldb, C1, ldc, c_dtype, nullptr, 0.f, stream);
+    }
+    const bool a_mn = transa != 0, b_mn = transb == 0;
+    NSD_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "gemm_bf16_x2: lda=%d / ldb=%d must be multiples of 8", lda, ldb);
+    NSD_CHECK_ARG(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "gemm_bf16_x2: leading dimension smaller than the row length");
+    NSD_CHECK_ARG((((uintptr_t)A0 | (uintptr_t)A1 | (uintptr_t)B0 | (uintptr_t)B1) & 15) == 0, "gemm_bf16_x2: operands must be 16-byte aligned");
+    NSD_CHECK_ARG(c_dtype == NSD_F32 || c_dtype == NSD_BF16, "gemm_bf16_x2: bad output dtype");
+    const int bn2 = pair_tile_width(M, N, 2);
+    CUtensorMap ta, tb, ta2, tb2;
+    int rc = a_mn ? make_bf16_map_mn(&ta, A0, K, M, lda) : make_bf16_map(&ta, A0, M, K, lda, BM);
+    if (!rc) rc = a_mn ? make_bf16_map_mn(&ta2, A1, K, M, lda) : make_bf16_map(&ta2, A1, M, K, lda, BM);
+    if (!rc) rc = b_mn ? make_bf16_map_mn(&tb, B0, K, N, ldb) : make_bf16_map(&tb, B0, N, K, ldb, bn2 / 2);
+    if (!rc) rc = b_mn ? make_bf16_map_mn(&tb2, B1, K, N, ldb) : make_bf16_map(&tb2, B1, N, K, ldb, bn2 / 2);
+    if (rc) return rc;
+    return dispatch_pair(bn2, c_dtype == NSD_F32, a_mn, b_mn, ta, tb, ta2, tb2, C0, C1, ldc, nullptr, 0.f, M, N, K, 2, (cudaStream_t)stream);
 }

@@ -155,11 +155,14 @@ def decoder_backward_tc(ctx, dlogits):
         # wgrad W_ih: dW[D*3H, in_l] = dgi^T inp -- reduction over the T'*B rows, both operands M/N-major as stored
         ops.gemm(True, False, D * 3 * H, in_l, M, dgi, D * 3 * H, inp, in_l, v_wih, in_l)
         if Tp > 1:
-            for d in range(D):
-                # forward dir: dgh[t] pairs with h[t-1];  reverse dir: dgh[t] pairs with h[t+1]  (row-range views, no copies)
-                g_lo, h_lo = (0, B) if d == 1 else (B, 0)
+            # forward dir: dgh[t] pairs with h[t-1];  reverse dir: dgh[t] pairs with h[t+1]  (row-range views, no copies)
+            offs = [((B if d == 0 else 0) * D * 3 * H + d * 3 * H, (0 if d == 0 else B) * D * H + d * H, d * 3 * H * H) for d in range(D)]
+            if D == 2:                      # both directions in one launch
+                ops.gemm_x2(True, False, 3 * H, H, Mh, dgh, D * 3 * H, hseq_bf, D * H, v_whh, H,
+                            [o[0] for o in offs], [o[1] for o in offs], [o[2] for o in offs])
+            else:
                 ops.gemm(True, False, 3 * H, H, Mh, dgh, D * 3 * H, hseq_bf, D * H, v_whh, H,
-                         a_off=g_lo * D * 3 * H + d * 3 * H, b_off=h_lo * D * H + d * H, c_off=d * 3 * H * H)
+                         a_off=offs[0][0], b_off=offs[0][1], c_off=offs[0][2])
         dinp = None
         if l > 0 or day_w.requires_grad:
             dinp = torch.empty((M, in_l), device=dev, dtype=torch.float32 if l > 0 else torch.bfloat16)

@@ -75,6 +75,15 @@ def gemm(transa: bool, transb: bool, M: int, N: int, K: int, A, lda: int, B, ldb
              ptr(bias), beta, stream())
 
 
+def gemm_x2(transa: bool, transb: bool, M: int, N: int, K: int, A, lda: int, B, ldb: int, C, ldc: int, a_offs, b_offs, c_offs):
+    """Two bf16 GEMMs of identical shape in ONE launch: problem i reads A / B / writes C at element offsets a_offs[i] /
+    b_offs[i] / c_offs[i] of the same three buffers (the two directions' W_hh weight gradients)."""
+    ea, eb, ec = A.element_size(), B.element_size(), C.element_size()
+    call("nsd_gemm_bf16_x2", int(transa), int(transb), M, N, K, A.data_ptr() + a_offs[0] * ea, A.data_ptr() + a_offs[1] * ea, lda,
+         B.data_ptr() + b_offs[0] * eb, B.data_ptr() + b_offs[1] * eb, ldb, C.data_ptr() + c_offs[0] * ec, C.data_ptr() + c_offs[1] * ec, ldc,
+         dtype_code(C.dtype), stream())
+
+
 def colsum(a, M: int, N: int, lda: int, out, a_off: int = 0, out_off: int = 0):
     nbytes = _lib.lib().nsd_colsum_workspace(N)
     ws = torch.empty(nbytes, device=a.device, dtype=torch.uint8)

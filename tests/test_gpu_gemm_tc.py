@@ -94,3 +94,27 @@ def test_cast_transpose():
     view = big[:, 20:220]                                    # row stride 300, 200 columns
     d, dT = ops.cast_transpose(view, True, True)
     assert torch.equal(d, view.to(torch.bfloat16)) and torch.equal(dT, view.to(torch.bfloat16).T.contiguous())
+
+
+@pytest.mark.parametrize("M,N,K", [(3072, 1024, 7488), (384, 256, 200), (300, 192, 96), (64, 1024, 128)])
+def test_gemm_x2_equals_two_gemms(M, N, K):
+    """nsd_gemm_bf16_x2 (two same-shape problems in one launch, the W_hh weight-gradient form: both operands MN-major, sub-matrix
+    views of shared buffers) against two nsd_gemm_bf16 calls and a float64 product."""
+    torch.manual_seed(M + N)
+    lda, ldb = 2 * M + 24, 2 * N + 16
+    A = torch.randn(K + 5, lda, device=DEV).to(torch.bfloat16)       # op(A) = A^T: stored [K, M] (M-major)
+    Bm = torch.randn(K + 5, ldb, device=DEV).to(torch.bfloat16)      # op(B): stored [K, N] (N-major)
+    a_offs, b_offs = [3 * lda, M + 8 + (-M) % 8], [0, 2 * ldb + N + 16]          # 16-byte aligned sub-matrix origins
+    C = torch.zeros(2 * M, N, device=DEV)
+    ops.gemm_x2(True, False, M, N, K, A, lda, Bm, ldb, C, N, a_offs, b_offs, [0, M * N])
+    ref = torch.zeros_like(C)
+    for i in range(2):
+        ops.gemm(True, False, M, N, K, A, lda, Bm, ldb, ref, N, a_off=a_offs[i], b_off=b_offs[i], c_off=i * M * N)
+    assert torch.allclose(C, ref, rtol=1e-6, atol=1e-6)
+    Af, Bf = A.double().reshape(-1), Bm.double().reshape(-1)
+    for i in range(2):
+        a = torch.as_strided(Af, (K, M), (lda, 1), a_offs[i])
+        b = torch.as_strided(Bf, (K, N), (ldb, 1), b_offs[i])
+        want = a.T @ b
+        got = C[i * M:(i + 1) * M].double()
+        assert (got - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
