@@ -229,7 +229,7 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    _lib.profile_begin({"nsd_gemm_bf16", "nsd_gemm_f32", "nsd_adam_step", "nsd_frontend_fwd", "nsd_gru_fwd_bf16", "nsd_gru_bwd_bf16"})
+    _lib.profile_begin({"nsd_gemm_bf16", "nsd_gemm_bf16_x2", "nsd_gemm_f32", "nsd_adam_step", "nsd_frontend_fwd", "nsd_gru_fwd_bf16", "nsd_gru_bwd_bf16"})
     l0 = _lib.lib().nsd_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
