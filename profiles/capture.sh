@@ -9,9 +9,9 @@ $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_ou
 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!.*gru_).*$' -c 600 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# dominant kernel: the K2 GEMM.  Skip the warm-up steps' GEMM launches (3 steps x 28) and take the first three of a timed step
+# dominant kernel: the K2 GEMM.  Skip the warm-up steps' GEMM launches (3 steps x 23) and take the first three of a timed step
 # (layer-0 W_ih forward 7552x6144x8192, layer-1, layer-2).
-ncu --set full --clock-control none --import-source on -k "regex:gemm_tc2?_kernel" -s 84 -c 3 -f -o gpurun_out/prof_gemm \
+ncu --set full --clock-control none --import-source on -k "regex:gemm_tc2?_kernel" -s 69 -c 3 -f -o gpurun_out/prof_gemm \
     $CMD > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture rc=$?"
 # K1 / Adam / CTC: one launch each, for the HBM-bound rooflines
