@@ -104,7 +104,8 @@ size_t nsd_colsum_workspace(int N);
 /* dtype conversion of a contiguous buffer, f32 <-> bf16. */
 int nsd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 /* bf16 copies of a row-major [R,C] matrix (f32 or bf16 source): dst [R,C] (ld_dst) and/or its transpose dstT [C,R]
- * (ld_dstT); either may be NULL.  Produces the K-major operands nsd_gemm_bf16 needs for dgrad / wgrad. */
+ * (ld_dstT); either may be NULL.  (nsd_gemm_bf16 takes either operand major natively; the transposed form is what the
+ * BPTT kernel's stationary W_hh^T operand is loaded from.) */
 int nsd_cast_transpose(const void* src, int src_dtype, int R, int C, int ld_src, void* dst, int ld_dst, void* dstT,
                        int ld_dstT, void* stream);
 /* out[B,T,C] <- in[T,B,C] (or the inverse with the roles of T and B swapped by the caller). */
