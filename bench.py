@@ -13,8 +13,11 @@ Our arm prints one JSON line with
   e2e           utt/s through the public API with HOST (pinned) inputs: H2D copies + a D2H read of the loss per step
   roofline      the dominant kernel (K2 GEMM, tensor-bound): algorithmic FLOP / CUDA-event time measured in the timed region
   cpu_baseline  the torch-operator port of the reference (oracle/torch_port.py) on this box's host cores (rank 0, N=1)
-``--impl reference`` times that CPU port alone (the reference has no GPU-independent build to ship: it is
-pure Python over third-party torch, and /root/reference does not exist on the GPU box).
+``--impl reference`` times the reference's CPU path alone on the FULL batch: the reference's own ``GRUDecoder`` module,
+byte-compiled from /root/reference into oracle/_ref by oracle/build_ref.py ("kind": "reference"), or -- when oracle/_ref has
+not been built -- the torch-operator port oracle/torch_port.py ("kind": "port"); the trainer's loss / Adam lines are
+restated in oracle/torch_port.py:train_step in both cases.  ``--impl reference-cuda`` (secondary, never the headline
+ratio) runs the same reference module on the GPU (cuDNN GRU, fp32/TF32 and bf16 autocast): the "beat-this" bar of SURVEY 2a.
 """
 from __future__ import annotations
 
@@ -32,6 +35,7 @@ sys.path.insert(0, ROOT)
 METRIC = "train utterances/sec (GRUDecoder, B=64, T=500)"
 UNIT = "utterances/s"
 NOISE = dict(white_noise_sd=0.8, constant_offset_sd=0.2)     # scripts/train_model.py:17-18 (whiteNoiseSD, constantOffsetSD)
+K1_SAVED_TENSORS = 2          # [B,T,N] f32 tensors K1's forward writes for its own backward (ys, z)
 MODEL_KW = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, dropout=0.4, strideLen=4,
                 kernelLen=32, gaussianSmoothWidth=2.0)
 
@@ -41,7 +45,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--precision", default=os.environ.get("NSD_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--T", type=int, default=500)
@@ -55,10 +59,19 @@ def parse():
     return ap.parse_args()
 
 
+def baseline_config_name(a):
+    """Which BASELINE.json configs[] entry the flags select."""
+    if a.T == 500 and a.batch == 64 and not a.strong:
+        return "BASELINE configs[0] (class default: unidirectional)" if a.uni else "BASELINE configs[1]"
+    if a.T == 2000 and a.batch == 256:
+        return "BASELINE configs[4] (long-sequence sweep)"
+    return "non-BASELINE shape"
+
+
 def config_dict(a, n_gpus, impl_note=""):
     bi = not a.uni
     return {"workload": f"GRUDecoder {'bi' if bi else 'uni'}directional 5x1024, 256 feats, 24 days, k32/s4, 41 classes, "
-                        f"dropout 0.4, white noise 0.8 + constant offset 0.2; train step augment+fwd+CTC+bwd+Adam; B={a.batch}/GPU T={a.T} (BASELINE configs[1])",
+                        f"dropout 0.4, white noise 0.8 + constant offset 0.2; train step augment+fwd+CTC+bwd+Adam; B={a.batch}/GPU T={a.T} ({baseline_config_name(a)})",
             "global_batch": a.batch * n_gpus, "T": a.T, "frames": (a.T - 32) // 4 + 1,
             "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
             "l2": "working set (0.54 GB weights + >1 GB activations per step) far exceeds the 126 MB L2; no flush needed"}
@@ -67,48 +80,100 @@ def config_dict(a, n_gpus, impl_note=""):
 # ----------------------------------------------------------------------------------------------------------
 # CPU baseline: the torch-operator port of the reference on the host cores
 # ----------------------------------------------------------------------------------------------------------
-def cpu_port_run(a, sample_b, steps, warmup):
+def reference_model(a, device="cpu"):
+    """(module, kind): the reference's own GRUDecoder from oracle/_ref ("reference"), else the torch-operator port ("port")."""
+    import torch
+    from oracle import torch_port as P
+    from oracle.build_ref import load_reference_decoder
+    torch.manual_seed(0)
+    Ref = load_reference_decoder()
+    if Ref is not None:
+        return Ref(device=device, bidirectional=not a.uni, **MODEL_KW), "reference"
+    return P.PortGRUDecoder(bidirectional=not a.uni, **MODEL_KW), "port"
+
+
+def cpu_reference_run(a, steps, warmup, budget_s=200.0):
+    """Reference train step on the host cores, FULL batch (same config as our arm), all host threads.  The number of timed
+    steps is bounded so the whole run stays within ``budget_s``; the batch is never reduced."""
     import torch
     from oracle import torch_port as P
     from neural_speech_decoder_b200.synthetic import make_batch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    m = P.PortGRUDecoder(bidirectional=not a.uni, **MODEL_KW)
+    m, kind = reference_model(a)
     m.train()
     opt = P.make_adam(m)
-    batch = make_batch(sample_b, a.T, seed=1)
-    for _ in range(warmup):
+    batch = make_batch(a.batch, a.T, seed=1)
+    t0 = time.perf_counter()
+    P.train_step(m, opt, *batch, **NOISE)                     # first step: also the probe that sizes the run
+    t_first = time.perf_counter() - t0
+    warm = max(0, min(warmup - 1, int(budget_s * 0.25 / max(t_first, 1e-3))))
+    for _ in range(warm):
         P.train_step(m, opt, *batch, **NOISE)
+    n = max(1, min(steps, int((budget_s - (warm + 1) * t_first) / max(t_first, 1e-3))))
     times = []
-    for _ in range(steps):
+    for _ in range(n):
         t0 = time.perf_counter()
         P.train_step(m, opt, *batch, **NOISE)
         times.append(time.perf_counter() - t0)
-    return sample_b * len(times) / sum(times), cores, sum(times) / len(times)
+    t_step = sum(times) / len(times)
+    sample = (f"full batch B={a.batch} T={a.T} per step, {len(times)} timed steps after {warm + 1} warm-up, torch {cores} threads"
+              + ("" if len(times) == steps else f" (bounded from {steps} steps to stay under {budget_s:.0f} s)"))
+    return a.batch / t_step, cores, t_step, kind, sample, len(times), warm + 1
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: a probe step at B=4 sizes the per-step sample so that K+W steps stay near 150 s
-    probe, cores, t_probe = cpu_port_run(a, 4, 1, 1)
-    per_utt = t_probe / 4
-    budget = 150.0 / max(1, a.steps + a.warmup)
-    sb = 64
-    while sb > 4 and sb * per_utt > budget:
-        sb //= 2
-    sb = min(sb, a.batch)
-    val, cores, t_step = cpu_port_run(a, sb, a.steps, a.warmup)
-    sample = f"{sb} utterances/step of the B={a.batch} T={a.T} workload, {a.steps} timed steps, torch {cores} threads"
-    line = {"metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+    val, cores, t_step, kind, sample, n_timed, n_warm = cpu_reference_run(a, a.steps, a.warmup)
+    line = {"metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": n_timed, "warmup": n_warm,
             "ms_per_step": round(t_step * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config_dict(a, a.gpus),
-            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def run_reference_cuda(a):
+    """SECONDARY line (SURVEY 2a "beat-this" bar): the unmodified reference module on the GPU -- torch + cuDNN GRU + cuBLAS,
+    none of this repo's kernels -- for the same train step.  Never the headline ratio."""
+    import torch
+    from oracle import torch_port as P
+    from neural_speech_decoder_b200.synthetic import make_batch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    for mode in ("fp32 (cudnn.allow_tf32 default)", "bf16 autocast"):
+        m, kind = reference_model(a, device="cuda")
+        m = m.to(dev).train()
+        opt = P.make_adam(m)
+        batch = [t.to(dev) for t in make_batch(a.batch, a.T, seed=1)]
+
+        def step():
+            if mode.startswith("bf16"):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return P.train_step(m, opt, *batch, **NOISE)
+            return P.train_step(m, opt, *batch, **NOISE)
+
+        for _ in range(max(a.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        print(json.dumps({"metric": METRIC, "value": round(a.batch / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+                          "warmup": max(a.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True, "impl": "reference-cuda",
+                          "kind": kind, "dtype": mode, "data": "synthetic", "config": config_dict(a, 1), "loss": float(loss),
+                          "note": "secondary: reference module on the GPU through torch/cuDNN/cuBLAS (no repo kernels); not the headline ratio"}),
+              flush=True)
+        del m, opt
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -200,6 +265,7 @@ def run_ours(a):
         opt.grad_scale = gs.grad_scale
         for p in model.parameters():                       # identical start on every rank
             dist.broadcast(p.data, 0)
+        model.invalidate_weight_copies()                    # .data writes are invisible to autograd's version counters
     host = [t.pin_memory() for t in make_batch(a.batch, a.T, seed=1 + rank)]
     devb = [t.to(dev) for t in host]
     frames = (a.T - 32) // 4 + 1
@@ -229,7 +295,8 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    _lib.profile_begin({"nsd_gemm_bf16", "nsd_gemm_bf16_x2", "nsd_gemm_f32", "nsd_adam_step", "nsd_frontend_fwd", "nsd_gru_fwd_bf16", "nsd_gru_bwd_bf16"})
+    _lib.profile_begin({"nsd_gemm_bf16", "nsd_gemm_bf16_x2", "nsd_gemm_f32", "nsd_adam_step", "nsd_frontend_fwd", "nsd_frontend_bwd",
+                        "nsd_gru_fwd_bf16", "nsd_gru_bwd_bf16"})
     l0 = _lib.lib().nsd_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -277,7 +344,8 @@ def run_ours(a):
     ach = gemm_flops_per_step(a, frames) * a.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     traffic, traffic_note = None, "no ncu capture found under profiles/"
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_gemm_traffic.json"))
+        tj = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
         traffic = tj["dram_bytes"]
         traffic_note = (f"ncu --set full, {tj['launch']}: dram read+write {tj['dram_bytes'] / 1e6:.0f} MB vs "
                         f"{tj['algorithmic_bytes'] / 1e6:.0f} MB algorithmic operand+result bytes of that launch")
@@ -297,12 +365,22 @@ def run_ours(a):
         gbs = n_upd * (30 if a.precision == "bf16" else 28) / (t_ms * 1e-3) / 1e9
         others.append({"kernel": "Adam (nsd_adam_step)", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
                        "frac": round(gbs / hbm, 4), "ms_per_step": round(t_ms, 3), "bytes_per_param": 30 if a.precision == "bf16" else 28})
+    esz = 2 if a.precision == "bf16" else 4
     if "nsd_frontend_fwd" in prof:
+        # algorithmic bytes per utterance = read X (T*N*4) + write patches (T'*N*K*e); what the kernel saves for its
+        # own backward is its choice and is listed as extra traffic, not counted as achieved bandwidth
         t_ms = prof["nsd_frontend_fwd"][1] / a.steps
-        byt = a.batch * (a.T * 256 * 4 + frames * 8192 * (2 if a.precision == "bf16" else 4) + 2 * a.T * 256 * 4)
+        byt = a.batch * (a.T * 256 * 4 + frames * 8192 * esz)
         gbs = byt / (t_ms * 1e-3) / 1e9
         others.append({"kernel": "K1 front end forward (nsd_frontend_fwd)", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
-                       "frac": round(gbs / hbm, 4), "ms_per_step": round(t_ms, 3)})
+                       "frac": round(gbs / hbm, 4), "ms_per_step": round(t_ms, 3), "algorithmic_bytes": byt,
+                       "extra_bytes_saved_for_backward": a.batch * K1_SAVED_TENSORS * a.T * 256 * 4})
+    if "nsd_frontend_bwd" in prof:
+        t_ms = prof["nsd_frontend_bwd"][1] / a.steps
+        byt = a.batch * frames * 8192 * esz                   # read dPatches (the dW/db outputs are 6.3 MB, L2-sized)
+        gbs = byt / (t_ms * 1e-3) / 1e9
+        others.append({"kernel": "K1 front end backward (nsd_frontend_bwd)", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
+                       "frac": round(gbs / hbm, 4), "ms_per_step": round(t_ms, 3), "algorithmic_bytes": byt})
     for k, nm in (("nsd_gru_fwd_bf16", "K3 recurrence forward"), ("nsd_gru_bwd_bf16", "K3 recurrence BPTT")):
         if k in prof:
             t_ms = prof[k][1] / a.steps
@@ -315,9 +393,8 @@ def run_ours(a):
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "roofline": roofline, "rooflines_other": others, "loss": float(lv)}
     if world == 1 and not a.no_cpu_baseline:
-        val, cores, t_step = cpu_port_run(a, 16, 1, 1)
-        line["cpu_baseline"] = {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"1 timed step (after 1 warm-up) on 16 of the {a.batch} utterances, T={a.T}, torch {cores} threads"}
+        val, cores, t_step, kind, sample, _, _ = cpu_reference_run(a, 3, 1, budget_s=30.0)     # same protocol as --impl reference, bounded to ~30 s
+        line["cpu_baseline"] = {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -363,6 +440,47 @@ def run_infer(a):
                               "us_per_output_frame": round(med * 1e6 / frames, 2), "us_per_20ms_bin": round(med * 1e6 / a.T, 2),
                               "utterances_per_s": round(B / med, 1), "calls": a.steps, "impl": "ours", "data": "synthetic"}), flush=True)
     nsd.set_default_precision("bf16")
+    if not a.no_cpu_baseline:
+        cpu_infer_reference(a, frames)
+
+
+def cpu_infer_reference(a, frames):
+    """The reference's eval lines on the host cores for the same inference call (trainer:299-320: forward -> log_softmax ->
+    per-utterance argmax / unique_consecutive / drop blank), unidirectional model, B=1 and B=32."""
+    import torch
+    from neural_speech_decoder_b200.synthetic import make_batch
+    a.uni = True
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m, kind = reference_model(a)
+    m.eval()
+    for B in (1, 32):
+        X, y, X_len, y_len, day = make_batch(B, a.T, seed=2)
+
+        @torch.no_grad()
+        def call():
+            pred = m.forward(X, day)                                                         # trainer:299
+            lens = ((X_len - m.kernelLen) / m.strideLen).to(torch.int32)                     # trainer:300
+            pred = pred.log_softmax(2)
+            out = []
+            for i in range(pred.shape[0]):                                                   # trainer:313-320
+                d = torch.argmax(pred[i, 0:int(lens[i]), :], dim=-1)
+                d = torch.unique_consecutive(d, dim=-1).numpy()
+                out.append(d[d != 0])
+            return out
+
+        call()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            call()
+            ts.append(time.perf_counter() - t0)
+        med = sorted(ts)[1]
+        print(json.dumps({"metric": "inference latency, unidirectional GRUDecoder + greedy CTC decode (host in, decoded ids out)",
+                          "batch": B, "T_bins": a.T, "frames": frames, "dtype": "f32", "ms_per_call": round(med * 1e3, 3),
+                          "us_per_output_frame": round(med * 1e6 / frames, 2), "us_per_20ms_bin": round(med * 1e6 / a.T, 2),
+                          "utterances_per_s": round(B / med, 1), "calls": 3, "impl": "reference", "kind": kind, "cores": cores,
+                          "data": "synthetic"}), flush=True)
 
 
 def run_stream(a):
@@ -408,5 +526,7 @@ if __name__ == "__main__":
         run_infer(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args)
     else:
         run_ours(args)

@@ -42,15 +42,19 @@ class FusedAdam(torch.optim.Optimizer):
                 touched.append(p)
                 step = st["step"] if step is None else step
                 if st["step"] != step:        # parameters that joined later: separate launch group
-                    ops.adam_step([p], [p.grad.contiguous()], [st["exp_avg"]], [st["exp_avg_sq"]], group["lr"],
-                                  *group["betas"], group["eps"], group["weight_decay"], st["step"], self.grad_scale)
+                    with torch.cuda.device(p.device):
+                        ops.adam_step([p], [p.grad.contiguous()], [st["exp_avg"]], [st["exp_avg_sq"]], group["lr"],
+                                      *group["betas"], group["eps"], group["weight_decay"], st["step"], self.grad_scale)
                     continue
                 ps.append(p); gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
                 ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
             sh = [self.shadows.slice_for(p) for p in ps] if self.shadows is not None else None
             if ps:
-                ops.adam_step(ps, gs, ms, vs, group["lr"], *group["betas"], group["eps"], group["weight_decay"], step,
-                              self.grad_scale, sh)
+                if any(p.device != ps[0].device for p in ps):
+                    raise RuntimeError("FusedAdam (B200): the parameters of one group must live on one device")
+                with torch.cuda.device(ps[0].device):
+                    ops.adam_step(ps, gs, ms, vs, group["lr"], *group["betas"], group["eps"], group["weight_decay"], step,
+                                  self.grad_scale, sh)
             # the kernels write through raw pointers: tell autograd (and the shadow cache) that the parameters changed
             if touched:
                 torch.autograd.graph.increment_version(touched)

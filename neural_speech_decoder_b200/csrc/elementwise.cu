@@ -1,4 +1,6 @@
 // Element-wise kernels of the path: inter-layer dropout (nn.GRU dropout=p, reference model.py:55).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nsd {
@@ -82,9 +84,44 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-tensor gather: up to 64 small f32 vectors copied to their destinations in ONE launch (the per-direction GRU
+// biases packed side by side, so that one GEMM epilogue / one recurrence launch serves both directions).
+constexpr int COPY_MAX_TENSORS = 64;
+struct CopyTable {
+    const float* src[COPY_MAX_TENSORS]; float* dst[COPY_MAX_TENSORS]; long long n[COPY_MAX_TENSORS];
+    int count;
+};
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ CopyTable tab) {
+    const int ti = blockIdx.y;
+    const float* __restrict__ S = tab.src[ti];
+    float* __restrict__ D = tab.dst[ti];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tab.n[ti]; i += (long long)gridDim.x * blockDim.x) D[i] = S[i];
+}
+
 }  // namespace nsd
 
 extern "C" {
+
+int nsd_multi_copy_f32(int n_tensors, const void* const* src, void* const* dst, const int64_t* numel, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(n_tensors >= 0, "multi_copy: bad n_tensors=%d", n_tensors);
+    for (int t0 = 0; t0 < n_tensors; t0 += COPY_MAX_TENSORS) {
+        CopyTable tab;
+        tab.count = std::min(COPY_MAX_TENSORS, n_tensors - t0);
+        long long nmax = 0;
+        for (int i = 0; i < tab.count; ++i) {
+            NSD_CHECK_ARG(numel[t0 + i] >= 0 && (numel[t0 + i] == 0 || (src[t0 + i] && dst[t0 + i])), "multi_copy: null tensor %d", t0 + i);
+            tab.src[i] = (const float*)src[t0 + i]; tab.dst[i] = (float*)dst[t0 + i]; tab.n[i] = numel[t0 + i];
+            nmax = std::max<long long>(nmax, numel[t0 + i]);
+        }
+        if (nmax == 0) continue;
+        const dim3 grid((unsigned)std::min<long long>((nmax + 255) / 256, 64), (unsigned)tab.count);
+        multi_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tab);
+        NSD_LAUNCH_CHECK();
+    }
+    return NSD_OK;
+}
 
 int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                   void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,

@@ -4,7 +4,7 @@
 // (24 rows of W_hh), keeps them resident in shared memory for the whole sequence and walks the
 // timesteps inside ONE cooperative launch with a grid-wide barrier per step; h_{t-1} is re-read from
 // L2 each step.  When the grid cannot be co-resident (large H) the same kernel body is launched once
-// per step with W_hh streamed from L2 instead.  The tensor-core path is in gru_tc.cu.
+// per step with W_hh streamed from L2 instead.  The tensor-core path is in gru_ts.cu.
 #include <cooperative_groups.h>
 
 #include "common.cuh"

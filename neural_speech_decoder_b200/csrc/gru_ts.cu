@@ -712,7 +712,10 @@ static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const C
     attrs[0].val.clusterDim.x = cs; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     attrs[1].id = cudaLaunchAttributeCooperative;
     attrs[1].val.cooperative = 1;
-    cfg.attrs = attrs; cfg.numAttrs = 2;
+    // NSD_GRU_NO_COOP=1 (profiling aid): drop the cooperative attribute, which Nsight Compute's kernel replay cannot combine
+    // with clusters.  Co-residency of the whole grid is still checked below; it then holds only while the GPU is otherwise idle.
+    static const bool no_coop = [] { const char* e = getenv("NSD_GRU_NO_COOP"); return e && e[0] == '1'; }();
+    cfg.attrs = attrs; cfg.numAttrs = no_coop ? 1 : 2;
     int max_clusters = 0;
     NSD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters * cs < grid) { set_error("gru_ts: %d CTAs in clusters of %d cannot be co-resident (max %d clusters)", grid, cs, max_clusters); return NSD_ERR_INVALID; }

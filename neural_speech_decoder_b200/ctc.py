@@ -76,13 +76,15 @@ class _CtcFunction(torch.autograd.Function):
 
 
 def _ctc_apply(act, targets, in_lens, tgt_lens, blank, reduction, zero_infinity, is_logits, tbc):
+    require_cuda(act, "log_probs")
     dev = act.device
     targets = _prep_targets(targets, dev)
     in_lens = _as_i32(in_lens, dev)
     tgt_lens = _as_i32(tgt_lens, dev)
     if reduction not in ("mean", "sum", "none"):
         raise ValueError(reduction)
-    return _CtcFunction.apply(act, targets, in_lens, tgt_lens, blank, reduction, zero_infinity, is_logits, tbc)
+    with torch.cuda.device(dev):            # raw-pointer launches must target the tensors' device, not the caller's current one
+        return _CtcFunction.apply(act, targets, in_lens, tgt_lens, blank, reduction, zero_infinity, is_logits, tbc)
 
 
 class CTCLoss(nn.Module):
@@ -107,7 +109,8 @@ def log_softmax_tbc(logits: torch.Tensor) -> torch.Tensor:
     """``logits.log_softmax(2).permute(1, 0, 2)`` (trainer:210, 301): logits [B,T',C] -> log-probs as a
     [T',B,C] view of a contiguous [B,T',C] buffer, exactly the layout the reference hands to CTCLoss."""
     require_cuda(logits, "logits")
-    return ops.log_softmax(logits.float().contiguous()).permute(1, 0, 2)
+    with torch.cuda.device(logits.device):
+        return ops.log_softmax(logits.float().contiguous()).permute(1, 0, 2)
 
 
 def out_lens(X_len: torch.Tensor, kernel_len: int, stride_len: int) -> torch.Tensor:
@@ -124,7 +127,8 @@ def greedy_decode(log_probs: torch.Tensor, lens: torch.Tensor, blank: int = 0) -
         log_probs = log_probs.float()
     T, B, C = log_probs.shape
     st, sb, sc = log_probs.stride()
-    return ops.greedy_decode_raw(log_probs, st, sb, sc, _as_i32(lens, log_probs.device), T, B, C, blank)
+    with torch.cuda.device(log_probs.device):
+        return ops.greedy_decode_raw(log_probs, st, sb, sc, _as_i32(lens, log_probs.device), T, B, C, blank)
 
 
 def decoded_to_lists(dec: torch.Tensor, dec_len: torch.Tensor) -> List[List[int]]:
@@ -135,8 +139,9 @@ def decoded_to_lists(dec: torch.Tensor, dec_len: torch.Tensor) -> List[List[int]
 def edit_distances(dec, dec_len, targets, target_lengths) -> torch.Tensor:
     """Levenshtein distance per utterance on the device (SequenceMatcher.distance(), trainer:322-330)."""
     dev = dec.device
-    return ops.edit_distance_raw(dec.contiguous(), _as_i32(dec_len, dev), _prep_targets(targets, dev),
-                                 _as_i32(target_lengths, dev))
+    with torch.cuda.device(dev):
+        return ops.edit_distance_raw(dec.contiguous(), _as_i32(dec_len, dev), _prep_targets(targets, dev),
+                                     _as_i32(target_lengths, dev))
 
 
 def phoneme_error_rate(log_probs, lens, targets, target_lengths, blank: int = 0) -> Tuple[int, int]:

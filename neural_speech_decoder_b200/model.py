@@ -137,6 +137,11 @@ class GRUDecoder(nn.Module):
                         getattr(g, f"bias_ih_l{layer}{sfx}"), getattr(g, f"bias_hh_l{layer}{sfx}")]
         return out
 
+    def invalidate_weight_copies(self) -> None:
+        """Call after writing parameters through ``.data`` / raw pointers (autograd cannot see those writes): the kept
+        bf16 operand copies are re-made by the next forward."""
+        self._shadows.invalidate()
+
     def check_errors(self) -> None:
         """Raise the deferred IndexError of an out-of-range dayIdx (the kernel flags it asynchronously)."""
         if self._err_flag is not None and int(self._err_flag.item()) != 0:
@@ -163,8 +168,16 @@ class GRUDecoder(nn.Module):
             cfg["seed"] = (int(torch.initial_seed()) * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF
         cfg["noise"] = (float(self.input_noise[0]), float(self.input_noise[1]), cfg["seed"] ^ 0x5DEECE66D) if noisy else None
         taps = self.gaussianSmoother.weight[0, 0].contiguous()
-        return _DecoderFunction.apply(cfg, neuralInput, dayIdx, taps, self.dayWeights, self.dayBias,
-                                      self.fc_decoder_out.weight, self.fc_decoder_out.bias, *self._gru_weights())
+        params = (self.dayWeights, self.dayBias, self.fc_decoder_out.weight, self.fc_decoder_out.bias, *self._gru_weights())
+        for p in params:
+            if p.device != neuralInput.device:
+                raise NsdError(f"GRUDecoder parameters live on {p.device} but neuralInput on {neuralInput.device}")
+        # grad mode is always off inside autograd.Function.forward: decide here whether the BPTT saves are needed
+        cfg["need_grad"] = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        # raw pointers are handed to the C ABI: the CUDA runtime's current device (kernel launches, TMA maps, cooperative
+        # launches) and the stream must be the tensors' device, whatever the caller's current device is
+        with torch.cuda.device(neuralInput.device):
+            return _DecoderFunction.apply(cfg, neuralInput, dayIdx, taps, *params)
 
 
 def _flat_views(shapes, dev, grad_sync, zero=False):
@@ -207,7 +220,7 @@ class _DecoderFunction(torch.autograd.Function):
         Tp = ops.n_frames(T, K, S)
         M = Tp * B
         day_idx = day_idx.to(device=dev, dtype=torch.int64).contiguous()
-        need_grad = any(t.requires_grad for t in (day_w, day_b, fc_w, fc_b) + tuple(gru_w))
+        need_grad = cfg.get("need_grad", True)
         patches, ys, z = ops.frontend_fwd(x, day_idx, day_w.detach().contiguous(), day_b.detach().contiguous(), taps,
                                           K, S, torch.float32, cfg["err_flag"], cfg.get("noise"))
         inp = patches
@@ -244,10 +257,15 @@ class _DecoderFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
+        with torch.cuda.device(dlogits.device):
+            if ctx.cfg["precision"] != "fp32":
+                from .model_tc import decoder_backward_tc
+                return decoder_backward_tc(ctx, dlogits)
+            return _DecoderFunction._backward_f32(ctx, dlogits)
+
+    @staticmethod
+    def _backward_f32(ctx, dlogits):
         cfg = ctx.cfg
-        if cfg["precision"] != "fp32":
-            from .model_tc import decoder_backward_tc
-            return decoder_backward_tc(ctx, dlogits)
         K, S, H, L, D = cfg["K"], cfg["S"], cfg["H"], cfg["L"], cfg["D"]
         B, T, N, Tp = ctx.dims
         M = Tp * B

@@ -17,14 +17,22 @@ from . import ops
 
 class Bf16Shadows:
     """bf16 operand copies of the fp32 master weights, kept across steps.  A copy is valid while the parameter's
-    (data_ptr, autograd version) is the one it was made from; anything that modifies a parameter in place (optimizers,
-    load_state_dict, broadcasts) bumps the version and the copy is re-made by the next forward.  FusedAdam, when attached,
-    rewrites the copies inside its update kernel and marks them fresh, so a training step does no weight casts at all."""
+    (data_ptr, autograd version) is the one it was made from; anything that modifies a parameter in place THROUGH
+    AUTOGRAD-VISIBLE OPS (optimizers, load_state_dict, ``p.copy_``/``dist.broadcast(p)`` under no_grad) bumps the version and
+    the copy is re-made by the next forward.  FusedAdam, when attached, rewrites the copies inside its update kernel and
+    marks them fresh, so a training step does no weight casts at all.
+    Writes through ``p.data`` (``p.data.copy_()``, ``p.data[...] =``, NCCL broadcast of ``p.data``, raw pointers) do NOT bump
+    the version: call ``invalidate()`` (or ``GRUDecoder.invalidate_weight_copies()``) after them."""
 
     def __init__(self):
         self.bufs = {}        # key -> stacked bf16 buffer [D*R, C]
         self.tags = {}        # (key, d) -> (data_ptr, version) of the fp32 source
         self.where = {}       # data_ptr of the fp32 source -> (key, d)
+
+    def invalidate(self) -> None:
+        """Forget every copy's validity (the buffers are kept and re-filled by the next forward)."""
+        self.tags.clear()
+        self.where.clear()
 
     def stacked(self, key, ws):
         """Up-to-date bf16 copy of the D fp32 matrices ``ws`` ([R, C] each) stacked by rows."""
@@ -38,8 +46,11 @@ class Bf16Shadows:
                 self.tags.pop((key, d), None)
         for d, w in enumerate(ws):
             tag = (w.data_ptr(), w._version)
-            if self.tags.get((key, d)) != tag:
+            old = self.tags.get((key, d))
+            if old != tag:
                 ops.cast_transpose_into(w.detach(), buf[d * R:(d + 1) * R], None)
+                if old is not None and old[0] != tag[0] and self.where.get(old[0]) == (key, d):
+                    del self.where[old[0]]               # the parameter was reallocated: its old address may be reused
                 self.tags[(key, d)] = tag
                 self.where[w.data_ptr()] = (key, d)
         return buf
@@ -50,6 +61,8 @@ class Bf16Shadows:
             return None
         key, d = loc
         buf = self.bufs[key]
+        if p.dim() != 2 or self.tags.get(loc, (None,))[0] != p.data_ptr():
+            return None
         R = p.shape[0]
         if buf.shape[1] != p.shape[1] or (d + 1) * R > buf.shape[0]:
             return None
@@ -68,13 +81,18 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
     Tp = ops.n_frames(T, K, S)
     M = Tp * B
     day_idx = day_idx.to(device=dev, dtype=torch.int64).contiguous()
-    need_grad = any(t.requires_grad for t in (day_w, day_b, fc_w, fc_b) + tuple(gru_w))
+    need_grad = cfg.get("need_grad", True)
     patches, ys, z = ops.frontend_fwd(x, day_idx, day_w.detach().contiguous(), day_b.detach().contiguous(), taps,
                                       K, S, torch.bfloat16, cfg["err_flag"], cfg.get("noise"))
     inp = patches                                            # bf16 [M, in_l]
     sh = cfg.get("shadows") or Bf16Shadows()                 # the module's cache of bf16 weight copies (a throw-away one otherwise)
     layers = []
     hseq = None
+    # both directions run in one GEMM / one recurrence launch: their bias vectors side by side, packed in ONE launch
+    if D > 1:
+        bias_all = torch.empty((L, 2, D * 3 * H), device=dev, dtype=torch.float32)
+        ops.multi_copy([gru_w[(l * D + d) * 4 + 2 + k].detach() for l in range(L) for k in range(2) for d in range(D)],
+                       [bias_all[l, k, d * 3 * H:(d + 1) * 3 * H] for l in range(L) for k in range(2) for d in range(D)])
     for l in range(L):
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
@@ -86,8 +104,7 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
             w_hhT_bf = torch.empty((D * H, 3 * H), device=dev, dtype=torch.bfloat16)
             for d in range(D):
                 ops.cast_transpose_into(w_hh_bf[d * 3 * H:(d + 1) * 3 * H], None, w_hhT_bf[d * H:(d + 1) * H])
-        b_ih = torch.cat([w[2] for w in ws]) if D > 1 else ws[0][2]
-        b_hh = torch.cat([w[3] for w in ws]) if D > 1 else ws[0][3]
+        b_ih, b_hh = (bias_all[l, 0], bias_all[l, 1]) if D > 1 else (ws[0][2], ws[0][3])
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
         ops.gemm(False, True, M, D * 3 * H, in_l, inp, in_l, w_ih_bf, in_l, gi, D * 3 * H, bias=b_ih.contiguous())
         if cfg["p_drop"] > 0 and l < L - 1:      # inter-layer dropout fused into the recurrence's epilogue

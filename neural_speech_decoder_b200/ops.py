@@ -228,6 +228,18 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
          float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), stream())
 
 
+def multi_copy(srcs, dsts):
+    """Copy the f32 tensors ``srcs[i]`` into the equally sized contiguous views ``dsts[i]`` in one launch."""
+    import ctypes as C
+    n = len(srcs)
+    if n == 0:
+        return
+    for s_, d_ in zip(srcs, dsts):
+        assert s_.dtype == torch.float32 and d_.dtype == torch.float32 and s_.numel() == d_.numel() and s_.is_contiguous() and d_.is_contiguous()
+    call("nsd_multi_copy_f32", n, (C.c_void_p * n)(*[t.data_ptr() for t in srcs]), (C.c_void_p * n)(*[t.data_ptr() for t in dsts]),
+         (C.c_int64 * n)(*[t.numel() for t in srcs]), stream())
+
+
 def greedy_decode_raw(act, st, sb, sc, lens, T, B, Cc, blank) -> Tuple[torch.Tensor, torch.Tensor]:
     out = torch.empty((B, T), device=act.device, dtype=torch.int64)
     out_len = torch.empty(B, device=act.device, dtype=torch.int32)

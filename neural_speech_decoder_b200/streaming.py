@@ -113,7 +113,8 @@ class StreamingDecoder:
         j1 = complete_frames(self.n_bins, self.K, self.S, self.right) - 1
         if j1 < self.next_frame:
             return None
-        out = self._emit(self.next_frame, j1, self.S * j1 + self.K + self.right)
+        with torch.cuda.device(self.dev):
+            out = self._emit(self.next_frame, j1, self.S * j1 + self.K + self.right)
         self.next_frame = j1 + 1
         self._trim()
         return out
@@ -128,7 +129,8 @@ class StreamingDecoder:
         j1 = (self.n_bins - self.K) // self.S
         if j1 < self.next_frame:
             return None
-        out = self._emit(self.next_frame, j1, self.n_bins)
+        with torch.cuda.device(self.dev):
+            out = self._emit(self.next_frame, j1, self.n_bins)
         self.next_frame = j1 + 1
         self._trim()
         return out

@@ -35,6 +35,14 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
     ``white_noise_sd`` / ``constant_offset_sd`` (args["whiteNoiseSD"], args["constantOffsetSD"]): the in-loop
     augmentation of trainer:194-201, generated inside the front-end kernel instead of in extra passes over X."""
     model.grad_sync = grad_sync
+    # the buckets are all-reduced with SUM: the 1/world average is folded into the Adam kernel.  Adam with eps=0.1 and
+    # L2-in-gradient is NOT scale-invariant, so the scale must follow the sync object on every step.
+    want_scale = grad_sync.grad_scale if grad_sync is not None else 1.0
+    if isinstance(optimizer, FusedAdam):
+        optimizer.grad_scale = want_scale
+    elif grad_sync is not None and grad_sync.world > 1:
+        raise RuntimeError("train_step(grad_sync=...) sums gradients over ranks; use FusedAdam (make_optimizer), which folds the "
+                           "1/world_size average into its update, or divide the gradients yourself")
     model.input_noise = (white_noise_sd, constant_offset_sd) if (white_noise_sd or constant_offset_sd) else None
     pred = model.forward(X, dayIdx)                                         # trainer:208
     lens = _ctc.out_lens(X_len, model.kernelLen, model.strideLen)           # trainer:209

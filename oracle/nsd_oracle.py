@@ -152,6 +152,8 @@ def _sigmoid(x):
 
 def gru_dir_fwd(x, w_ih, w_hh, b_ih, b_hh, reverse=False):
     """One layer, one direction, h0 = 0 (model.py:104-117).  x: [B,T',in].
+    ``w_ih is None``: x already IS the input projection gi [B,T',3H] (recurrence-only checks at sizes where an
+    identity W_ih would cost a 3H x 3H matmul per row).
     Gate row order [r,z,n]:
       gi = x W_ih^T + b_ih ; gh = h_{t-1} W_hh^T + b_hh
       r = s(gi_r+gh_r) ; z = s(gi_z+gh_z) ; n = tanh(gi_n + r*gh_n)
@@ -160,7 +162,7 @@ def gru_dir_fwd(x, w_ih, w_hh, b_ih, b_hh, reverse=False):
     Returns (hseq [B,T',H], saved)."""
     B, Tp, _ = x.shape
     H = w_hh.shape[1]
-    gi = x @ w_ih.T + b_ih                      # time-batched input projection (a5)
+    gi = x if w_ih is None else x @ w_ih.T + b_ih      # time-batched input projection (a5)
     hseq = np.zeros((B, Tp, H), dtype=x.dtype)
     r_s = np.zeros_like(hseq); z_s = np.zeros_like(hseq)
     n_s = np.zeros_like(hseq); hn_s = np.zeros_like(hseq); hp_s = np.zeros_like(hseq)
@@ -201,6 +203,9 @@ def gru_dir_bwd(dhseq, saved, w_ih, w_hh, reverse=False):
         dh = dht * z + dgh[:, t] @ w_hh
     dgi2 = dgi.reshape(B * Tp, 3 * H)
     dgh2 = dgh.reshape(B * Tp, 3 * H)
+    if w_ih is None:                            # x was gi itself: dx = dgi, no input weights
+        dw_hh = dgh2.T @ saved["hprev"].reshape(B * Tp, H)
+        return dgi, None, dw_hh, dgi2.sum(0), dgh2.sum(0)
     dx = (dgi2 @ w_ih).reshape(B, Tp, -1)
     dw_ih = dgi2.T @ x.reshape(B * Tp, -1)
     dw_hh = dgh2.T @ saved["hprev"].reshape(B * Tp, H)

@@ -72,7 +72,7 @@ class PortGRUDecoder(nn.Module):
         x = F.softsign(x)                                                    # model.py:93
         x = F.unfold(x.permute(0, 2, 1).unsqueeze(3), (self.kernelLen, 1), stride=self.strideLen).permute(0, 2, 1)  # :96-101
         D = 2 if self.bidirectional else 1
-        h0 = torch.zeros(self.layer_dim * D, x.size(0), self.hidden_dim, dtype=x.dtype)   # model.py:104-117
+        h0 = torch.zeros(self.layer_dim * D, x.size(0), self.hidden_dim, dtype=x.dtype, device=x.device)   # model.py:104-117
         hid, _ = self.gru(x, h0)                                             # model.py:119
         return self.fc(hid)                                                  # model.py:122
 
@@ -83,9 +83,9 @@ def make_adam(model, lr=0.02, l2=1e-5):
 
 def train_step(model, opt, X, y, X_len, y_len, dayIdx, white_noise_sd: float = 0.0, constant_offset_sd: float = 0.0):
     if white_noise_sd > 0:                                                           # trainer:194-196
-        X = X + torch.randn(X.shape) * white_noise_sd
+        X = X + torch.randn(X.shape, device=X.device) * white_noise_sd
     if constant_offset_sd > 0:                                                       # trainer:198-201
-        X = X + torch.randn([X.shape[0], 1, X.shape[2]]) * constant_offset_sd
+        X = X + torch.randn([X.shape[0], 1, X.shape[2]], device=X.device) * constant_offset_sd
     pred = model(X, dayIdx)                                                          # trainer:208
     out_lens = ((X_len - model.kernelLen) / model.strideLen).to(torch.int32)         # trainer:209
     log_probs = pred.log_softmax(2).permute(1, 0, 2)                                 # trainer:210

@@ -13,9 +13,14 @@ import torch.distributed as dist
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    backend = os.environ.get("NSD_DP_BACKEND", "nccl")     # "gloo": both ranks may share ONE GPU (NCCL refuses duplicate devices)
+    local = local % torch.cuda.device_count()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group(backend)
     import neural_speech_decoder_b200 as nsd
     from neural_speech_decoder_b200.parallel import GradSync
     from neural_speech_decoder_b200.synthetic import fill_trained_like_, make_batch
@@ -36,10 +41,10 @@ def main():
         args = dict(lrStart=0.02, lrEnd=0.02, nBatch=100, l2_decay=1e-5)
         m = fresh()
         opt, sched = nsd.make_optimizer(m, args)
-        gs = GradSync(world)
-        opt.grad_scale = gs.grad_scale
+        gs = GradSync(world)                                    # train_step folds gs.grad_scale into the optimizer itself
         shard = [t[rank * per:(rank + 1) * per].contiguous().to(dev) for t in full]
         loss = nsd.train_step(m, opt, *shard, scheduler=sched, grad_sync=gs)
+        assert opt.grad_scale == gs.grad_scale
         losses = [torch.zeros_like(loss) for _ in range(world)]
         dist.all_gather(losses, loss)
         torch.cuda.synchronize()

@@ -1,0 +1,252 @@
+"""Parity AT THE BENCHMARKED SHAPES (BASELINE configs[1]: B=64, T=500 -> T'=118; configs[4]: T=2000 -> T'=493).
+
+The small fixtures (T' <= 13) cannot show what 118 / 493 sequential recurrent steps do to a bf16 state exchange,
+mbarrier parities, ring wrap-arounds or tanh.approx, so this file runs
+  * the K3 tensor-core recurrence + BPTT alone against the fp64 numpy oracle (oracle/nsd_oracle.py:gru_dir_fwd/bwd)
+    at (B=64, T'=118, H=1024, D=2), (B=32, T'=493, ...) and the unidirectional form, printing the error against the
+    step index so growth is visible;
+  * the whole drop-in module (fp32 path and bf16 path) against the CPU torch-operator port of the reference
+    (oracle/torch_port.py, pinned to the reference's own fixtures) run in fp64 on the box's host cores with the same
+    seeded weights and the same synthetic batch: logits, loss and EVERY gradient.
+Measured errors are written to gpurun_out/parity_fullshape.json; the asserted tolerances are <= 3x those measurements
+(DESIGN.md section 2 tabulates them).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import nsd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from neural_speech_decoder_b200 import ops
+    import neural_speech_decoder_b200 as nsd
+    from neural_speech_decoder_b200.synthetic import fill_trained_like_, make_batch
+
+DEV = "cuda"
+COMP = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, dropout=0.0, strideLen=4, kernelLen=32,
+            gaussianSmoothWidth=2.0)
+
+
+def record(key, val):
+    """Append a measurement to gpurun_out/parity_fullshape.json (merged back by gpurun; scratch elsewhere)."""
+    path = os.path.join(ROOT, "gpurun_out", "parity_fullshape.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    try:
+        cur = json.load(open(path))
+    except Exception:
+        cur = {}
+    cur[key] = val
+    json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+
+
+def bf(a):
+    return torch.from_numpy(np.asarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy().astype(np.float64)
+
+
+def cu(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(DEV)
+
+
+# Tolerances of the K3-only check: (max |h - h_ref| over everything [h in (-1,1)], max |gate - ref|, BPTT max err / max |dgi|,
+# dW_hh max err / max |dW_hh|).  Measured on B200 (gpurun_out/parity_fullshape.json -> DESIGN.md section 2) x <= 3.
+K3_TOL = dict(h=2.5e-2, gates=4e-2, dgi=4e-2, dwhh=4e-2)
+
+
+@pytest.mark.parametrize("B,Tp,H,D", [(64, 118, 1024, 2), (32, 493, 1024, 2), (64, 118, 1024, 1), (256, 30, 1024, 2)])
+def test_gru_tc_benchmark_shape(B, Tp, H, D):
+    rng = np.random.default_rng(1000 + Tp + B + D)
+    M = Tp * B
+    w_hh = [bf(rng.standard_normal((3 * H, H)) / np.sqrt(H)) for _ in range(D)]
+    b_hh = [rng.standard_normal(3 * H) * 0.1 for _ in range(D)]
+    gi = (rng.standard_normal((B, Tp, D * 3 * H)) * 0.8).astype(np.float32).astype(np.float64)
+    href, saved = [], []
+    for d in range(D):
+        h, sv = O.gru_dir_fwd(gi[:, :, d * 3 * H:(d + 1) * 3 * H], None, w_hh[d], None, b_hh[d], d == 1)
+        href.append(h); saved.append(sv)
+    href = np.concatenate(href, axis=2)
+    gi_tm = cu(gi.transpose(1, 0, 2).reshape(M, D * 3 * H))
+    w_bf = cu(np.concatenate(w_hh, 0), torch.bfloat16)
+    hseq, hseq_bf, sv = ops.gru_fwd_bf16(gi_tm, w_bf, cu(np.concatenate(b_hh)), Tp, B, H, D, 0, True)
+    got = hseq.view(Tp, B, D * H).permute(1, 0, 2).cpu().numpy().astype(np.float64)
+    # error against the number of recurrent steps taken (forward direction: step = t; reverse: step = Tp-1-t)
+    err_t = np.abs(got - href).max(axis=0)                                   # [Tp, D*H]
+    by_step = [err_t[:, :H].max(axis=1)] + ([err_t[::-1, H:].max(axis=1)] if D == 2 else [])
+    marks = sorted({0, 1, Tp // 8, Tp // 4, Tp // 2, 3 * Tp // 4, Tp - 1})
+    growth = {f"dir{d}": {int(s): float(e[s]) for s in marks} for d, e in enumerate(by_step)}
+    err = float(err_t.max())
+    print(f"K3 fwd B={B} T'={Tp} H={H} D={D}: max|h-ref| = {err:.3e}; by step {growth}")
+    assert torch.equal(hseq_bf, hseq.to(torch.bfloat16))
+    gate_err = 0.0
+    for d in range(D):
+        for name, t in zip(("r", "z", "n", "hn"), sv):
+            ref = saved[d][name].transpose(1, 0, 2).reshape(M, H)
+            gate_err = max(gate_err, float(np.abs(t[d].cpu().numpy() - ref).max()))
+    # the error must not grow with the step count: late steps within 2x of the worst early step (plus a floor)
+    for e in by_step:
+        early, late = e[:max(8, Tp // 8)].max(), e[-max(8, Tp // 8):].max()
+        assert late <= 2.0 * early + 2e-3, (early, late)
+    # BPTT on the oracle's own saved activations (so that the check isolates the backward recurrence)
+    dh = rng.standard_normal((B, Tp, D * H)).astype(np.float32).astype(np.float64)
+    dh_tm = cu(dh.transpose(1, 0, 2).reshape(M, D * H))
+    sv_ref = tuple(cu(np.stack([saved[d][k].transpose(1, 0, 2).reshape(M, H) for d in range(D)])) for k in ("r", "z", "n", "hn"))
+    hseq_ref = cu(href.transpose(1, 0, 2).reshape(M, D * H))
+    whT = torch.cat([cu(w_hh[d], torch.bfloat16).T.contiguous() for d in range(D)], 0)
+    db_ih, db_hh = torch.empty(D * 3 * H, device=DEV), torch.empty(D * 3 * H, device=DEV)
+    dgi, dgh = ops.gru_bwd_bf16(dh_tm, hseq_ref, sv_ref, whT, Tp, B, H, D, 0, 0.0, 0, db_ih, db_hh)
+    dgi_np, dgh_np = dgi.float().cpu().numpy().astype(np.float64), dgh.float().cpu().numpy().astype(np.float64)
+    e_dgi = e_dwhh = e_db = 0.0
+    bwd_growth = {}
+    for d in range(D):
+        dx_ref, _, dwh_ref, dbi_ref, dbh_ref = O.gru_dir_bwd(dh[:, :, d * H:(d + 1) * H], saved[d], None, w_hh[d], d == 1)
+        sl = slice(d * 3 * H, (d + 1) * 3 * H)
+        ref_tm = dx_ref.transpose(1, 0, 2).reshape(Tp, B, 3 * H)
+        got_tm = dgi_np[:, sl].reshape(Tp, B, 3 * H)
+        scale = np.abs(ref_tm).max()
+        et = np.abs(got_tm - ref_tm).max(axis=(1, 2)) / scale                # by time index
+        et = et if d == 1 else et[::-1]                                      # -> by BPTT step
+        bwd_growth[f"dir{d}"] = {int(s): float(et[s]) for s in marks}
+        e_dgi = max(e_dgi, float(et.max()))
+        hprev = saved[d]["hprev"].transpose(1, 0, 2).reshape(M, H)
+        dwh = dgh_np[:, sl].T @ hprev
+        e_dwhh = max(e_dwhh, float(np.abs(dwh - dwh_ref).max() / max(1.0, np.abs(dwh_ref).max())))
+        e_db = max(e_db, float(np.abs(db_ih[sl].cpu().numpy() - dbi_ref).max() / np.abs(dbi_ref).max()),
+                   float(np.abs(db_hh[sl].cpu().numpy() - dbh_ref).max() / np.abs(dbh_ref).max()))
+    print(f"K3 bwd: max err/max|dgi| = {e_dgi:.3e} by step {bwd_growth}; dW_hh {e_dwhh:.3e}; db {e_db:.3e}; gates {gate_err:.3e}")
+    record(f"k3_B{B}_Tp{Tp}_H{H}_D{D}", dict(h=err, gates=gate_err, dgi=e_dgi, dwhh=e_dwhh, db=e_db, fwd_by_step=growth,
+                                             bwd_by_step=bwd_growth))
+    assert err < K3_TOL["h"] and gate_err < K3_TOL["gates"] and e_dgi < K3_TOL["dgi"] and e_dwhh < K3_TOL["dwhh"]
+    assert e_db < 2e-2
+
+
+def test_gru_tc_fused_dropout_benchmark_shape():
+    """Fused dropout forms at (64, 118, 1024, 2): bit-equal to the separate kernels (as at the small shapes)."""
+    B, Tp, H, D = 64, 118, 1024, 2
+    torch.manual_seed(5)
+    M = Tp * B
+    gi = torch.randn(M, D * 3 * H, device=DEV)
+    w = (torch.randn(D * 3 * H, H, device=DEV) / np.sqrt(H)).to(torch.bfloat16)
+    b = torch.randn(D * 3 * H, device=DEV) * 0.1
+    hseq, hbf, sv, hdrop = ops.gru_fwd_bf16(gi, w, b, Tp, B, H, D, False, True, 0.4, 99)
+    hseq2, hbf2, sv2 = ops.gru_fwd_bf16(gi, w, b, Tp, B, H, D, False, True)
+    assert torch.equal(hseq, hseq2) and torch.equal(hdrop, ops.dropout(hbf, 0.4, 99))
+    wT = torch.cat([w[d * 3 * H:(d + 1) * 3 * H].T.contiguous() for d in range(D)], 0)
+    dh = torch.randn(M, D * H, device=DEV)
+    dgi, dgh = ops.gru_bwd_bf16(dh, hseq, sv, wT, Tp, B, H, D, False, 0.4, 99)
+    dgi2, dgh2 = ops.gru_bwd_bf16(ops.dropout(dh, 0.4, 99), hseq, sv, wT, Tp, B, H, D, False)
+    assert torch.equal(dgi, dgi2) and torch.equal(dgh, dgh2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole module vs the CPU port of the reference (fp64) at the benchmark configuration
+# ---------------------------------------------------------------------------------------------------------------------
+_PORT_CACHE = {}
+
+
+def port_reference(bidirectional, B, T):
+    """fp64 CPU run of oracle/torch_port.PortGRUDecoder (reference operators) with fill_trained_like_ weights (seed 7),
+    dropout 0: logits, loss, all gradients.  Cached per configuration (both precisions compare against the same run)."""
+    key = (bidirectional, B, T)
+    if key in _PORT_CACHE:
+        return _PORT_CACHE[key]
+    from oracle import torch_port as P
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    ours = nsd.GRUDecoder(device="cpu", bidirectional=bidirectional, **COMP)
+    fill_trained_like_(ours, seed=7)
+    sd = {k: v.detach().clone() for k, v in ours.state_dict().items()}
+    port = P.PortGRUDecoder(bidirectional=bidirectional, **COMP)
+    port.load_reference_state(sd)
+    port = port.double().eval()
+    X, y, X_len, y_len, day = make_batch(B, T, seed=11, ragged=True)
+    pred = port(X.double(), day)
+    pred.retain_grad()
+    lens = ((X_len - port.kernelLen) / port.strideLen).to(torch.int32)                    # trainer:209
+    lp = pred.log_softmax(2).permute(1, 0, 2)                                             # trainer:210
+    loss = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(lp, y, lens, y_len).sum()
+    loss.backward()
+    grads = {}
+    for k, p in port.named_parameters():
+        name = k.replace("gru.", "gru_decoder.", 1) if k.startswith("gru.") else k.replace("fc.", "fc_decoder_out.", 1) if k.startswith("fc.") else k
+        grads[name] = p.grad.numpy().copy()
+    out = dict(sd=sd, batch=(X, y, X_len, y_len, day), logits=pred.detach().numpy(), dlogits=pred.grad.numpy().copy(),
+               loss=float(loss), grads=grads, lens=lens.numpy())
+    _PORT_CACHE[key] = out
+    return out
+
+
+# bf16 whole-model tolerances (stated separately from fp32, north star): measured values x <= 3, see DESIGN.md section 2
+BF16_TOL = dict(logits_abs=6e-2, loss_rel=2e-2, grad_rel_l2=0.1, argmax_agree=0.9)
+
+
+@pytest.mark.parametrize("bidirectional,precision,B,T", [(True, "fp32", 64, 500), (True, "bf16", 64, 500), (False, "bf16", 64, 500),
+                                                         (True, "bf16", 8, 2000)])
+def test_model_benchmark_shape_vs_reference_port(bidirectional, precision, B, T):
+    ref = port_reference(bidirectional, B, T)
+    nsd.set_default_precision(precision)
+    try:
+        torch.manual_seed(0)
+        m = nsd.GRUDecoder(device=DEV, bidirectional=bidirectional, **COMP)
+    finally:
+        nsd.set_default_precision("fp32")
+    m.load_state_dict(ref["sd"], strict=True)
+    m = m.to(DEV).eval()
+    X, y, X_len, y_len, day = (t.to(DEV) for t in ref["batch"])
+    pred = m.forward(X, day)
+    pred.retain_grad()
+    lens = nsd.out_lens(X_len, m.kernelLen, m.strideLen)
+    loss = nsd.ctc_loss_from_logits(pred, y, lens, y_len)
+    loss.backward()
+    m.check_errors()
+    assert np.array_equal(lens.cpu().numpy(), ref["lens"])
+    got = pred.detach().cpu().numpy().astype(np.float64)
+    rl = ref["logits"]
+    e_log = float(np.abs(got - rl).max())
+    # error of the logits against the frame index (both directions contribute to every frame; growth would show at the ends)
+    e_t = np.abs(got - rl).max(axis=(0, 2))
+    Tp = rl.shape[1]
+    marks = sorted({0, Tp // 8, Tp // 4, Tp // 2, 3 * Tp // 4, Tp - 1})
+    by_frame = {int(t): float(e_t[t]) for t in marks}
+    e_loss = abs(loss.item() - ref["loss"]) / abs(ref["loss"])
+    agree = float((got.argmax(-1) == rl.argmax(-1)).mean())
+    e_dlog = float(np.abs(pred.grad.cpu().numpy() - ref["dlogits"]).max() / np.abs(ref["dlogits"]).max())
+    params = dict(m.named_parameters())
+    gerr = {}
+    for n, gref in ref["grads"].items():
+        g = params[n].grad
+        assert g is not None, n
+        gg = g.detach().cpu().numpy().astype(np.float64)
+        gerr[n] = (float(np.linalg.norm(gg - gref) / max(np.linalg.norm(gref), 1e-30)), float(np.abs(gg - gref).max() / max(np.abs(gref).max(), 1e-30)))
+    worst = max(gerr.items(), key=lambda kv: kv[1][0])
+    tag = f"model_{'bi' if bidirectional else 'uni'}_{precision}_B{B}_T{T}"
+    print(f"{tag}: logits max abs err {e_log:.3e} (|ref| max {np.abs(rl).max():.2f}) by frame {by_frame}; loss {loss.item():.6f} vs "
+          f"{ref['loss']:.6f} (rel {e_loss:.2e}); argmax agreement {agree:.4f}; dlogits {e_dlog:.2e}; worst grad {worst[0]} rel L2 {worst[1][0]:.3e}")
+    for n, (l2, mx) in sorted(gerr.items()):
+        print(f"    grad {n:44s} rel L2 {l2:.3e}  max/max {mx:.3e}")
+    record(tag, dict(logits_abs=e_log, logits_ref_max=float(np.abs(rl).max()), logits_by_frame=by_frame, loss=loss.item(), loss_ref=ref["loss"],
+                     loss_rel=e_loss, argmax_agree=agree, dlogits_rel=e_dlog, grad_rel_l2={k: v[0] for k, v in gerr.items()},
+                     grad_max_rel={k: v[1] for k, v in gerr.items()}))
+    if precision == "fp32":
+        # north star: rtol 1e-3 on logits, loss and gradients (atol: logits and gradient entries cross zero)
+        np.testing.assert_allclose(got, rl, rtol=1e-3, atol=1e-4 * np.abs(rl).max())
+        assert e_loss < 1e-3
+        for n, gref in ref["grads"].items():
+            np.testing.assert_allclose(params[n].grad.cpu().numpy(), gref, rtol=1e-3, atol=1e-4 * np.abs(gref).max(), err_msg=n)
+        # bit-exact greedy decode + PER given identical log-probs (the reference's own fp64 -> fp32 log-probs)
+        lp = torch.from_numpy(rl).float().log_softmax(2).permute(1, 0, 2)
+        dec, dec_len = nsd.greedy_decode(lp.to(DEV), lens)
+        want = O.greedy_decode(lp.numpy(), ref["lens"])
+        assert nsd.decoded_to_lists(dec, dec_len) == want
+        dist, tot = nsd.phoneme_error_rate(lp.to(DEV), lens, y, y_len)
+        assert (dist, tot) == O.phoneme_error_rate(want, ref["batch"][1].numpy(), ref["batch"][3].numpy())
+    else:
+        assert e_log < BF16_TOL["logits_abs"]
+        assert e_loss < BF16_TOL["loss_rel"]
+        assert agree >= BF16_TOL["argmax_agree"]
+        for n, (l2, _) in gerr.items():
+            assert l2 < BF16_TOL["grad_rel_l2"], (n, l2)

@@ -115,3 +115,24 @@ def test_torch_port_matches_reference_fixture(name):
     np.testing.assert_allclose(pred.detach().numpy(), g["logits"], rtol=1e-5, atol=1e-6)
     loss = P.train_step(m, P.make_adam(m), X, y, X_len, y_len, day)
     np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+
+
+def test_compiled_reference_equals_port():
+    """oracle/_ref (the reference's own GRUDecoder, byte-compiled from /root/reference by oracle/build_ref.py) and the
+    torch-operator port give the same logits for the same state: bench.py's "reference" and "port" kinds are interchangeable."""
+    import torch
+    from oracle import torch_port as P
+    from oracle.build_ref import load_reference_decoder
+    Ref = load_reference_decoder()
+    if Ref is None:
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    kw = dict(neural_dim=16, n_classes=6, hidden_dim=24, layer_dim=2, nDays=3, dropout=0.0, strideLen=4, kernelLen=8,
+              gaussianSmoothWidth=2.0, bidirectional=True)
+    torch.manual_seed(3)
+    ref = Ref(device="cpu", **kw).eval()
+    port = P.PortGRUDecoder(**kw).eval()
+    port.load_reference_state(ref.state_dict())
+    X, day = torch.randn(3, 50, 16), torch.tensor([0, 2, 1])
+    with torch.no_grad():
+        a, b = ref(X, day), port(X, day)
+    assert torch.allclose(a, b, rtol=0, atol=1e-6)
