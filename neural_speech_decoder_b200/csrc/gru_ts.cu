@@ -14,11 +14,15 @@
 //     lane (= one gate row), converts its row to bf16 and stages it in the outbox of the CTA that finalises that unit;
 //     one cp.async.bulk per peer completes the peer's inbox mbarrier.  Each CTA finalises 16 (BPTT: 32) units: gate math
 //     for (batch row, 4 units) per thread and pass, bf16 state stored first and published, fp32 state / saved gates after.
-//   * steps are separated by a grid barrier per (direction, batch group): a release/acquire counter in global memory
-//     that only the TMA-producer thread polls.
-//   * LATENCY HIDING: the batch is cut into groups of 32 rows (UMMA N = 32) that are independent sequences.  Two
-//     groups are in flight at once, each with its own smem operand buffer, TMEM accumulator, in/outbox and epilogue
-//     warpgroup, so the barrier + exchange latency of one group runs under the MMAs and gate math of the other.
+//   * steps are separated by per-cluster ("zone") step counters in global memory (release add / acquire polls).
+//   * OPERAND RING: the previous state arrives as 64-column boxes, one TMA per box into a ring of shared-memory stages
+//     (full / empty mbarriers).  Lane c of the TMA warp owns box c of every item: it waits only for the zone(s) that
+//     PRODUCE its 64 columns (plus this CTA's own cluster) and issues its box the moment they have published; the MMA
+//     warp consumes boxes in order, so the tensor work of early zones runs under the wait for late ones.
+//   * LATENCY HIDING: two independent batch chains are in flight per CTA, each with its own TMEM accumulator and
+//     in/outbox, so the barrier + exchange latency of one chain runs under the MMAs and gate math of the other.
+//     B <= 64 (WPC = 1): a chain is 32 batch rows (UMMA N = 32) and owns one epilogue warpgroup.  B > 64 (WPC = 2): a
+//     chain is 64 rows (N = 64, same MMA cost), both warpgroups finalise 32 rows each and alternate between the chains.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -27,14 +31,14 @@ namespace nsd {
 namespace rts {
 using namespace nsd::tc;
 
-constexpr int NG = 32;                  // batch rows per group = UMMA N
-constexpr int BOX_BYTES = NG * 128;     // one [32 rows x 64 k] bf16 box, 128B-swizzled
-constexpr int CTRL_THREADS = 128;       // warp 0: TMA + grid barrier, warp 1: MMA issue, warp 2: TMEM alloc, warp 3: idle
-constexpr int WG_THREADS = 128;         // one epilogue warpgroup per in-flight batch group
+constexpr int NG = 32;                  // batch rows per epilogue warpgroup pass (one TMEM column block)
+constexpr int CTRL_THREADS = 128;       // warp 0: zone polls + TMA, warp 1: MMA issue, warp 2: TMEM alloc, warp 3: idle
+constexpr int WG_THREADS = 128;         // epilogue warpgroup
 constexpr int THREADS = CTRL_THREADS + 2 * WG_THREADS;
 constexpr int TMEM_COLS = 512;
-constexpr int A_COL0 = 128;             // TMEM: accumulators at columns [0, 128), stationary weights at [128, 512)
 constexpr int CNT_STRIDE = 32;          // uint32 slots between two step counters (128 B apart)
+constexpr int MAX_STAGES = 24;
+constexpr int RING_BYTES = 96 * 1024;   // upper bound of the operand ring
 constexpr int TRACE_STEPS = 16;
 
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -74,21 +78,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         }
     }
 }
-__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
-    if (ld_acquire_u32(counter) >= target) return;
-    const long long t0 = clock64();
-    unsigned int spins = 0;
-    while (ld_acquire_u32(counter) < target) {
-        if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
-            printf("nsd gru_ts: grid barrier timeout (block %d, have %u want %u)\n", blockIdx.x, ld_acquire_u32(counter), target);
-            __trap();
-        }
-    }
-}
 __device__ __forceinline__ void red_release_add(unsigned int* p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-__device__ __forceinline__ void wg_bar_sync(int gg) { asm volatile("bar.sync %0, %1;" ::"r"(1 + gg), "n"(WG_THREADS) : "memory"); }
+__device__ __forceinline__ void wg_bar_sync(int w) { asm volatile("bar.sync %0, %1;" ::"r"(1 + w), "n"(WG_THREADS) : "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]: A = stationary weights, lane = row, two bf16 of consecutive k per 32-bit column
 __device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -106,13 +99,13 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)
 struct Common {
     int Tp, B, H, D, reverse0;
     int nper;                               // CTAs per direction
-    int G;                                  // batch groups of NG rows
+    int nchain;                             // batch chains of 32 * WPC rows
     int ktot, kper;                         // reduction length (H forward, 3H BPTT) and its share per CTA (multiple of 16)
     int s0, row_off;                        // first step with a recurrent term (0 when an initial state is given, else 1); rows the
                                             // exchanged-state tensor is shifted by (B when its first B rows hold the initial state)
-    int chunked;                            // 1: K shares are whole 64-wide chunks -> single 3-D TMA box per operand
-    int cs, upz, nzone;                         // units per zone (= per cluster) and zones per direction
-    unsigned int* counters;                 // [D][G][nzone] step counters, CNT_STRIDE apart: CS arrivals per step
+    int nstage;                             // operand ring depth (boxes)
+    int cs, upz, nzone;                     // CTAs per cluster, units per zone (= per cluster), zones per direction
+    unsigned int* counters;                 // [D][nchain][nzone] step counters, CNT_STRIDE apart: cs * WPC arrivals per step
     long long* trace;                       // debug (NSD_GRU_TRACE=1)
 };
 // Debug stamps go to shared memory (a global store here would sit in front of the next fence) and are dumped at exit.
@@ -131,8 +124,8 @@ __device__ __forceinline__ void trace_dump(const Common& c, const long long* tsm
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < TRACE_STEPS * 8; i += blockDim.x) c.trace[i] = tsm[i];
 }
-__device__ __forceinline__ unsigned int* zone_counter(const Common& c, int d, int g, int zone) {
-    return c.counters + (size_t)((d * c.G + g) * c.nzone + zone) * CNT_STRIDE;
+__device__ __forceinline__ unsigned int* zone_counter(const Common& c, int d, int chain, int zone) {
+    return c.counters + (size_t)((d * c.nchain + chain) * c.nzone + zone) * CNT_STRIDE;
 }
 
 // Exchange rows are [gate][unit 0..UU-1][batch 0..31]; the batch index is rotated per unit so that both the row-wise
@@ -141,35 +134,41 @@ __device__ __forceinline__ unsigned int* zone_counter(const Common& c, int d, in
 __device__ __forceinline__ int rot_f32(int u) { return ((4 * ((u >> 2) & 1) + 2 * ((u >> 3) & 1) + 2 * ((u >> 1) & 1) + (u & 1)) & 7) * 4; }
 __device__ __forceinline__ int rot_bf16(int u) { return (((u >> 1) & 3) ^ ((u >> 3) & 1)) * 8; }
 
-// Shared memory: [B operand: 2 buffers x nbox_max boxes][inbox: 2 x (CS-1) messages][outbox: same][self: 2 x fp32 rows][barriers]
+// Shared memory: [operand ring: nstage boxes][inbox: NSLOT x (CS-1) messages][outbox: same][self: 2 x fp32 rows][barriers]
+// NSLOT = 2 * WPC message slots: one per (warpgroup, chain the warpgroup works on).
 struct Smem {
-    uint8_t* b; uint8_t* inbox; uint8_t* outbox; float* self;
-    uint64_t* full; uint64_t* tmem_full; uint64_t* inbox_bar;     // [2] each
+    uint8_t* ring; uint8_t* inbox; uint8_t* outbox; float* self;
+    uint64_t* full; uint64_t* empty;                               // [MAX_STAGES] each
+    uint64_t* tmem_full;                                           // [2] one per chain in flight
+    uint64_t* inbox_bar;                                           // [4] one per message slot
     uint32_t* tmem_slot;
     long long* trace;
     float* bsum;                                                   // BPTT: [2 warpgroups][32 values][128 threads] bias-gradient partial sums
 };
-__device__ __forceinline__ Smem carve(uint8_t* raw, int nbox_max, int msgs_bytes, int self_bytes) {
+constexpr int BAR_WORDS = 2 * MAX_STAGES + 2 + 4 + 2;             // uint64 slots in the barrier block
+__device__ __forceinline__ Smem carve(uint8_t* raw, int ring_bytes, int nslot, int msgs_bytes, int self_bytes) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     Smem s;
-    s.b = base;
-    s.inbox = base + (size_t)2 * nbox_max * BOX_BYTES;
-    s.outbox = s.inbox + 2 * msgs_bytes;
-    s.self = reinterpret_cast<float*>(s.outbox + 2 * msgs_bytes);
+    s.ring = base;
+    s.inbox = base + ring_bytes;
+    s.outbox = s.inbox + nslot * msgs_bytes;
+    s.self = reinterpret_cast<float*>(s.outbox + nslot * msgs_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.self) + 2 * self_bytes);
-    s.full = bars; s.tmem_full = bars + 2; s.inbox_bar = bars + 4;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    s.trace = reinterpret_cast<long long*>(bars + 8);
+    s.full = bars; s.empty = bars + MAX_STAGES; s.tmem_full = bars + 2 * MAX_STAGES; s.inbox_bar = bars + 2 * MAX_STAGES + 2;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+    s.trace = reinterpret_cast<long long*>(bars + BAR_WORDS);
     s.bsum = reinterpret_cast<float*>(s.trace + (TRACE_STEPS + 1) * 8);
     return s;
 }
-static size_t smem_bytes(int nbox_max, int msgs_bytes, int self_bytes, size_t extra = 0) {
-    return extra + (size_t)2 * nbox_max * BOX_BYTES + 4 * (size_t)msgs_bytes + 2 * (size_t)self_bytes + 8 * 8 + (TRACE_STEPS + 1) * 64 + 1024 + 64;
+static size_t smem_bytes(int ring_bytes, int nslot, int msgs_bytes, int self_bytes, size_t extra = 0) {
+    return extra + (size_t)ring_bytes + 2 * (size_t)nslot * msgs_bytes + 2 * (size_t)self_bytes + BAR_WORDS * 8 + (TRACE_STEPS + 1) * 64 + 1024 + 64;
 }
 
-__device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane) {
+__device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane, int nstage) {
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.inbox_bar[i], 1); }
+        for (int i = 0; i < nstage; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) mbar_init(&sm.tmem_full[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&sm.inbox_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -213,92 +212,108 @@ __device__ __forceinline__ void load_a_row(uint32_t taddr_row, const __nv_bfloat
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// Control warps of both kernels.  Item (s, g): step s >= 1 of batch group g consumes the rows the direction produced
-// in step s-1 of that group.  Groups run in pairs (2p, 2p+1); group parity selects the buffers.  No "buffer free"
-// barriers are needed: passing the grid barrier of (s, g) implies that this CTA published (s-1, g), i.e. that its
-// MMAs and its epilogue for the previous use of the same buffers are finished.
-template <int NT>
-__device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, const CUtensorMap* tmB3, int warp, int lane, uint32_t tmem_base,
-                                              const Common& c, int d, int my_zone, int k_lo, int k_hi, int nslab, int nbox, int nbox_max,
+// Control warps of both kernels.  Item (s, ch): step s >= s0 of the chain `ch` of the current chain pair consumes the rows
+// the direction produced in step s-1 of that chain, as nbox boxes of 64 columns.
+//   warp 0, lane c < nbox: box c of every item.  It waits for (a) its ring stage to be free, (b) the zone(s) producing its
+//     columns and (c) this CTA's own cluster to have published step s-1 of the chain -- (c) means my MMAs and epilogue of the
+//     previous step of this chain are finished and my peers have drained their inboxes, so the chain's TMEM accumulator and
+//     message buffers are free -- and then issues the box.
+//   warp 1: waits for each box in order and issues its MMAs; a tcgen05.commit per box frees the stage, one per item wakes the
+//     chain's epilogue.
+template <int NT, int WPC>
+__device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, int warp, int lane, uint32_t tmem_base,
+                                              const Common& c, int d, int my_zone, int k_lo, int k_hi, int nslab, int nbox,
                                               int b_col0, bool bptt) {
+    constexpr int NROW = NG * WPC;
+    constexpr int BOXB = NROW * 128;
+    constexpr uint32_t A_COL0 = 2 * NT * NROW;
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int kc = c.kper / 2;
+    const int nboxe = nbox > 0 ? nbox : 1;          // a CTA without a K share still paces its epilogue with one empty "box"
+    const int npair = (c.nchain + 1) / 2;
     if (warp == 0) {
-        // Lane i < nbox fetches box i of this CTA's K share: it waits for the zone(s) that produce those columns (a 64-wide
-        // box touches at most two).  Lane 31 waits for this CTA's own cluster: once it has published (s-1, g), my MMAs and
-        // epilogue of (s-1, g) are finished and my peers have drained their inboxes, so every buffer of parity gg is free.
-        int z0 = my_zone, z1 = my_zone;
-        if (lane < nbox) {
-            const int c0 = k_lo + lane * BK, c1 = min(c0 + BK, k_hi) - 1;
-            z0 = (c0 % c.H) / c.upz; z1 = (c1 % c.H) / c.upz;
-        }
-        const bool poller = lane < nbox || lane == 31;
-        for (int g0 = 0; g0 < c.G; g0 += 2) {
-            for (int s = c.s0; s < c.Tp; ++s) {
-                int t_src;
-                if (!bptt) { const int t = rev ? (c.Tp - 1 - s) : s; t_src = rev ? t + 1 : t - 1; }
-                else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
-                for (int gg = 0; gg < 2 && g0 + gg < c.G; ++gg) {
-                    const int g = g0 + gg;
-                    const unsigned int want = (unsigned int)(s * c.cs);
-                    if (poller) {
-                        grid_wait(zone_counter(c, d, g, z0), want);
-                        if (z1 != z0) grid_wait(zone_counter(c, d, g, z1), want);
-                    }
-                    __syncwarp();
-                    if (lane == 0 && nbox > 0) mbar_expect_tx(&sm.full[gg], (uint32_t)(nbox * BOX_BYTES));
-                    __syncwarp();
-                    if (lane == 0 && g == 0) stamp(c, sm.trace, s, 0);
-                    if (c.chunked) {
-                        // K share aligned to 64-wide chunks: the whole operand (nbox swizzled tiles) in one TMA instruction
-                        if (lane == 0) {
-                            asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes (acquired above) -> TMA reads
-                            tma_load_3d(tmB3, &sm.full[gg], sm.b + (size_t)(gg * nbox_max) * BOX_BYTES, 0, t_src * c.B + g * NG + c.row_off, (b_col0 + k_lo) / BK);
+        if (lane < nboxe) {
+            int z0 = my_zone, z1 = my_zone;
+            if (nbox > 0) {
+                const int c0 = k_lo + lane * BK, c1 = min(c0 + BK, k_hi) - 1;
+                z0 = (c0 % c.H) / c.upz; z1 = (c1 % c.H) / c.upz;
+            }
+            uint32_t seq = (uint32_t)lane;
+            for (int pr = 0; pr < npair; ++pr) {
+                for (int s = c.s0; s < c.Tp; ++s) {
+                    int t_src;
+                    if (!bptt) { const int t = rev ? (c.Tp - 1 - s) : s; t_src = rev ? t + 1 : t - 1; }
+                    else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
+                    for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch, seq += (uint32_t)nboxe) {
+                        const int chain = 2 * pr + ch;
+                        const uint32_t stage = seq % (uint32_t)c.nstage, use = seq / (uint32_t)c.nstage;
+                        mbar_wait(&sm.empty[stage], (use & 1u) ^ 1u);
+                        const unsigned int want = (unsigned int)(s * c.cs * WPC);
+                        const unsigned int* p0 = zone_counter(c, d, chain, z0);
+                        const unsigned int* p1 = zone_counter(c, d, chain, z1);
+                        const unsigned int* pm = zone_counter(c, d, chain, my_zone);
+                        const long long t0 = clock64();
+                        unsigned int spins = 0;
+                        for (;;) {
+                            bool ok = ld_acquire_u32(p0) >= want;
+                            if (p1 != p0) ok = (ld_acquire_u32(p1) >= want) && ok;
+                            if (pm != p0 && pm != p1) ok = (ld_acquire_u32(pm) >= want) && ok;
+                            if (ok) break;
+                            if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
+                                printf("nsd gru_ts: zone barrier timeout (block %d lane %d step %d, want %u)\n", blockIdx.x, lane, s, want);
+                                __trap();
+                            }
                         }
-                    } else if (lane < nbox) {
-                        asm volatile("fence.proxy.async.global;" ::: "memory");
-                        tma_load_2d(tmB, &sm.full[gg], sm.b + (size_t)(gg * nbox_max + lane) * BOX_BYTES, b_col0 + k_lo + lane * BK, t_src * c.B + g * NG + c.row_off);
-                    } else if (lane == 0) {
-                        mbar_arrive(&sm.full[gg]);
+                        if (lane == 0 && chain == 0) stamp(c, sm.trace, s, 0);
+                        if (nbox > 0) {
+                            asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy writes (acquired above) -> TMA reads
+                            mbar_expect_tx(&sm.full[stage], (uint32_t)BOXB);
+                            tma_load_2d(tmB, &sm.full[stage], sm.ring + (size_t)stage * BOXB, b_col0 + k_lo + lane * BK,
+                                        t_src * c.B + chain * NROW + c.row_off);
+                        } else {
+                            mbar_arrive(&sm.full[stage]);
+                        }
+                        if (lane == 0 && chain == 0) stamp(c, sm.trace, s, 1);
                     }
-                    if (lane == 0 && g == 0) stamp(c, sm.trace, s, 1);
                 }
             }
         }
     } else if (warp == 1) {
         // The whole warp walks the items; one elected lane issues the MMAs (the compiler then keeps the operands in
         // uniform registers instead of emitting a per-instruction R2UR waterfall, which made the issue rate the bound).
-        constexpr uint32_t idesc = make_idesc_bf16(128, NG);
-        uint32_t n[2] = {0u, 0u};
-        for (int g0 = 0; g0 < c.G; g0 += 2) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NROW);
+        uint32_t seq = 0;
+        for (int pr = 0; pr < npair; ++pr) {
             for (int s = c.s0; s < c.Tp; ++s) {
-                for (int gg = 0; gg < 2 && g0 + gg < c.G; ++gg) {
-                    mbar_wait(&sm.full[gg], n[gg] & 1);
-                    ++n[gg];
-                    if (lane == 0 && g0 + gg == 0) stamp(c, sm.trace, s, 2);
-                    tcgen05_fence_after();
-                    if (elect_one()) {
-                        if (nslab > 0) {
+                for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch) {
+                    for (int bx = 0; bx < nboxe; ++bx, ++seq) {
+                        const uint32_t stage = seq % (uint32_t)c.nstage, use = seq / (uint32_t)c.nstage;
+                        mbar_wait(&sm.full[stage], use & 1u);
+                        if (lane == 0 && 2 * pr + ch == 0 && bx == 0) stamp(c, sm.trace, s, 2);
+                        tcgen05_fence_after();
+                        if (elect_one()) {
+                            if (nslab > 0) {
+                                const int ns = min(4, nslab - 4 * bx);                  // one box = 4 K slabs
+                                const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.ring + (size_t)stage * BOXB));
 #pragma unroll
-                            for (int t = 0; t < NT; ++t) {
-                                const uint32_t dcol = tmem_base + (uint32_t)((gg * NT + t) * NG);
-                                uint32_t acol = tmem_base + (uint32_t)(A_COL0 + t * kc);
-                                uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.b + (size_t)(gg * nbox_max) * BOX_BYTES));
-                                for (int sl = 0; sl < nslab; sl += 4, acol += 32u, bdesc += (uint64_t)(BOX_BYTES >> 4)) {   // one box = 4 slabs
-                                    const int ns = nslab - sl;
-                                    umma_ts_bf16(dcol, acol, bdesc, idesc, sl != 0);
+                                for (int t = 0; t < NT; ++t) {
+                                    const uint32_t dcol = tmem_base + (uint32_t)((ch * NT + t) * NROW);
+                                    const uint32_t acol = tmem_base + A_COL0 + (uint32_t)(t * kc + bx * 32);
+                                    umma_ts_bf16(dcol, acol, bdesc, idesc, bx != 0);
                                     if (ns > 1) umma_ts_bf16(dcol, acol + 8u, bdesc + 2u, idesc, 1u);
                                     if (ns > 2) umma_ts_bf16(dcol, acol + 16u, bdesc + 4u, idesc, 1u);
                                     if (ns > 3) umma_ts_bf16(dcol, acol + 24u, bdesc + 6u, idesc, 1u);
                                 }
+                                umma_commit(&sm.empty[stage]);
+                                if (bx == nboxe - 1) umma_commit(&sm.tmem_full[ch]);
+                            } else {
+                                mbar_arrive(&sm.empty[stage]);
+                                if (bx == nboxe - 1) mbar_arrive(&sm.tmem_full[ch]);
                             }
-                            umma_commit(&sm.tmem_full[gg]);
-                        } else {
-                            mbar_arrive(&sm.tmem_full[gg]);
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    if (lane == 0 && g0 + gg == 0) stamp(c, sm.trace, s, 3);
+                    if (lane == 0 && 2 * pr + ch == 0) stamp(c, sm.trace, s, 3);
                 }
             }
         }
@@ -318,7 +333,7 @@ __device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const float (&v)[4]) 
     *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
 }
 
-// Phase A of the exchange: this thread's TMEM lane of accumulator tile `dcol` is gate row (gate, cluster unit ul) with
+// Phase A of the exchange: this thread's TMEM lane of accumulator tile `taddr` is gate row (gate, cluster unit ul) with
 // 32 batch columns.  The CTA that finalises unit ul is rank ul / UU: keep the row (fp32) if that is me, else stage it as
 // bf16 in the outbox slot of that peer (slot = (peer - me - 1) mod CS).
 template <int CS, int NGATE, int UU>
@@ -392,10 +407,12 @@ struct FwdParams {
     __nv_bfloat16* hdrop; uint32_t drop_thresh; float inv_keep; uint64_t seed;   // fused inter-layer dropout output (or null)
 };
 
+template <int WPC>
 __global__ void __launch_bounds__(THREADS, 1)
-gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmH3, const FwdParams p) {
-    constexpr int CS = 4, NT = 2, NGATE = 3, U = 16;
+gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
+    constexpr int CS = 4, NT = 2, NGATE = 3, U = 16, NROW = NG * WPC, NSLOT = 2 * WPC;
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
+    constexpr uint32_t A_COL0 = 2 * NT * NROW;
     extern __shared__ uint8_t smem_raw[];
     const Common& c = p.c;
     const int H = c.H, B = c.B;
@@ -406,118 +423,135 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     const int uc0 = my_zone * (CS * U);                                  // first unit of the cluster
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
-    const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK, nbox_max = (c.kper + BK - 1) / BK;
+    const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK;
     const int kc = c.kper / 2;
-    const Smem sm = carve(smem_raw, nbox_max, MSGS, SELF);
+    const Smem sm = carve(smem_raw, c.nstage * NROW * 128, NSLOT, MSGS, SELF);
     if (c.trace != nullptr)
         for (int i = threadIdx.x; i < (TRACE_STEPS + 1) * 8; i += blockDim.x) sm.trace[i] = 0;
-    const uint32_t tmem_base = setup(sm, warp, lane);
+    const uint32_t tmem_base = setup(sm, warp, lane, c.nstage);
 
     if (warp >= 4) {
         // stationary weights: tile t = units uc0 + 32t .. +32, lanes [r | z | n | unused] x 32 units, my quarter of K
         const int e = warp - 4, w4 = e & 3, t = e >> 2;
         const int unit = uc0 + 32 * t + lane;
         const __nv_bfloat16* row = (w4 < 3 && unit < H) ? p.w + (size_t)(d * 3 * H + w4 * H + unit) * H : nullptr;
-        load_a_row(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(A_COL0 + t * kc), row, k_lo, k_hi, kc, 0, 1);
+        load_a_row(tmem_base + ((uint32_t)(w4 * 32) << 16) + A_COL0 + (uint32_t)(t * kc), row, k_lo, k_hi, kc, 0, 1);
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT>(sm, &tmH, &tmH3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * H, false);
+        control_warps<NT, WPC>(sm, &tmH, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * H, false);
     } else {
-        // ------------------------------------------------------------ epilogue warpgroup gg: batch groups of parity gg
-        const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
+        // ------------------------------------------------------------ epilogue warpgroup w
+        // WPC == 1: it owns chain w of every chain pair (32 rows).  WPC == 2: it finalises rows [32w, 32w+32) of BOTH chains.
+        const int e = warp - 4, w4 = e & 3, w = e >> 2, te = w4 * 32 + lane;
         const int bl = te >> 2, uo4 = te & 3;
         const int ub = uc0 + me * U + 4 * uo4;             // first of this thread's 4 units
-        uint8_t* inbox = sm.inbox + gg * MSGS;
-        uint8_t* outbox = sm.outbox + gg * MSGS;
-        float* self = sm.self + gg * (SELF / 4);
+        float* self = sm.self + w * (SELF / 4);
         float bh[3][4];
 #pragma unroll
         for (int g = 0; g < 3; ++g) ld4g(p.b_hh + d * 3 * H + g * H + ub, bh[g]);
-        uint32_t it = 0;
-        for (int g0 = 0; g0 + gg < c.G; g0 += 2) {
-            const int grp = g0 + gg;
-            const int b = grp * NG + bl;
-            const bool row_ok = b < B;
-            float k_h[4] = {0.f, 0.f, 0.f, 0.f};          // h_{t-1} of this thread's (row, 4 units), fp32, in registers
-            if (p.h0 != nullptr && row_ok) ld4g(p.h0 + (size_t)b * p.ldh + d * H + ub, k_h);
+        uint32_t it[WPC];
+#pragma unroll
+        for (int k = 0; k < WPC; ++k) it[k] = 0;
+        const int npair = (c.nchain + 1) / 2;
+        for (int pr = 0; pr < npair; ++pr) {
+            float k_h[WPC][4];                             // h_{t-1} of this thread's (row, 4 units) per chain, fp32, in registers
+#pragma unroll
+            for (int k = 0; k < WPC; ++k) {
+                const int ch = WPC == 1 ? w : k;
+                const int b = (2 * pr + ch) * NROW + (WPC == 1 ? 0 : w * NG) + bl;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) k_h[k][i] = 0.f;
+                if (p.h0 != nullptr && 2 * pr + ch < c.nchain && b < B) ld4g(p.h0 + (size_t)b * p.ldh + d * H + ub, k_h[k]);
+            }
             for (int s = 0; s < c.Tp; ++s) {
                 const int t = rev ? (c.Tp - 1 - s) : s;
-                const size_t m = (size_t)t * B + b;
-                float gi[3][4];
-                if (row_ok) {
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) {
-                        ld4g(p.gi + m * p.ldgi + d * 3 * H + g * H + ub, gi[g]);
-                        if (g < 2) {
+                for (int k = 0; k < WPC; ++k) {
+                    const int ch = WPC == 1 ? w : k;
+                    const int chain = 2 * pr + ch;
+                    if (chain >= c.nchain) continue;
+                    const int slot = WPC == 1 ? w : 2 * w + k;
+                    uint8_t* inbox = sm.inbox + slot * MSGS;
+                    uint8_t* outbox = sm.outbox + slot * MSGS;
+                    const int b = chain * NROW + (WPC == 1 ? 0 : w * NG) + bl;
+                    const bool row_ok = b < B;
+                    const size_t m = (size_t)t * B + b;
+                    float gi[3][4];
+                    if (row_ok) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) gi[g][i] += bh[g][i];
+                        for (int g = 0; g < 3; ++g) {
+                            ld4g(p.gi + m * p.ldgi + d * 3 * H + g * H + ub, gi[g]);
+                            if (g < 2) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) gi[g][i] += bh[g][i];
+                            }
                         }
                     }
-                }
-                float acc[3][4];
+                    float acc[3][4];
 #pragma unroll
-                for (int g = 0; g < 3; ++g)
+                    for (int g = 0; g < 3; ++g)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
-                if (s >= c.s0) {
-                    if (te == 0) mbar_expect_tx(&sm.inbox_bar[gg], (uint32_t)MSGS);
-                    mbar_wait(&sm.tmem_full[gg], it & 1);
-                    tcgen05_fence_after();
-                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 4);
-                    if (w4 < 3) {
+                        for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
+                    if (s >= c.s0) {
+                        if (te == 0) mbar_expect_tx(&sm.inbox_bar[slot], (uint32_t)MSGS);
+                        mbar_wait(&sm.tmem_full[ch], it[k] & 1);
+                        tcgen05_fence_after();
+                        if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 4);
+                        if (w4 < 3) {
 #pragma unroll
-                        for (int t2 = 0; t2 < NT; ++t2)
-                            stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)((gg * NT + t2) * NG), nslab > 0, w4,
-                                                 32 * t2 + lane, me, self, outbox);
+                            for (int t2 = 0; t2 < NT; ++t2)
+                                stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)((ch * NT + t2) * NROW + (WPC == 1 ? 0 : w * NG)),
+                                                        nslab > 0, w4, 32 * t2 + lane, me, self, outbox);
+                        }
+                        tcgen05_fence_before();
+                        fence_proxy_async_smem();
+                        wg_bar_sync(w);
+                        if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[slot], me, te);
+                        mbar_wait_cluster(&sm.inbox_bar[slot], it[k] & 1);
+                        if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 5);
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) gather<CS, NGATE, U>(self, inbox, g, 4 * uo4, bl, acc[g]);
+                        ++it[k];
                     }
-                    tcgen05_fence_before();
-                    fence_proxy_async_smem();
-                    wg_bar_sync(gg);
-                    if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[gg], me, te);
-                    mbar_wait_cluster(&sm.inbox_bar[gg], it & 1);
-                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 5);
+                    float rr[4], zz[4], nn[4], gn[4];
+                    if (row_ok) {
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) gather<CS, NGATE, U>(self, inbox, g, 4 * uo4, bl, acc[g]);
-                    ++it;
-                }
-                float rr[4], zz[4], nn[4], gn[4];
-                if (row_ok) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        rr[i] = fast_sigmoid(gi[0][i] + acc[0][i]);
-                        zz[i] = fast_sigmoid(gi[1][i] + acc[1][i]);
-                        gn[i] = acc[2][i] + bh[2][i];
-                        nn[i] = fast_tanh(fmaf(rr[i], gn[i], gi[2][i]));
-                        k_h[i] = fmaf(zz[i], k_h[i] - nn[i], nn[i]);        // (1-z)*n + z*h_prev
+                        for (int i = 0; i < 4; ++i) {
+                            rr[i] = fast_sigmoid(gi[0][i] + acc[0][i]);
+                            zz[i] = fast_sigmoid(gi[1][i] + acc[1][i]);
+                            gn[i] = acc[2][i] + bh[2][i];
+                            nn[i] = fast_tanh(fmaf(rr[i], gn[i], gi[2][i]));
+                            k_h[k][i] = fmaf(zz[i], k_h[k][i] - nn[i], nn[i]);        // (1-z)*n + z*h_prev
+                        }
+                        // the bf16 state is what the other CTAs wait for: store it first, publish, then write the rest
+                        st4_bf16(p.hseq_bf + (m + c.row_off) * p.ldh + d * H + ub, k_h[k]);
                     }
-                    // the bf16 state is what the other CTAs wait for: store it first, publish, then write the rest
-                    st4_bf16(p.hseq_bf + (m + c.row_off) * p.ldh + d * H + ub, k_h);
-                }
-                if (te == 0 && grp == 0) stamp(c, sm.trace, s, 6);
-                wg_bar_sync(gg);                             // (the consumer fences generic->async proxy after its acquire)
-                if (te == 0) {
-                    red_release_add(zone_counter(c, d, grp, my_zone));
-                    if (grp == 0) stamp(c, sm.trace, s, 7);
-                }
-                if (row_ok) {                                // off the critical path: nobody else reads these during the launch
-                    st4(p.hseq + m * p.ldh + d * H + ub, k_h);
-                    if (p.r) {
-                        const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
-                        st4(p.r + o, rr); st4(p.z + o, zz); st4(p.n + o, nn); st4(p.hn + o, gn);
+                    if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
+                    wg_bar_sync(w);                              // (the consumer fences generic->async proxy after its acquire)
+                    if (te == 0) {
+                        red_release_add(zone_counter(c, d, chain, my_zone));
+                        if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
                     }
-                    if (p.hdrop) {                           // same mask and rounding as nsd_dropout on the bf16 [Tp*B, ldh] tensor
-                        const size_t e = m * p.ldh + d * H + ub;
-                        const uint4 bits = dropout_bits(e >> 2, p.seed);
-                        const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
-                        float o[4];
+                    if (row_ok) {                                // off the critical path: nobody else reads these during the launch
+                        st4(p.hseq + m * p.ldh + d * H + ub, k_h[k]);
+                        if (p.r) {
+                            const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
+                            st4(p.r + o, rr); st4(p.z + o, zz); st4(p.n + o, nn); st4(p.hn + o, gn);
+                        }
+                        if (p.hdrop) {                           // same mask and rounding as nsd_dropout on the bf16 [Tp*B, ldh] tensor
+                            const size_t el = m * p.ldh + d * H + ub;
+                            const uint4 bits = dropout_bits(el >> 2, p.seed);
+                            const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
+                            float o[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            o[i] = bw[i] >= p.drop_thresh ? __bfloat162float(__float2bfloat16_rn(k_h[i])) * p.inv_keep : 0.f;
-                        st4_bf16(p.hdrop + e, o);
+                            for (int i = 0; i < 4; ++i)
+                                o[i] = bw[i] >= p.drop_thresh ? __bfloat162float(__float2bfloat16_rn(k_h[k][i])) * p.inv_keep : 0.f;
+                            st4_bf16(p.hdrop + el, o);
+                        }
                     }
                 }
             }
@@ -538,10 +572,12 @@ struct BwdParams {
     float* db_ih; float* db_hh;                          // [D*3H] column sums of dgi / dgh over all rows (or null), pre-zeroed
 };
 
+template <int WPC>
 __global__ void __launch_bounds__(THREADS, 1)
-gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG3, const BwdParams p) {
-    constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16;       // NP passes of (batch row, 4 units) per thread
+gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
+    constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16, NROW = NG * WPC, NSLOT = 2 * WPC;       // NP passes of (batch row, 4 units) per thread
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
+    constexpr uint32_t A_COL0 = 2 * NT * NROW;
     extern __shared__ uint8_t smem_raw[];
     const Common& c = p.c;
     const int H = c.H, B = c.B;
@@ -552,12 +588,12 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int uc0 = my_zone * (CS * U);
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
-    const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK, nbox_max = (c.kper + BK - 1) / BK;
+    const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK;
     const int kc = c.kper / 2;
-    const Smem sm = carve(smem_raw, nbox_max, MSGS, SELF);
+    const Smem sm = carve(smem_raw, c.nstage * NROW * 128, NSLOT, MSGS, SELF);
     if (c.trace != nullptr)
         for (int i = threadIdx.x; i < (TRACE_STEPS + 1) * 8; i += blockDim.x) sm.trace[i] = 0;
-    const uint32_t tmem_base = setup(sm, warp, lane);
+    const uint32_t tmem_base = setup(sm, warp, lane, c.nstage);
 
     if (warp >= 4) {
         // stationary weights: lane = unit uc0 + lane of W_hh^T [H, 3H], my quarter of the gate index; the two warpgroups
@@ -565,118 +601,130 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const int e = warp - 4, w4 = e & 3, half = e >> 2;
         const int unit = uc0 + w4 * 32 + lane;
         const __nv_bfloat16* row = unit < H ? p.wT + (size_t)(d * H + unit) * (3 * H) : nullptr;
-        load_a_row(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)A_COL0, row, k_lo, k_hi, kc, half, 2);
+        load_a_row(tmem_base + ((uint32_t)(w4 * 32) << 16) + A_COL0, row, k_lo, k_hi, kc, half, 2);
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT>(sm, &tmG, &tmG3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, nbox_max, d * 3 * H, true);
+        control_warps<NT, WPC>(sm, &tmG, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * 3 * H, true);
     } else {
-        const int e = warp - 4, w4 = e & 3, gg = e >> 2, te = w4 * 32 + lane;
+        const int e = warp - 4, w4 = e & 3, w = e >> 2, te = w4 * 32 + lane;
         const int bl = te >> 2, uo4 = te & 3;
         const int ub0 = uc0 + me * U + 4 * uo4;             // pass q handles units ub0 + 16q .. +3
-        uint8_t* inbox = sm.inbox + gg * MSGS;
-        uint8_t* outbox = sm.outbox + gg * MSGS;
-        float* self = sm.self + gg * (SELF / 4);
-        float* bsum = sm.bsum + (size_t)gg * 16 * NP * WG_THREADS + te;
+        float* self = sm.self + w * (SELF / 4);
+        float* bsum = sm.bsum + (size_t)w * 16 * NP * WG_THREADS + te;
         if (p.db_ih)
             for (int v = 0; v < 16 * NP; ++v) bsum[v * WG_THREADS] = 0.f;
-        uint32_t it = 0;
-        for (int g0 = 0; g0 + gg < c.G; g0 += 2) {
-            const int grp = g0 + gg;
-            const int b = grp * NG + bl;
-            float cr[NP][4];                                 // dh_t * z_t carried to the next step, in registers
+        uint32_t it[WPC];
 #pragma unroll
-            for (int q = 0; q < NP; ++q)
+        for (int k = 0; k < WPC; ++k) it[k] = 0;
+        const int npair = (c.nchain + 1) / 2;
+        for (int pr = 0; pr < npair; ++pr) {
+            float cr[WPC][NP][4];                            // dh_t * z_t carried to the next step, in registers
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cr[q][i] = 0.f;
+            for (int k = 0; k < WPC; ++k)
+#pragma unroll
+                for (int q = 0; q < NP; ++q)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cr[k][q][i] = 0.f;
             for (int s = 0; s < c.Tp; ++s) {
                 const int t = rev ? s : (c.Tp - 1 - s);              // BPTT visits time in the opposite order of the forward pass
                 const int tprev = rev ? t + 1 : t - 1;               // forward-time predecessor (source of h_{t-1})
                 const bool has_prev = rev ? (t + 1 < c.Tp) : (t > 0);
-                const size_t m = (size_t)t * B + b;
-                float dh[NP][4], rr[NP][4], zz[NP][4], nn[NP][4], gn[NP][4], hp[NP][4];
 #pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    const int ub = ub0 + 16 * q;
+                for (int k = 0; k < WPC; ++k) {
+                    const int ch = WPC == 1 ? w : k;
+                    const int chain = 2 * pr + ch;
+                    if (chain >= c.nchain) continue;
+                    const int slot = WPC == 1 ? w : 2 * w + k;
+                    uint8_t* inbox = sm.inbox + slot * MSGS;
+                    uint8_t* outbox = sm.outbox + slot * MSGS;
+                    const int b = chain * NROW + (WPC == 1 ? 0 : w * NG) + bl;
+                    const size_t m = (size_t)t * B + b;
+                    float dh[NP][4], rr[NP][4], zz[NP][4], nn[NP][4], gn[NP][4], hp[NP][4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) hp[q][i] = 0.f;
-                    if (b < B && ub < H) {                   // H % 64 == 0: a pass's 16 units are all inside or all outside
-                        const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
-                        ld4g(p.dhseq + m * p.lddh + d * H + ub, dh[q]);
-                        if (p.drop_thresh != 0u) {           // gradient through this layer's output dropout (mask of nsd_dropout)
-                            const uint4 bits = dropout_bits((m * p.lddh + d * H + ub) >> 2, p.seed);
-                            const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
+                    for (int q = 0; q < NP; ++q) {
+                        const int ub = ub0 + 16 * q;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dh[q][i] = bw[i] >= p.drop_thresh ? dh[q][i] * p.inv_keep : 0.f;
+                        for (int i = 0; i < 4; ++i) hp[q][i] = 0.f;
+                        if (b < B && ub < H) {                   // H % 64 == 0: a pass's 16 units are all inside or all outside
+                            const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
+                            ld4g(p.dhseq + m * p.lddh + d * H + ub, dh[q]);
+                            if (p.drop_thresh != 0u) {           // gradient through this layer's output dropout (mask of nsd_dropout)
+                                const uint4 bits = dropout_bits((m * p.lddh + d * H + ub) >> 2, p.seed);
+                                const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) dh[q][i] = bw[i] >= p.drop_thresh ? dh[q][i] * p.inv_keep : 0.f;
+                            }
+                            ld4g(p.r + o, rr[q]); ld4g(p.z + o, zz[q]); ld4g(p.n + o, nn[q]); ld4g(p.hn + o, gn[q]);
+                            if (has_prev) ld4g(p.hseq + ((size_t)tprev * B + b) * p.ldh + d * H + ub, hp[q]);
                         }
-                        ld4g(p.r + o, rr[q]); ld4g(p.z + o, zz[q]); ld4g(p.n + o, nn[q]); ld4g(p.hn + o, gn[q]);
-                        if (has_prev) ld4g(p.hseq + ((size_t)tprev * B + b) * p.ldh + d * H + ub, hp[q]);
                     }
-                }
-                float acc[NP][4];
+                    float acc[NP][4];
 #pragma unroll
-                for (int q = 0; q < NP; ++q)
+                    for (int q = 0; q < NP; ++q)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
-                if (s > 0) {
-                    if (te == 0) mbar_expect_tx(&sm.inbox_bar[gg], (uint32_t)MSGS);
-                    mbar_wait(&sm.tmem_full[gg], it & 1);
-                    tcgen05_fence_after();
-                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 4);
-                    stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(gg * NT * NG), nslab > 0, 0, w4 * 32 + lane, me, self, outbox);
-                    tcgen05_fence_before();
-                    fence_proxy_async_smem();
-                    wg_bar_sync(gg);
-                    if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[gg], me, te);
-                    mbar_wait_cluster(&sm.inbox_bar[gg], it & 1);
-                    if (te == 0 && grp == 0) stamp(c, sm.trace, s, 5);
+                        for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
+                    if (s > 0) {
+                        if (te == 0) mbar_expect_tx(&sm.inbox_bar[slot], (uint32_t)MSGS);
+                        mbar_wait(&sm.tmem_full[ch], it[k] & 1);
+                        tcgen05_fence_after();
+                        if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 4);
+                        stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(ch * NT * NROW + (WPC == 1 ? 0 : w * NG)), nslab > 0, 0,
+                                                w4 * 32 + lane, me, self, outbox);
+                        tcgen05_fence_before();
+                        fence_proxy_async_smem();
+                        wg_bar_sync(w);
+                        if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &sm.inbox_bar[slot], me, te);
+                        mbar_wait_cluster(&sm.inbox_bar[slot], it[k] & 1);
+                        if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 5);
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) gather<CS, NGATE, U>(self, inbox, 0, 16 * q + 4 * uo4, bl, acc[q]);
-                    ++it;
-                }
-                float drt[NP][4], dzt[NP][4], dnt[NP][4];
-#pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    const int ub = ub0 + 16 * q;
-                    if (b < B && ub < H) {
-                        float dgn[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float dht = dh[q][i] + cr[q][i] + acc[q][i];
-                            const float dn = dht * (1.0f - zz[q][i]);
-                            const float dz = dht * (hp[q][i] - nn[q][i]);
-                            dnt[q][i] = dn * (1.0f - nn[q][i] * nn[q][i]);
-                            dzt[q][i] = dz * zz[q][i] * (1.0f - zz[q][i]);
-                            drt[q][i] = dnt[q][i] * gn[q][i] * rr[q][i] * (1.0f - rr[q][i]);
-                            dgn[i] = dnt[q][i] * rr[q][i];
-                            cr[q][i] = dht * zz[q][i];
-                        }
-                        __nv_bfloat16* gh_row = p.dgh + m * p.ldg + d * 3 * H + ub;
-                        st4_bf16(gh_row, drt[q]); st4_bf16(gh_row + H, dzt[q]); st4_bf16(gh_row + 2 * H, dgn);   // what the other CTAs wait for
+                        for (int q = 0; q < NP; ++q) gather<CS, NGATE, U>(self, inbox, 0, 16 * q + 4 * uo4, bl, acc[q]);
+                        ++it[k];
                     }
-                }
-                if (te == 0 && grp == 0) stamp(c, sm.trace, s, 6);
-                wg_bar_sync(gg);                             // (the consumer fences generic->async proxy after its acquire)
-                if (te == 0) {
-                    red_release_add(zone_counter(c, d, grp, my_zone));
-                    if (grp == 0) stamp(c, sm.trace, s, 7);
-                }
+                    float drt[NP][4], dzt[NP][4], dnt[NP][4];
 #pragma unroll
-                for (int q = 0; q < NP; ++q) {               // off the critical path
-                    const int ub = ub0 + 16 * q;
-                    if (b < B && ub < H) {
-                        __nv_bfloat16* gi_row = p.dgi + m * p.ldg + d * 3 * H + ub;
-                        st4_bf16(gi_row, drt[q]); st4_bf16(gi_row + H, dzt[q]); st4_bf16(gi_row + 2 * H, dnt[q]);
-                        if (p.db_ih) {                       // bias gradients: fp32 sums over (t, b) of dgi and dgh, this thread's cells
+                    for (int q = 0; q < NP; ++q) {
+                        const int ub = ub0 + 16 * q;
+                        if (b < B && ub < H) {
+                            float dgn[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                bsum[((0 * NP + q) * 4 + i) * WG_THREADS] += drt[q][i];
-                                bsum[((1 * NP + q) * 4 + i) * WG_THREADS] += dzt[q][i];
-                                bsum[((2 * NP + q) * 4 + i) * WG_THREADS] += dnt[q][i];
-                                bsum[((3 * NP + q) * 4 + i) * WG_THREADS] += dnt[q][i] * rr[q][i];
+                                const float dht = dh[q][i] + cr[k][q][i] + acc[q][i];
+                                const float dn = dht * (1.0f - zz[q][i]);
+                                const float dz = dht * (hp[q][i] - nn[q][i]);
+                                dnt[q][i] = dn * (1.0f - nn[q][i] * nn[q][i]);
+                                dzt[q][i] = dz * zz[q][i] * (1.0f - zz[q][i]);
+                                drt[q][i] = dnt[q][i] * gn[q][i] * rr[q][i] * (1.0f - rr[q][i]);
+                                dgn[i] = dnt[q][i] * rr[q][i];
+                                cr[k][q][i] = dht * zz[q][i];
+                            }
+                            __nv_bfloat16* gh_row = p.dgh + m * p.ldg + d * 3 * H + ub;
+                            st4_bf16(gh_row, drt[q]); st4_bf16(gh_row + H, dzt[q]); st4_bf16(gh_row + 2 * H, dgn);   // what the other CTAs wait for
+                        }
+                    }
+                    if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
+                    wg_bar_sync(w);                              // (the consumer fences generic->async proxy after its acquire)
+                    if (te == 0) {
+                        red_release_add(zone_counter(c, d, chain, my_zone));
+                        if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {               // off the critical path
+                        const int ub = ub0 + 16 * q;
+                        if (b < B && ub < H) {
+                            __nv_bfloat16* gi_row = p.dgi + m * p.ldg + d * 3 * H + ub;
+                            st4_bf16(gi_row, drt[q]); st4_bf16(gi_row + H, dzt[q]); st4_bf16(gi_row + 2 * H, dnt[q]);
+                            if (p.db_ih) {                       // bias gradients: fp32 sums over (t, b) of dgi and dgh, this thread's cells
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    bsum[((0 * NP + q) * 4 + i) * WG_THREADS] += drt[q][i];
+                                    bsum[((1 * NP + q) * 4 + i) * WG_THREADS] += dzt[q][i];
+                                    bsum[((2 * NP + q) * 4 + i) * WG_THREADS] += dnt[q][i];
+                                    bsum[((3 * NP + q) * 4 + i) * WG_THREADS] += dnt[q][i] * rr[q][i];
+                                }
                             }
                         }
                     }
@@ -686,9 +734,9 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         if (p.db_ih) {
             // fold the 32 batch rows of this warpgroup; the two warpgroups then add into the zero-initialised outputs
             // (two commutative additions per element: the result does not depend on their order)
-            wg_bar_sync(gg);
+            wg_bar_sync(w);
             const int v = te >> 2, gate4 = v / (4 * NP), q = (v >> 2) % NP, i = v & 3;
-            const float* col = sm.bsum + (size_t)gg * 16 * NP * WG_THREADS + (size_t)v * WG_THREADS + uo4;
+            const float* col = sm.bsum + (size_t)w * 16 * NP * WG_THREADS + (size_t)v * WG_THREADS + uo4;
             float sum = 0.f;
             for (int r = 0; r < NG; ++r) sum += col[4 * r];
             const int unit = uc0 + me * U + 4 * uo4 + 16 * q + i;
@@ -703,7 +751,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 
 // ---------------------------------------------------------------- host side
 template <typename Kern, typename P>
-static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1, const P& p, cudaStream_t s) {
+static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const P& p, cudaStream_t s) {
     NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -719,12 +767,12 @@ static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const C
     int max_clusters = 0;
     NSD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters * cs < grid) { set_error("gru_ts: %d CTAs in clusters of %d cannot be co-resident (max %d clusters)", grid, cs, max_clusters); return NSD_ERR_INVALID; }
-    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, p));
+    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, p));
     count_launch(1);
     return NSD_OK;
 }
 
-// Debug aid: NSD_GRU_TRACE=1 prints block 0's per-step event times of batch group 0 (SM cycles relative to the step's barrier pass).
+// Debug aid: NSD_GRU_TRACE=1 prints block 0's per-step event times of batch chain 0 (SM cycles relative to the step's barrier pass).
 static long long* trace_begin() {
     const char* e = getenv("NSD_GRU_TRACE");
     if (!e || e[0] != '1') return nullptr;
@@ -739,7 +787,7 @@ static void trace_end(const char* who, long long* d, cudaStream_t s, int grid = 
     cudaStreamSynchronize(s);
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d);
-    fprintf(stderr, "[%s trace, group 0, cycles] step: barrier->tma_issued operand_landed mma_committed epi_wake inbox_complete state_stored published | step period\n", who);
+    fprintf(stderr, "[%s trace, chain 0, cycles] step: box0 zones seen->tma_issued first_box_landed mma_committed epi_wake inbox_complete state_stored published | step period\n", who);
     for (int st = 1; st < TRACE_STEPS; ++st) {
         const long long* r = h + st * 8;
         if (r[0] == 0) break;
@@ -757,8 +805,21 @@ static void trace_end(const char* who, long long* d, cudaStream_t s, int grid = 
     }
 }
 
-static int n_groups(int B) { return (B + NG - 1) / NG; }
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+// chains of 32 rows (one warpgroup each) up to B = 64, chains of 64 rows (both warpgroups) beyond
+static int wg_per_chain(int B) {
+    static const int forced = [] { const char* e = getenv("NSD_GRU_WPC"); return e ? atoi(e) : 0; }();      // debug: force 1 or 2
+    if (forced == 1 || forced == 2) return forced;
+    return B > 2 * NG ? 2 : 1;
+}
+static int n_chains(int B, int wpc) { return (B + NG * wpc - 1) / (NG * wpc); }
+static int ring_stages(int nbox, int wpc) {
+    const int box_bytes = NG * wpc * 128;
+    int n = 2 * (nbox > 0 ? nbox : 1);
+    if (n > RING_BYTES / box_bytes) n = RING_BYTES / box_bytes;
+    if (n > MAX_STAGES) n = MAX_STAGES;
+    return n < 2 ? 2 : n;
+}
 
 static int check_shape(const char* who, int Tp, int B, int H, int D, int cs, int u) {
     if (!(Tp > 0 && B > 0 && H > 0 && (D == 1 || D == 2))) { set_error("%s: bad sizes Tp=%d B=%d H=%d D=%d", who, Tp, B, H, D); return NSD_ERR_INVALID; }
@@ -774,7 +835,7 @@ static int check_shape(const char* who, int Tp, int B, int H, int D, int cs, int
 extern "C" {
 
 size_t nsd_gru_tc_workspace(int B, int H, int D) {
-    return 256 + (size_t)D * nsd::rts::n_groups(B) * nsd::cdiv(H, 64) * nsd::rts::CNT_STRIDE * sizeof(unsigned int);
+    return 256 + (size_t)D * nsd::rts::n_chains(B, 1) * nsd::cdiv(H, 64) * nsd::rts::CNT_STRIDE * sizeof(unsigned int);
 }
 
 int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
@@ -791,25 +852,25 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     if (workspace_bytes < nsd_gru_tc_workspace(B, H, D)) { set_error("gru_fwd_bf16: workspace too small"); return NSD_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
     NSD_CUDA(cudaMemsetAsync(workspace, 0, nsd_gru_tc_workspace(B, H, D), s));
+    const int wpc = wg_per_chain(B);
     CUtensorMap tmH;
     const int row_off = h0 ? B : 0;       // with an initial state, hseq_bf16 has Tp*B + B rows: [bf16(h0) | h_0 .. h_{Tp-1}]
-    rc = make_bf16_map(&tmH, hseq_bf16, (long long)Tp * B + row_off, D * H, ldh, NG);
+    rc = make_bf16_map(&tmH, hseq_bf16, (long long)Tp * B + row_off, D * H, ldh, NG * wpc);
     if (rc) return rc;
     FwdParams p;
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
     const int kper = round_up(cdiv(H, CS), UMMA_K);
-    const int chunked = (kper % BK == 0 && H % BK == 0) ? 1 : 0;
-    CUtensorMap tmH3 = tmH;
-    if (chunked) { rc = make_bf16_map_chunked(&tmH3, hseq_bf16, (long long)Tp * B + row_off, D * H, ldh, NG, kper / BK); if (rc) return rc; }
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), H, kper, h0 ? 0 : 1, row_off, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    const int nbox = cdiv(kper, BK), nstage = ring_stages(nbox, wpc);
+    p.c = {Tp, B, H, D, reverse0, nper, n_chains(B, wpc), H, kper, h0 ? 0 : 1, row_off, nstage, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
     p.h0 = h0;
     p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.hdrop = reinterpret_cast<__nv_bfloat16*>(hdrop_bf16); p.drop_thresh = dropout_threshold(p_drop); p.inv_keep = 1.0f / (1.0f - p_drop); p.seed = seed;
-    const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
-    rc = launch_cluster_coop(gru_fwd_ts_kernel, D * nper, CS, smem, tmH, tmH3, p, s);
+    const size_t smem = smem_bytes(nstage * NG * wpc * 128, 2 * wpc, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
+    rc = wpc == 1 ? launch_cluster_coop(gru_fwd_ts_kernel<1>, D * nper, CS, smem, tmH, p, s)
+                  : launch_cluster_coop(gru_fwd_ts_kernel<2>, D * nper, CS, smem, tmH, p, s);
     trace_end("gru_fwd_bf16", tr, s, D * nper);
     return rc;
 }
@@ -829,17 +890,16 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     if (workspace_bytes < nsd_gru_tc_workspace(B, H, D)) { set_error("gru_bwd_bf16: workspace too small"); return NSD_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
     NSD_CUDA(cudaMemsetAsync(workspace, 0, nsd_gru_tc_workspace(B, H, D), s));
+    const int wpc = wg_per_chain(B);
     CUtensorMap tmG;
-    rc = make_bf16_map(&tmG, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG);
+    rc = make_bf16_map(&tmG, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG * wpc);
     if (rc) return rc;
     BwdParams p;
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
     const int kper = round_up(cdiv(3 * H, CS), UMMA_K);
-    const int chunked = (kper % BK == 0) ? 1 : 0;
-    CUtensorMap tmG3 = tmG;
-    if (chunked) { rc = make_bf16_map_chunked(&tmG3, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG, kper / BK); if (rc) return rc; }
-    p.c = {Tp, B, H, D, reverse0, nper, n_groups(B), 3 * H, kper, 1, 0, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    const int nbox = cdiv(kper, BK), nstage = ring_stages(nbox, wpc);
+    p.c = {Tp, B, H, D, reverse0, nper, n_chains(B, wpc), 3 * H, kper, 1, 0, nstage, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
     p.wT = reinterpret_cast<const __nv_bfloat16*>(w_hhT_bf16);
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
@@ -849,8 +909,9 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
         NSD_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)D * 3 * H, s));
         NSD_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)D * 3 * H, s));
     }
-    const size_t smem = smem_bytes(cdiv(p.c.kper, BK), (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
-    rc = launch_cluster_coop(gru_bwd_ts_kernel, D * nper, CS, smem, tmG, tmG3, p, s);
+    const size_t smem = smem_bytes(nstage * NG * wpc * 128, 2 * wpc, (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
+    rc = wpc == 1 ? launch_cluster_coop(gru_bwd_ts_kernel<1>, D * nper, CS, smem, tmG, p, s)
+                  : launch_cluster_coop(gru_bwd_ts_kernel<2>, D * nper, CS, smem, tmG, p, s);
     trace_end("gru_bwd_bf16", tr, s, D * nper);
     return rc;
 }

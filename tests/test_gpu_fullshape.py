@@ -55,7 +55,9 @@ def cu(a, dtype=torch.float32):
 
 # Tolerances of the K3-only check: (max |h - h_ref| over everything [h in (-1,1)], max |gate - ref|, BPTT max err / max |dgi|,
 # dW_hh max err / max |dW_hh|).  Measured on B200 (gpurun_out/parity_fullshape.json -> DESIGN.md section 2) x <= 3.
-K3_TOL = dict(h=2.5e-2, gates=4e-2, dgi=4e-2, dwhh=4e-2)
+# Round-2 measurements (profiles/r02_parity_fullshape.json): h 2.6e-3..3.3e-3, gates 5.3e-3..5.7e-3, dgi 2.8e-3..3.1e-3,
+# dW_hh 1.5e-3..1.7e-3, db 6.7e-4..8.9e-4 -- flat from step 1 to step 117 / 492 (no growth with the step count).
+K3_TOL = dict(h=8e-3, gates=1.5e-2, dgi=8e-3, dwhh=5e-3, db=2.5e-3)
 
 
 @pytest.mark.parametrize("B,Tp,H,D", [(64, 118, 1024, 2), (32, 493, 1024, 2), (64, 118, 1024, 1), (256, 30, 1024, 2)])
@@ -121,7 +123,7 @@ def test_gru_tc_benchmark_shape(B, Tp, H, D):
     record(f"k3_B{B}_Tp{Tp}_H{H}_D{D}", dict(h=err, gates=gate_err, dgi=e_dgi, dwhh=e_dwhh, db=e_db, fwd_by_step=growth,
                                              bwd_by_step=bwd_growth))
     assert err < K3_TOL["h"] and gate_err < K3_TOL["gates"] and e_dgi < K3_TOL["dgi"] and e_dwhh < K3_TOL["dwhh"]
-    assert e_db < 2e-2
+    assert e_db < K3_TOL["db"]
 
 
 def test_gru_tc_fused_dropout_benchmark_shape():
@@ -180,8 +182,12 @@ def port_reference(bidirectional, B, T):
     return out
 
 
-# bf16 whole-model tolerances (stated separately from fp32, north star): measured values x <= 3, see DESIGN.md section 2
-BF16_TOL = dict(logits_abs=6e-2, loss_rel=2e-2, grad_rel_l2=0.1, argmax_agree=0.9)
+# bf16 whole-model tolerances (stated separately from fp32, north star) = about 2x the round-2 measurements at these shapes
+# (profiles/r02_parity_fullshape.json): logits max abs error 4.5e-2..5.9e-2 at |logits| <= 8.2 (0.7 % of
+# the range), loss 1.1e-4..3.0e-4 relative, gradients 1.1e-2..3.4e-2 relative L2 per tensor, greedy argmax agreement
+# 0.9926..0.9954.  torch's own bf16 autocast of the reference module lands in the same place (recorded by
+# test_reference_bf16_autocast_yardstick).
+BF16_TOL = dict(logits_abs=0.12, loss_rel=8e-4, grad_rel_l2=0.08, argmax_agree=0.985)
 
 
 @pytest.mark.parametrize("bidirectional,precision,B,T", [(True, "fp32", 64, 500), (True, "bf16", 64, 500), (False, "bf16", 64, 500),
@@ -250,3 +256,23 @@ def test_model_benchmark_shape_vs_reference_port(bidirectional, precision, B, T)
         assert agree >= BF16_TOL["argmax_agree"]
         for n, (l2, _) in gerr.items():
             assert l2 < BF16_TOL["grad_rel_l2"], (n, l2)
+
+
+def test_reference_bf16_autocast_yardstick():
+    """Not a check of this repo's kernels: what bf16 costs the REFERENCE module itself.  The port (torch operators: cuDNN GRU,
+    cuBLAS) under torch.autocast(bfloat16) on the GPU against its own fp64 CPU run, same weights and batch as the bf16
+    parity test above.  Recorded next to our errors so the stated bf16 tolerance can be judged against it."""
+    from oracle import torch_port as P
+    ref = port_reference(True, 64, 500)
+    port = P.PortGRUDecoder(bidirectional=True, **COMP)
+    port.load_reference_state(ref["sd"])
+    port = port.to(DEV).eval()
+    X, y, X_len, y_len, day = (t.to(DEV) for t in ref["batch"])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred = port(X, day)
+    got = pred.float().detach().cpu().numpy().astype(np.float64)
+    e_log = float(np.abs(got - ref["logits"]).max())
+    agree = float((got.argmax(-1) == ref["logits"].argmax(-1)).mean())
+    print(f"reference module under bf16 autocast (cuDNN): logits max abs err {e_log:.3e}, argmax agreement {agree:.4f}")
+    record("yardstick_reference_bf16_autocast_bi_B64_T500", dict(logits_abs=e_log, argmax_agree=agree))
+    assert e_log < 1.0
