@@ -7,13 +7,14 @@
 // X is read once (plus a (ntaps-1)-row halo per block), ys/z are written once for the backward,
 // patches are written once with 16-byte stores in time-major row order (m = j*B + b).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace nsd {
 
-constexpr int FE_THREADS = 256;
 constexpr int FE_TT = 32;       // z rows computed per block
+constexpr int FE_NTAPS = 20;    // the reference's smoothing kernel size (augmentations.py / model.py:84): unrolled fast path
 constexpr int FE_TTP = 36;      // padded row length of the transposed ys tile (float4-aligned, conflict-free)
 
 struct FrontendFwdParams {
@@ -42,18 +43,21 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
-// NTW = 0: fp32 FFMA day affine (the fp32 parity path, any N).  NTW = N/64 > 0: bf16 tensor-core day affine, N = 64*NTW:
+// NTW = 0: fp32 FFMA day affine (the fp32 parity path, any N).  NTW > 0: bf16 tensor-core day affine, N = 8*NTW*NWARPS:
 // warp w owns output channels [8*NTW*w, 8*NTW*(w+1)) and keeps its slice of dayWeights[day] as mma B fragments in
-// registers for the whole CTA; the smoothed block is the A operand (bf16, shared memory), fp32 accumulate.
-template <typename OutT, int NTW>
-__global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwdParams p) {
+// registers for the whole CTA; the smoothed block is the A operand (bf16, shared memory), fp32 accumulate.  The
+// competition shape (N = 256) runs 16 warps with NTW = 2: 64 weight registers per thread instead of 128, twice the warps
+// to hide the shared-memory and HBM latency of the four phases of a block.
+template <typename OutT, int NTW, int NWARPS>
+__global__ void __launch_bounds__(32 * NWARPS, 1) frontend_fwd_kernel(FrontendFwdParams p) {
+    constexpr int FE_THREADS = 32 * NWARPS;
     extern __shared__ __align__(16) float smem[];
     const int N = p.N, K = p.K, S = p.S, T = p.T, ntaps = p.ntaps;
     const int left = (ntaps - 1) / 2;
     const int xrows = FE_TT + ntaps - 1;
     const int NP = N + 1;
-    constexpr int KS = NTW * 4;                             // k-steps of 16 input channels (N / 16)
-    constexpr int NA = NTW * 64 + 8;                        // padded row length (bf16) of the A tile: conflict-free ldmatrix
+    constexpr int KS = NTW * NWARPS / 2;                    // k-steps of 16 input channels (N / 16)
+    constexpr int NA = NTW * NWARPS * 8 + 8;                // padded row length (bf16) of the A tile: conflict-free ldmatrix
     float* taps_s = smem;                                   // [64]
     float* xs = smem + 64;                                  // [xrows][N]
     float* ysT = xs + (size_t)xrows * N;                    // SIMT: [N][FE_TTP] f32;  TC: [FE_TT][NA] bf16
@@ -143,6 +147,42 @@ __global__ void __launch_bounds__(FE_THREADS, 1) frontend_fwd_kernel(FrontendFwd
         }
         __syncthreads();
         // 2. depthwise FIR: ys[t][c] = sum_k taps[k] * x[t-left+k][c]
+        if (ntaps == FE_NTAPS && (FE_THREADS % N) == 0 && (FE_TT % (FE_THREADS / N)) == 0) {
+            // fast path: a thread owns one channel and FE_TT / (FE_THREADS / N) consecutive rows; the rows' input window is
+            // read once into registers (RPT + 19 shared-memory loads instead of 2 * 20 * RPT) and the taps stay in registers
+            constexpr int RPT_MAX = FE_TT;
+            const int parts = FE_THREADS / N, rpt = FE_TT / parts;
+            const int c = tid % N, r0 = (tid / N) * rpt;
+            float tp[FE_NTAPS];
+#pragma unroll
+            for (int k = 0; k < FE_NTAPS; ++k) tp[k] = taps_s[k];
+            if (rpt == 16) {
+                float w[16 + FE_NTAPS - 1];
+#pragma unroll
+                for (int i = 0; i < 16 + FE_NTAPS - 1; ++i) w[i] = xs[(size_t)(r0 + i) * N + c];
+#pragma unroll
+                for (int tt = 0; tt < 16; ++tt) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < FE_NTAPS; ++k) acc = fmaf(tp[k], w[tt + k], acc);
+                    if (r0 + tt < rows) ysb[(size_t)(rb + r0 + tt) * N + c] = acc; else acc = 0.f;
+                    if constexpr (NTW > 0) ysA[(size_t)(r0 + tt) * NA + c] = __float2bfloat16_rn(acc);
+                    else ysT[(size_t)c * FE_TTP + r0 + tt] = acc;
+                }
+            } else {
+                (void)RPT_MAX;
+                for (int tt = r0; tt < r0 + rpt; ++tt) {
+                    float acc = 0.f;
+                    if (tt < rows) {
+#pragma unroll
+                        for (int k = 0; k < FE_NTAPS; ++k) acc = fmaf(tp[k], xs[(size_t)(tt + k) * N + c], acc);
+                        ysb[(size_t)(rb + tt) * N + c] = acc;
+                    }
+                    if constexpr (NTW > 0) ysA[(size_t)tt * NA + c] = __float2bfloat16_rn(acc);
+                    else ysT[(size_t)c * FE_TTP + tt] = acc;
+                }
+            }
+        } else
         for (int c = tid; c < N; c += FE_THREADS) {
             for (int tt = 0; tt < FE_TT; ++tt) {
                 float acc = 0.f;
@@ -528,6 +568,127 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_tc_kernel(Frontend
     if (half == 0) p.partial_b[(size_t)b * N + c0 + kl] = bacc + bsum[kl];
 }
 
+// Competition-shape form of the tensor-core backward (N = 256, kernelLen 32, stride 4, bf16 dpatches): 16 warps, and the
+// col2im runs in REGISTERS.  Thread (cl, ph) owns channel cl of the CTA's 128-column block and the rows t = ph (mod 4): a
+// row receives one tap from each of the K/S = 8 frames that cover it, so 8 rotating partial sums per thread are enough -- frame j
+// adds its taps ph, ph+4, .., ph+28 to the 8 sums and completes row 4j+ph.  No shared-memory ring, no read-modify-write,
+// two barriers per group of 4 frames (= one 16-row mma chunk): stage -> [col2im, softsign', bf16 tiles] -> mma, with the
+// tile buffers double-buffered so the mma of one group runs under the staging of the next.
+constexpr int FB2_THREADS = 512;
+__global__ void __launch_bounds__(FB2_THREADS, 1) frontend_bwd_tc2_kernel(FrontendBwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int N = 256, K = 32, S = 4, NYS = N + 8, NDP = FB_CN + 8, KP = 36, G = 4;
+    const int T = p.T, B = p.B, Tp = p.Tp;
+    const int b = blockIdx.x;
+    const int c0 = blockIdx.y * FB_CN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = tid >> 2, ph = tid & 3;
+    float* stage = smem;                                                                   // [G][FB_CN][KP] f32
+    __nv_bfloat16* ys_s = reinterpret_cast<__nv_bfloat16*>(stage + (size_t)G * FB_CN * KP);   // [2][16][N+8]
+    __nv_bfloat16* dp_s = ys_s + 2 * 16 * NYS;                                             // [2][16][FB_CN+8]
+    const float* ysb = p.ys + (size_t)b * T * N;
+    const float* zb = p.z + (size_t)b * T * N;
+    const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(p.dp);
+    constexpr int F = N * K;
+
+    float acc[FB_CN / 8][4];                     // dW rows [16*warp, 16*warp+16) x the CTA's 128 columns (mma C fragments)
+#pragma unroll
+    for (int nt = 0; nt < FB_CN / 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    float slot[8];                               // partial col2im sums of rows 4j+ph .. 4(j+7)+ph
+#pragma unroll
+    for (int i = 0; i < 8; ++i) slot[i] = 0.f;
+    float bacc = 0.f;
+    const int last_row = (Tp - 1) * S + K - 1;   // last z row any frame touches
+    const int ngroups = (Tp + 7 + G - 1) / G;    // real frames + 7 virtual (empty) frames that flush the rotating sums
+    int buf = 0;
+    for (int grp = 0; grp < ngroups; grp += 2) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int jg = (grp + hf) * G;
+            if (jg >= ngroups * G) break;
+            // a. stage this CTA's slice of up to 4 gradient rows (coalesced 16-byte loads), f32 in shared memory
+            for (int i = tid; i < G * FB_CN * K / 8; i += FB2_THREADS) {
+                const int g = i / (FB_CN * K / 8), r = i - g * (FB_CN * K / 8);
+                const int e = 8 * r, c = e / K, kk = e - c * K;
+                if (jg + g < Tp) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(dp + ((size_t)(jg + g) * B + b) * F + (size_t)c0 * K) + r);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    float* d = stage + (size_t)g * FB_CN * KP + c * KP + kk;
+                    const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+                    *reinterpret_cast<float4*>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    *reinterpret_cast<float4*>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+                }
+            }
+            // A^T tile: the 16 rows of ys this group completes, as bf16 (zero rows past the end)
+            __nv_bfloat16* ysw = ys_s + (size_t)buf * 16 * NYS;
+            __nv_bfloat16* dpw = dp_s + (size_t)buf * 16 * NDP;
+            for (int i = tid; i < 16 * (N / 4); i += FB2_THREADS) {
+                const int rr = i / (N / 4), c4 = i - rr * (N / 4);
+                const int t = jg * S + rr;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t <= last_row) v = __ldg(reinterpret_cast<const float4*>(ysb + (size_t)t * N) + c4);
+                *reinterpret_cast<uint2*>(ysw + (size_t)rr * NYS + 4 * c4) = make_uint2(pack2_bf16(v.x, v.y), pack2_bf16(v.z, v.w));
+            }
+            float zz[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int t = (jg + g) * S + ph;
+                zz[g] = (t <= last_row) ? __ldg(zb + (size_t)t * N + c0 + cl) : 0.f;
+            }
+            __syncthreads();
+            // b. register col2im: frame jg+g adds tap ph+4i to the sum of row 4(jg+g+i)+ph, then row 4(jg+g)+ph is complete
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                constexpr int dummy = 0; (void)dummy;
+                const int sl0 = (4 * hf + g) & 7;                    // static after unrolling: slot of the row this frame completes
+                if (jg + g < Tp) {
+                    const float* st = stage + (size_t)g * FB_CN * KP + cl * KP + ph;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) slot[(sl0 + i) & 7] += st[4 * i];
+                }
+                const int t = (jg + g) * S + ph;
+                float dpre = 0.f;
+                if (t <= last_row) {
+                    const float sg = 1.0f - fabsf(zz[g]);
+                    dpre = slot[sl0] * sg * sg;
+                }
+                slot[sl0] = 0.f;
+                bacc += dpre;
+                dpw[(size_t)(4 * g + ph) * NDP + cl] = __float2bfloat16_rn(dpre);
+            }
+            __syncthreads();
+            // c. dW[d][c] += sum over the 16 rows of ys[row][d] * dpre[row][c] on mma.sync (bf16 operands, fp32 accumulate)
+            {
+                uint32_t a[4];
+                ldmatrix_x4_trans(a, ysw + (size_t)((lane & 7) + 8 * (lane >> 4)) * NYS + warp * 16 + 8 * ((lane >> 3) & 1));
+#pragma unroll
+                for (int np = 0; np < FB_CN / 16; ++np) {
+                    uint32_t bq[4];
+                    ldmatrix_x4_trans(bq, dpw + (size_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * NDP + 16 * np + 8 * (lane >> 4));
+                    mma_bf16_16816(acc[2 * np], a, bq[0], bq[1]);
+                    mma_bf16_16816(acc[2 * np + 1], a, bq[2], bq[3]);
+                }
+            }
+            buf ^= 1;
+        }
+    }
+    // this utterance's partial dW block / db: C fragment (row = lane/4 (+8), cols 2*(lane%4), +1)
+    float* pw = p.partial_w + (size_t)b * N * N;
+    const int fg = lane >> 2, fc = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < FB_CN / 8; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int d = warp * 16 + fg + 8 * h;
+            *reinterpret_cast<float2*>(pw + (size_t)d * N + c0 + 8 * nt + 2 * fc) = make_float2(acc[nt][2 * h], acc[nt][2 * h + 1]);
+        }
+    bacc += __shfl_xor_sync(0xffffffffu, bacc, 1);          // the four phases of a channel sit in adjacent lanes
+    bacc += __shfl_xor_sync(0xffffffffu, bacc, 2);
+    if (ph == 0) p.partial_b[(size_t)b * N + c0 + cl] = bacc;
+}
+
 // out[d][e] = sum_{b : day[b]==d} partial[b][e], utterances visited in index order (deterministic).
 __global__ void day_segment_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
                                           const int64_t* __restrict__ day_idx, int B, int NN, int N, int n_days,
@@ -599,24 +760,24 @@ int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w,
     p.frames_per_seg = cdiv(p.Tp, nseg);
     p.ring = 1;
     while (p.ring < kernel_len + FE_TT) p.ring <<= 1;      // power of two: ring rows are addressed with a mask
-    // bf16 patches (the tensor-core model path) with 64 | N <= 256: day affine on mma.sync; otherwise the exact fp32 FFMA form
-    const int ntw = (patches_dtype == NSD_BF16 && N % 64 == 0 && N <= 256) ? N / 64 : 0;
+    // bf16 patches (the tensor-core model path) with N in {64, 128, 256}: day affine on mma.sync; otherwise the exact fp32 FFMA form
+    const bool tc = patches_dtype == NSD_BF16 && (N == 64 || N == 128 || N == 256);
     size_t smem = sizeof(float) * (64 + (size_t)(FE_TT + ntaps - 1) * N + (size_t)p.ring * (N + 1) +
-                                   (ntw ? (size_t)FE_TT * (N + 8) / 2 : (size_t)N * FE_TTP));
+                                   (tc ? (size_t)FE_TT * (N + 8) / 2 : (size_t)N * FE_TTP));
     NSD_CHECK_ARG(smem <= 227 * 1024, "frontend_fwd: N=%d kernelLen=%d need %zu B shared memory", N, kernel_len, smem);
     dim3 grid(B, cdiv(p.Tp, p.frames_per_seg));
     cudaStream_t s = (cudaStream_t)stream;
-    auto go = [&](auto kern) -> int {
+    auto go = [&](auto kern, int threads) -> int {
         NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, FE_THREADS, smem, s>>>(p);
+        kern<<<grid, threads, smem, s>>>(p);
         return NSD_OK;
     };
     int rc;
-    if (patches_dtype == NSD_F32) rc = go(frontend_fwd_kernel<float, 0>);
-    else if (ntw == 4) rc = go(frontend_fwd_kernel<__nv_bfloat16, 4>);
-    else if (ntw == 2) rc = go(frontend_fwd_kernel<__nv_bfloat16, 2>);
-    else if (ntw == 1) rc = go(frontend_fwd_kernel<__nv_bfloat16, 1>);
-    else rc = go(frontend_fwd_kernel<__nv_bfloat16, 0>);
+    if (patches_dtype == NSD_F32) rc = go(frontend_fwd_kernel<float, 0, 8>, 256);
+    else if (tc && N == 256) rc = go(frontend_fwd_kernel<__nv_bfloat16, 2, 16>, 512);
+    else if (tc && N == 128) rc = go(frontend_fwd_kernel<__nv_bfloat16, 1, 16>, 512);
+    else if (tc && N == 64) rc = go(frontend_fwd_kernel<__nv_bfloat16, 1, 8>, 256);
+    else rc = go(frontend_fwd_kernel<__nv_bfloat16, 0, 8>, 256);
     if (rc) return rc;
     NSD_LAUNCH_CHECK();
     return NSD_OK;
@@ -658,7 +819,14 @@ int nsd_frontend_bwd(const void* dpatches, int dpatches_dtype, const float* ys, 
     while (p.ring < (FB_G - 1) * stride_len + kernel_len) p.ring <<= 1;   // power of two: ring rows are addressed with a mask
     cudaStream_t s = (cudaStream_t)stream;
     const int mt = (dpatches_dtype == NSD_BF16 && (N == 128 || N == 256)) ? N / 128 : 0;
-    if (mt) {
+    static const bool no_fast = [] { const char* e = getenv("NSD_K1_BWD_V1"); return e && e[0] == '1'; }();     // debug: previous form
+    if (mt == 2 && kernel_len == 32 && stride_len == 4 && !no_fast) {
+        // competition shape: 16 warps, register col2im
+        const size_t smem = sizeof(float) * (size_t)4 * FB_CN * 36 + sizeof(__nv_bfloat16) * (2 * 16 * (size_t)(N + 8) + 2 * 16 * (size_t)(FB_CN + 8));
+        dim3 grid(B, N / FB_CN);
+        NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frontend_bwd_tc2_kernel<<<grid, FB2_THREADS, smem, s>>>(p);
+    } else if (mt) {
         // bf16 model path: per-utterance ys^T dpre on tensor cores
         size_t smem = sizeof(float) * ((((size_t)p.ring * (FB_CN + 1) + 3) & ~(size_t)3) + (size_t)FB_G * FB_CN * p.KP + FB_CN) +
                       sizeof(__nv_bfloat16) * (16 * (size_t)(N + 8) + 16 * (size_t)(FB_CN + 8));

@@ -15,10 +15,12 @@
 //     one cp.async.bulk per peer completes the peer's inbox mbarrier.  Each CTA finalises 16 (BPTT: 32) units: gate math
 //     for (batch row, 4 units) per thread and pass, bf16 state stored first and published, fp32 state / saved gates after.
 //   * steps are separated by per-cluster ("zone") step counters in global memory (release add / acquire polls).
-//   * OPERAND RING: the previous state arrives as 64-column boxes, one TMA per box into a ring of shared-memory stages
-//     (full / empty mbarriers).  Lane c of the TMA warp owns box c of every item: it waits only for the zone(s) that
-//     PRODUCE its 64 columns (plus this CTA's own cluster) and issues its box the moment they have published; the MMA
-//     warp consumes boxes in order, so the tensor work of early zones runs under the wait for late ones.
+//   * OPERAND RING: the previous state of a chain arrives as one (BPTT with 64-row chains: two) multi-chunk TMA box into a
+//     two-stage shared-memory ring with full / empty mbarriers.  The lanes of the TMA warp poll, in parallel, only the
+//     zones that PRODUCE this CTA's K share (plus the CTA's own cluster); one fence, one TMA per stage.  (Tried and
+//     rejected, profiles/r02_k3_ring_experiment.log: one TMA per 64-column box issued by its own lane as soon as that
+//     box's zone had published -- the zones publish within a few hundred cycles of each other, while a per-lane
+//     fence.proxy.async + per-box barrier hand-offs cost 0.5 us per step forward and 2 us per step in the BPTT.)
 //   * LATENCY HIDING: two independent batch chains are in flight per CTA, each with its own TMEM accumulator and
 //     in/outbox, so the barrier + exchange latency of one chain runs under the MMAs and gate math of the other.
 //     B <= 64 (WPC = 1): a chain is 32 batch rows (UMMA N = 32) and owns one epilogue warpgroup.  B > 64 (WPC = 2): a
@@ -37,8 +39,7 @@ constexpr int WG_THREADS = 128;         // epilogue warpgroup
 constexpr int THREADS = CTRL_THREADS + 2 * WG_THREADS;
 constexpr int TMEM_COLS = 512;
 constexpr int CNT_STRIDE = 32;          // uint32 slots between two step counters (128 B apart)
-constexpr int MAX_STAGES = 24;
-constexpr int RING_BYTES = 96 * 1024;   // upper bound of the operand ring
+constexpr int MAX_STAGES = 2;
 constexpr int TRACE_STEPS = 16;
 
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -78,6 +79,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         }
     }
 }
+__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
+    if (ld_acquire_u32(counter) >= target) return;
+    const long long t0 = clock64();
+    unsigned int spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+        if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
+            printf("nsd gru_ts: zone barrier timeout (block %d, have %u want %u)\n", blockIdx.x, ld_acquire_u32(counter), target);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void red_release_add(unsigned int* p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
@@ -103,10 +115,11 @@ struct Common {
     int ktot, kper;                         // reduction length (H forward, 3H BPTT) and its share per CTA (multiple of 16)
     int s0, row_off;                        // first step with a recurrent term (0 when an initial state is given, else 1); rows the
                                             // exchanged-state tensor is shifted by (B when its first B rows hold the initial state)
-    int nstage;                             // operand ring depth (boxes)
+    int bps, chunked;                       // boxes per ring stage (two stages); 1: the K shares are whole 64-wide chunks -> one 3-D TMA box per stage
     int cs, upz, nzone;                     // CTAs per cluster, units per zone (= per cluster), zones per direction
     unsigned int* counters;                 // [D][nchain][nzone] step counters, CNT_STRIDE apart: cs * WPC arrivals per step
     long long* trace;                       // debug (NSD_GRU_TRACE=1)
+    int dbg;                                // timing experiments only (WRONG RESULTS): bit 0 = skip the zone waits, bit 1 = publish without release fence
 };
 // Debug stamps go to shared memory (a global store here would sit in front of the next fence) and are dumped at exit.
 __device__ __forceinline__ void stamp(const Common& c, long long* tsm, int s, int ev) {
@@ -124,6 +137,10 @@ __device__ __forceinline__ void trace_dump(const Common& c, const long long* tsm
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < TRACE_STEPS * 8; i += blockDim.x) c.trace[i] = tsm[i];
 }
+__device__ __forceinline__ void publish(const Common& c, unsigned int* p) {
+    if (c.dbg & 2) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+    else red_release_add(p);
+}
 __device__ __forceinline__ unsigned int* zone_counter(const Common& c, int d, int chain, int zone) {
     return c.counters + (size_t)((d * c.nchain + chain) * c.nzone + zone) * CNT_STRIDE;
 }
@@ -134,7 +151,7 @@ __device__ __forceinline__ unsigned int* zone_counter(const Common& c, int d, in
 __device__ __forceinline__ int rot_f32(int u) { return ((4 * ((u >> 2) & 1) + 2 * ((u >> 3) & 1) + 2 * ((u >> 1) & 1) + (u & 1)) & 7) * 4; }
 __device__ __forceinline__ int rot_bf16(int u) { return (((u >> 1) & 3) ^ ((u >> 3) & 1)) * 8; }
 
-// Shared memory: [operand ring: nstage boxes][inbox: NSLOT x (CS-1) messages][outbox: same][self: 2 x fp32 rows][barriers]
+// Shared memory: [operand ring: 2 stages of bps boxes][inbox: NSLOT x (CS-1) messages][outbox: same][self: 2 x fp32 rows][barriers]
 // NSLOT = 2 * WPC message slots: one per (warpgroup, chain the warpgroup works on).
 struct Smem {
     uint8_t* ring; uint8_t* inbox; uint8_t* outbox; float* self;
@@ -164,9 +181,9 @@ static size_t smem_bytes(int ring_bytes, int nslot, int msgs_bytes, int self_byt
     return extra + (size_t)ring_bytes + 2 * (size_t)nslot * msgs_bytes + 2 * (size_t)self_bytes + BAR_WORDS * 8 + (TRACE_STEPS + 1) * 64 + 1024 + 64;
 }
 
-__device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane, int nstage) {
+__device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane) {
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < nstage; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
         for (int i = 0; i < 2; ++i) mbar_init(&sm.tmem_full[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&sm.inbox_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,15 +230,16 @@ __device__ __forceinline__ void load_a_row(uint32_t taddr_row, const __nv_bfloat
 }
 
 // Control warps of both kernels.  Item (s, ch): step s >= s0 of the chain `ch` of the current chain pair consumes the rows
-// the direction produced in step s-1 of that chain, as nbox boxes of 64 columns.
-//   warp 0, lane c < nbox: box c of every item.  It waits for (a) its ring stage to be free, (b) the zone(s) producing its
-//     columns and (c) this CTA's own cluster to have published step s-1 of the chain -- (c) means my MMAs and epilogue of the
-//     previous step of this chain are finished and my peers have drained their inboxes, so the chain's TMEM accumulator and
-//     message buffers are free -- and then issues the box.
-//   warp 1: waits for each box in order and issues its MMAs; a tcgen05.commit per box frees the stage, one per item wakes the
+// the direction produced in step s-1 of that chain: nbox boxes of 64 columns, loaded as nsub = nbox / bps TMA boxes of bps
+// chunks each into consecutive ring stages.
+//   warp 0: lane i < nbox polls the zone(s) that produce box i (a 64-wide box touches at most two); lane 31 polls this
+//     CTA's own cluster: once it has published step s-1 of the chain, my MMAs and epilogue of that step are finished and my
+//     peers have drained their inboxes, so the chain's TMEM accumulator and message buffers are free.  Then lane 0 fences
+//     once and issues the stage(s) as their empty barriers allow.
+//   warp 1: waits for each stage in order and issues its MMAs; a tcgen05.commit per stage frees it, one per item wakes the
 //     chain's epilogue.
 template <int NT, int WPC>
-__device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, int warp, int lane, uint32_t tmem_base,
+__device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, const CUtensorMap* tmB3, int warp, int lane, uint32_t tmem_base,
                                               const Common& c, int d, int my_zone, int k_lo, int k_hi, int nslab, int nbox,
                                               int b_col0, bool bptt) {
     constexpr int NROW = NG * WPC;
@@ -229,52 +247,54 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
     constexpr uint32_t A_COL0 = 2 * NT * NROW;
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int kc = c.kper / 2;
-    const int nboxe = nbox > 0 ? nbox : 1;          // a CTA without a K share still paces its epilogue with one empty "box"
+    const int bps = c.bps;                           // boxes per ring stage
+    const int nsub = nbox > 0 ? (nbox + bps - 1) / bps : 1;      // a CTA without a K share still paces its epilogue with one empty stage
     const int npair = (c.nchain + 1) / 2;
     if (warp == 0) {
-        if (lane < nboxe) {
-            int z0 = my_zone, z1 = my_zone;
-            if (nbox > 0) {
-                const int c0 = k_lo + lane * BK, c1 = min(c0 + BK, k_hi) - 1;
-                z0 = (c0 % c.H) / c.upz; z1 = (c1 % c.H) / c.upz;
-            }
-            uint32_t seq = (uint32_t)lane;
-            for (int pr = 0; pr < npair; ++pr) {
-                for (int s = c.s0; s < c.Tp; ++s) {
-                    int t_src;
-                    if (!bptt) { const int t = rev ? (c.Tp - 1 - s) : s; t_src = rev ? t + 1 : t - 1; }
-                    else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
-                    for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch, seq += (uint32_t)nboxe) {
-                        const int chain = 2 * pr + ch;
-                        const uint32_t stage = seq % (uint32_t)c.nstage, use = seq / (uint32_t)c.nstage;
-                        mbar_wait(&sm.empty[stage], (use & 1u) ^ 1u);
-                        const unsigned int want = (unsigned int)(s * c.cs * WPC);
-                        const unsigned int* p0 = zone_counter(c, d, chain, z0);
-                        const unsigned int* p1 = zone_counter(c, d, chain, z1);
-                        const unsigned int* pm = zone_counter(c, d, chain, my_zone);
-                        const long long t0 = clock64();
-                        unsigned int spins = 0;
-                        for (;;) {
-                            bool ok = ld_acquire_u32(p0) >= want;
-                            if (p1 != p0) ok = (ld_acquire_u32(p1) >= want) && ok;
-                            if (pm != p0 && pm != p1) ok = (ld_acquire_u32(pm) >= want) && ok;
-                            if (ok) break;
-                            if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
-                                printf("nsd gru_ts: zone barrier timeout (block %d lane %d step %d, want %u)\n", blockIdx.x, lane, s, want);
-                                __trap();
-                            }
-                        }
-                        if (lane == 0 && chain == 0) stamp(c, sm.trace, s, 0);
-                        if (nbox > 0) {
-                            asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy writes (acquired above) -> TMA reads
-                            mbar_expect_tx(&sm.full[stage], (uint32_t)BOXB);
-                            tma_load_2d(tmB, &sm.full[stage], sm.ring + (size_t)stage * BOXB, b_col0 + k_lo + lane * BK,
-                                        t_src * c.B + chain * NROW + c.row_off);
-                        } else {
-                            mbar_arrive(&sm.full[stage]);
-                        }
-                        if (lane == 0 && chain == 0) stamp(c, sm.trace, s, 1);
+        int z0 = my_zone, z1 = my_zone;
+        if (lane < nbox) {
+            const int c0 = k_lo + lane * BK, c1 = min(c0 + BK, k_hi) - 1;
+            z0 = (c0 % c.H) / c.upz; z1 = (c1 % c.H) / c.upz;
+        }
+        const bool poller = lane < nbox || lane == 31;
+        uint32_t seq = 0;
+        for (int pr = 0; pr < npair; ++pr) {
+            for (int s = c.s0; s < c.Tp; ++s) {
+                int t_src;
+                if (!bptt) { const int t = rev ? (c.Tp - 1 - s) : s; t_src = rev ? t + 1 : t - 1; }
+                else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
+                for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch) {
+                    const int chain = 2 * pr + ch;
+                    const unsigned int want = (unsigned int)(s * c.cs * WPC);
+                    if (poller && !(c.dbg & 1)) {
+                        grid_wait(zone_counter(c, d, chain, z0), want);
+                        if (z1 != z0) grid_wait(zone_counter(c, d, chain, z1), want);
                     }
+                    __syncwarp();
+                    if (lane == 0 && chain == 0) stamp(c, sm.trace, s, 0);
+                    if (lane == 0) asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy writes (acquired above) -> TMA reads
+                    const int row = t_src * c.B + chain * NROW + c.row_off;
+                    for (int sub = 0; sub < nsub; ++sub, ++seq) {
+                        const uint32_t stage = seq & 1u, use = seq >> 1;
+                        if (lane == 0) mbar_wait(&sm.empty[stage], (use & 1u) ^ 1u);
+                        __syncwarp();
+                        uint8_t* dst = sm.ring + (size_t)stage * bps * BOXB;
+                        const int nb = min(bps, nbox - sub * bps);              // boxes in this stage
+                        if (nbox == 0) {
+                            if (lane == 0) mbar_arrive(&sm.full[stage]);
+                        } else if (c.chunked) {
+                            // K share aligned to 64-wide chunks: the whole stage (nb swizzled tiles) in one TMA instruction
+                            if (lane == 0) {
+                                mbar_expect_tx(&sm.full[stage], (uint32_t)(nb * BOXB));
+                                tma_load_3d(tmB3, &sm.full[stage], dst, 0, row, (b_col0 + k_lo) / BK + sub * bps);
+                            }
+                        } else {
+                            if (lane == 0) mbar_expect_tx(&sm.full[stage], (uint32_t)(nb * BOXB));
+                            __syncwarp();
+                            if (lane < nb) tma_load_2d(tmB, &sm.full[stage], dst + (size_t)lane * BOXB, b_col0 + k_lo + (sub * bps + lane) * BK, row);
+                        }
+                    }
+                    if (lane == 0 && chain == 0) stamp(c, sm.trace, s, 1);
                 }
             }
         }
@@ -286,29 +306,32 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
         for (int pr = 0; pr < npair; ++pr) {
             for (int s = c.s0; s < c.Tp; ++s) {
                 for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch) {
-                    for (int bx = 0; bx < nboxe; ++bx, ++seq) {
-                        const uint32_t stage = seq % (uint32_t)c.nstage, use = seq / (uint32_t)c.nstage;
+                    for (int sub = 0; sub < nsub; ++sub, ++seq) {
+                        const uint32_t stage = seq & 1u, use = seq >> 1;
                         mbar_wait(&sm.full[stage], use & 1u);
-                        if (lane == 0 && 2 * pr + ch == 0 && bx == 0) stamp(c, sm.trace, s, 2);
+                        if (lane == 0 && 2 * pr + ch == 0 && sub == 0) stamp(c, sm.trace, s, 2);
                         tcgen05_fence_after();
                         if (elect_one()) {
                             if (nslab > 0) {
-                                const int ns = min(4, nslab - 4 * bx);                  // one box = 4 K slabs
-                                const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.ring + (size_t)stage * BOXB));
+                                const int sl0 = 4 * sub * bps, sl1 = min(nslab, sl0 + 4 * bps);      // K slabs of this stage (4 per box)
 #pragma unroll
                                 for (int t = 0; t < NT; ++t) {
                                     const uint32_t dcol = tmem_base + (uint32_t)((ch * NT + t) * NROW);
-                                    const uint32_t acol = tmem_base + A_COL0 + (uint32_t)(t * kc + bx * 32);
-                                    umma_ts_bf16(dcol, acol, bdesc, idesc, bx != 0);
-                                    if (ns > 1) umma_ts_bf16(dcol, acol + 8u, bdesc + 2u, idesc, 1u);
-                                    if (ns > 2) umma_ts_bf16(dcol, acol + 16u, bdesc + 4u, idesc, 1u);
-                                    if (ns > 3) umma_ts_bf16(dcol, acol + 24u, bdesc + 6u, idesc, 1u);
+                                    uint32_t acol = tmem_base + A_COL0 + (uint32_t)(t * kc + 8 * sl0);
+                                    uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.ring + (size_t)stage * bps * BOXB));
+                                    for (int sl = sl0; sl < sl1; sl += 4, acol += 32u, bdesc += (uint64_t)(BOXB >> 4)) {   // one box = 4 slabs
+                                        const int ns = sl1 - sl;
+                                        umma_ts_bf16(dcol, acol, bdesc, idesc, sl != 0);
+                                        if (ns > 1) umma_ts_bf16(dcol, acol + 8u, bdesc + 2u, idesc, 1u);
+                                        if (ns > 2) umma_ts_bf16(dcol, acol + 16u, bdesc + 4u, idesc, 1u);
+                                        if (ns > 3) umma_ts_bf16(dcol, acol + 24u, bdesc + 6u, idesc, 1u);
+                                    }
                                 }
                                 umma_commit(&sm.empty[stage]);
-                                if (bx == nboxe - 1) umma_commit(&sm.tmem_full[ch]);
+                                if (sub == nsub - 1) umma_commit(&sm.tmem_full[ch]);
                             } else {
                                 mbar_arrive(&sm.empty[stage]);
-                                if (bx == nboxe - 1) mbar_arrive(&sm.tmem_full[ch]);
+                                if (sub == nsub - 1) mbar_arrive(&sm.tmem_full[ch]);
                             }
                         }
                         __syncwarp();
@@ -409,7 +432,7 @@ struct FwdParams {
 
 template <int WPC>
 __global__ void __launch_bounds__(THREADS, 1)
-gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
+gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmH3, const FwdParams p) {
     constexpr int CS = 4, NT = 2, NGATE = 3, U = 16, NROW = NG * WPC, NSLOT = 2 * WPC;
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
     constexpr uint32_t A_COL0 = 2 * NT * NROW;
@@ -425,10 +448,10 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
     const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
     const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK;
     const int kc = c.kper / 2;
-    const Smem sm = carve(smem_raw, c.nstage * NROW * 128, NSLOT, MSGS, SELF);
+    const Smem sm = carve(smem_raw, 2 * c.bps * NROW * 128, NSLOT, MSGS, SELF);
     if (c.trace != nullptr)
         for (int i = threadIdx.x; i < (TRACE_STEPS + 1) * 8; i += blockDim.x) sm.trace[i] = 0;
-    const uint32_t tmem_base = setup(sm, warp, lane, c.nstage);
+    const uint32_t tmem_base = setup(sm, warp, lane);
 
     if (warp >= 4) {
         // stationary weights: tile t = units uc0 + 32t .. +32, lanes [r | z | n | unused] x 32 units, my quarter of K
@@ -442,7 +465,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT, WPC>(sm, &tmH, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * H, false);
+        control_warps<NT, WPC>(sm, &tmH, &tmH3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * H, false);
     } else {
         // ------------------------------------------------------------ epilogue warpgroup w
         // WPC == 1: it owns chain w of every chain pair (32 rows).  WPC == 2: it finalises rows [32w, 32w+32) of BOTH chains.
@@ -533,7 +556,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const FwdParams p) {
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
                     wg_bar_sync(w);                              // (the consumer fences generic->async proxy after its acquire)
                     if (te == 0) {
-                        red_release_add(zone_counter(c, d, chain, my_zone));
+                        publish(c, zone_counter(c, d, chain, my_zone));
                         if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
                     }
                     if (row_ok) {                                // off the critical path: nobody else reads these during the launch
@@ -574,7 +597,7 @@ struct BwdParams {
 
 template <int WPC>
 __global__ void __launch_bounds__(THREADS, 1)
-gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
+gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG3, const BwdParams p) {
     constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16, NROW = NG * WPC, NSLOT = 2 * WPC;       // NP passes of (batch row, 4 units) per thread
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
     constexpr uint32_t A_COL0 = 2 * NT * NROW;
@@ -590,10 +613,10 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
     const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK;
     const int kc = c.kper / 2;
-    const Smem sm = carve(smem_raw, c.nstage * NROW * 128, NSLOT, MSGS, SELF);
+    const Smem sm = carve(smem_raw, 2 * c.bps * NROW * 128, NSLOT, MSGS, SELF);
     if (c.trace != nullptr)
         for (int i = threadIdx.x; i < (TRACE_STEPS + 1) * 8; i += blockDim.x) sm.trace[i] = 0;
-    const uint32_t tmem_base = setup(sm, warp, lane, c.nstage);
+    const uint32_t tmem_base = setup(sm, warp, lane);
 
     if (warp >= 4) {
         // stationary weights: lane = unit uc0 + lane of W_hh^T [H, 3H], my quarter of the gate index; the two warpgroups
@@ -608,7 +631,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT, WPC>(sm, &tmG, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * 3 * H, true);
+        control_warps<NT, WPC>(sm, &tmG, &tmG3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * 3 * H, true);
     } else {
         const int e = warp - 4, w4 = e & 3, w = e >> 2, te = w4 * 32 + lane;
         const int bl = te >> 2, uo4 = te & 3;
@@ -708,7 +731,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
                     wg_bar_sync(w);                              // (the consumer fences generic->async proxy after its acquire)
                     if (te == 0) {
-                        red_release_add(zone_counter(c, d, chain, my_zone));
+                        publish(c, zone_counter(c, d, chain, my_zone));
                         if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
                     }
 #pragma unroll
@@ -751,7 +774,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
 
 // ---------------------------------------------------------------- host side
 template <typename Kern, typename P>
-static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const P& p, cudaStream_t s) {
+static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1, const P& p, cudaStream_t s) {
     NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -767,7 +790,7 @@ static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const C
     int max_clusters = 0;
     NSD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters * cs < grid) { set_error("gru_ts: %d CTAs in clusters of %d cannot be co-resident (max %d clusters)", grid, cs, max_clusters); return NSD_ERR_INVALID; }
-    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, p));
+    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, p));
     count_launch(1);
     return NSD_OK;
 }
@@ -805,6 +828,10 @@ static void trace_end(const char* who, long long* d, cudaStream_t s, int grid = 
     }
 }
 
+static int debug_flags() {
+    static const int f = [] { const char* e = getenv("NSD_GRU_DEBUG"); return e ? atoi(e) : 0; }();
+    return f;
+}
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // chains of 32 rows (one warpgroup each) up to B = 64, chains of 64 rows (both warpgroups) beyond
 static int wg_per_chain(int B) {
@@ -813,12 +840,12 @@ static int wg_per_chain(int B) {
     return B > 2 * NG ? 2 : 1;
 }
 static int n_chains(int B, int wpc) { return (B + NG * wpc - 1) / (NG * wpc); }
-static int ring_stages(int nbox, int wpc) {
+// boxes per ring stage: the whole K share of a step, or half of it when two such stages would not fit (BPTT, 64-row chains)
+static int boxes_per_stage(int nbox, int wpc) {
     const int box_bytes = NG * wpc * 128;
-    int n = 2 * (nbox > 0 ? nbox : 1);
-    if (n > RING_BYTES / box_bytes) n = RING_BYTES / box_bytes;
-    if (n > MAX_STAGES) n = MAX_STAGES;
-    return n < 2 ? 2 : n;
+    int bps = nbox > 0 ? nbox : 1;
+    if (2 * bps * box_bytes > 96 * 1024 && bps % 2 == 0) bps /= 2;
+    return bps;
 }
 
 static int check_shape(const char* who, int Tp, int B, int H, int D, int cs, int u) {
@@ -861,16 +888,19 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
     const int kper = round_up(cdiv(H, CS), UMMA_K);
-    const int nbox = cdiv(kper, BK), nstage = ring_stages(nbox, wpc);
-    p.c = {Tp, B, H, D, reverse0, nper, n_chains(B, wpc), H, kper, h0 ? 0 : 1, row_off, nstage, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    const int nbox = cdiv(kper, BK), bps = boxes_per_stage(nbox, wpc);
+    const int chunked = (kper % BK == 0 && H % BK == 0) ? 1 : 0;
+    CUtensorMap tmH3 = tmH;
+    if (chunked) { rc = make_bf16_map_chunked(&tmH3, hseq_bf16, (long long)Tp * B + row_off, D * H, ldh, NG * wpc, bps); if (rc) return rc; }
+    p.c = {Tp, B, H, D, reverse0, nper, n_chains(B, wpc), H, kper, h0 ? 0 : 1, row_off, bps, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr, debug_flags()};
     p.h0 = h0;
     p.w = reinterpret_cast<const __nv_bfloat16*>(w_hh_bf16);
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.hdrop = reinterpret_cast<__nv_bfloat16*>(hdrop_bf16); p.drop_thresh = dropout_threshold(p_drop); p.inv_keep = 1.0f / (1.0f - p_drop); p.seed = seed;
-    const size_t smem = smem_bytes(nstage * NG * wpc * 128, 2 * wpc, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
-    rc = wpc == 1 ? launch_cluster_coop(gru_fwd_ts_kernel<1>, D * nper, CS, smem, tmH, p, s)
-                  : launch_cluster_coop(gru_fwd_ts_kernel<2>, D * nper, CS, smem, tmH, p, s);
+    const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, 2 * wpc, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
+    rc = wpc == 1 ? launch_cluster_coop(gru_fwd_ts_kernel<1>, D * nper, CS, smem, tmH, tmH3, p, s)
+                  : launch_cluster_coop(gru_fwd_ts_kernel<2>, D * nper, CS, smem, tmH, tmH3, p, s);
     trace_end("gru_fwd_bf16", tr, s, D * nper);
     return rc;
 }
@@ -898,8 +928,11 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     long long* tr = trace_begin();
     const int nper = cdiv(H, CS * U) * CS;
     const int kper = round_up(cdiv(3 * H, CS), UMMA_K);
-    const int nbox = cdiv(kper, BK), nstage = ring_stages(nbox, wpc);
-    p.c = {Tp, B, H, D, reverse0, nper, n_chains(B, wpc), 3 * H, kper, 1, 0, nstage, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr};
+    const int nbox = cdiv(kper, BK), bps = boxes_per_stage(nbox, wpc);
+    const int chunked = (kper % BK == 0) ? 1 : 0;
+    CUtensorMap tmG3 = tmG;
+    if (chunked) { rc = make_bf16_map_chunked(&tmG3, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG * wpc, bps); if (rc) return rc; }
+    p.c = {Tp, B, H, D, reverse0, nper, n_chains(B, wpc), 3 * H, kper, 1, 0, bps, chunked, CS, CS * U, nper / CS, reinterpret_cast<unsigned int*>(workspace), tr, debug_flags()};
     p.wT = reinterpret_cast<const __nv_bfloat16*>(w_hhT_bf16);
     p.dhseq = dhseq; p.lddh = lddh; p.hseq = hseq; p.ldh = ldh; p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.dgi = reinterpret_cast<__nv_bfloat16*>(dgi_bf16); p.dgh = reinterpret_cast<__nv_bfloat16*>(dgh_bf16); p.ldg = ldg;
@@ -909,9 +942,9 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
         NSD_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)D * 3 * H, s));
         NSD_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)D * 3 * H, s));
     }
-    const size_t smem = smem_bytes(nstage * NG * wpc * 128, 2 * wpc, (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
-    rc = wpc == 1 ? launch_cluster_coop(gru_bwd_ts_kernel<1>, D * nper, CS, smem, tmG, p, s)
-                  : launch_cluster_coop(gru_bwd_ts_kernel<2>, D * nper, CS, smem, tmG, p, s);
+    const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, 2 * wpc, (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
+    rc = wpc == 1 ? launch_cluster_coop(gru_bwd_ts_kernel<1>, D * nper, CS, smem, tmG, tmG3, p, s)
+                  : launch_cluster_coop(gru_bwd_ts_kernel<2>, D * nper, CS, smem, tmG, tmG3, p, s);
     trace_end("gru_bwd_bf16", tr, s, D * nper);
     return rc;
 }
