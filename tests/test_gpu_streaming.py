@@ -67,3 +67,57 @@ def test_streaming_rejects_unsupported_models():
     m = build(bidirectional=True, **kw)
     with pytest.raises(nsd.NsdError):
         nsd.StreamingDecoder(m, 1, torch.zeros(1, dtype=torch.int64))
+
+
+def port_streaming_oracle(port, X, day, frames_per_call):
+    """Oracle for the streaming path built from the REFERENCE's operators (oracle/torch_port.py): the front end of the whole
+    utterance (smoothing -> day affine -> softsign -> unfold, model.py:84-101), then ``nn.GRU`` fed ``frames_per_call`` frames at
+    a time with the final state h_n of one call carried into the next as h0 -- what a stateful version of model.py:104-119
+    computes -- and the output layer.  Returns logits [B, T', C]."""
+    import torch.nn.functional as F
+    with torch.no_grad():
+        x = X.permute(0, 2, 1)
+        x = F.conv1d(x, port.smooth_w, groups=port.neural_dim, padding="same").permute(0, 2, 1)
+        w = torch.index_select(port.dayWeights, 0, day)
+        x = F.softsign(torch.einsum("btd,bdk->btk", x, w) + torch.index_select(port.dayBias, 0, day))
+        x = F.unfold(x.permute(0, 2, 1).unsqueeze(3), (port.kernelLen, 1), stride=port.strideLen).permute(0, 2, 1)
+        h = torch.zeros(port.layer_dim, x.size(0), port.hidden_dim, dtype=x.dtype)
+        outs = []
+        for j in range(0, x.size(1), frames_per_call):
+            hid, h = port.gru(x[:, j:j + frames_per_call], h)            # carried h_n
+            outs.append(port.fc(hid))
+        return torch.cat(outs, dim=1)
+
+
+def test_streaming_vs_reference_operators_with_carried_state():
+    """StreamingDecoder at the competition architecture (unidirectional 5x1024), 4 bins per push, against the chunked
+    reference-operator oracle above (CPU, fp64).  bf16 tolerance as stated in tests/test_gpu_fullshape.py (BF16_TOL)."""
+    from oracle import torch_port as P
+    kw = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, strideLen=4, kernelLen=32, gaussianSmoothWidth=2.0)
+    B, T = 2, 260
+    m = build(**kw)
+    port = P.PortGRUDecoder(bidirectional=False, dropout=0.0, **kw)
+    port.load_reference_state({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    port = port.double().eval()
+    g = torch.Generator().manual_seed(77)
+    X = torch.randn(B, T, 256, generator=g)
+    day = torch.randint(0, 24, (B,), generator=g)
+    ref = port_streaming_oracle(port, X.double(), day, frames_per_call=1).numpy()
+    # the chunked oracle equals the reference's offline forward (h0 = 0 once): carrying h_n is exact
+    with torch.no_grad():
+        np.testing.assert_allclose(ref, port(X.double(), day).numpy(), rtol=0, atol=1e-10)
+    sd = nsd.StreamingDecoder(m, B, day.to(DEV))
+    outs = []
+    for pos in range(0, T, 4):
+        o = sd.push(X[:, pos:pos + 4].to(DEV))
+        if o is not None:
+            outs.append(o)
+    o = sd.finish()
+    if o is not None:
+        outs.append(o)
+    got = torch.cat(outs, dim=1).cpu().numpy().astype(np.float64)
+    assert got.shape == ref.shape
+    err = np.abs(got - ref).max()
+    agree = (got.argmax(-1) == ref.argmax(-1)).mean()
+    print(f"streaming vs chunked reference operators: logits max abs err {err:.3e} (|ref| max {np.abs(ref).max():.2f}), argmax agreement {agree:.4f}")
+    assert err < 0.12 and agree >= 0.985
