@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--uni", action="store_true", help="unidirectional GRU (class default) instead of the training default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", action="store_true", help="strong scaling: --batch is the GLOBAL batch, split evenly over the GPUs (default: weak, --batch per GPU)")
+    ap.add_argument("--nccl-ctas", type=int, default=int(os.environ.get("NSD_NCCL_CTAS", "0")),
+                    help="N > 1 GPUs: cap NCCL at this many CTAs (NCCL_MAX_CTAS) and keep as many SMs free of the persistent GEMMs during the backward; 0 = off")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
     ap.add_argument("--mode", default="train", choices=["train", "infer", "stream"],
                     help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32; "
@@ -245,6 +247,8 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if a.nccl_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(a.nccl_ctas)
         dist.init_process_group("nccl", device_id=dev)
     if a.strong:
         if a.batch % world:
@@ -259,7 +263,7 @@ def run_ours(a):
     torch.manual_seed(0)
     model = nsd.GRUDecoder(device="cuda", bidirectional=not a.uni, **MODEL_KW).to(dev)
     model.train()
-    gs = GradSync(world) if world > 1 else None
+    gs = GradSync(world, reserve_sms=a.nccl_ctas) if world > 1 else None
     opt, sched = nsd.make_optimizer(model, dict(lrStart=0.02, lrEnd=0.02, nBatch=10000, l2_decay=1e-5))
     if gs is not None:
         opt.grad_scale = gs.grad_scale

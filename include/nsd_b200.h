@@ -203,6 +203,11 @@ int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, 
                   void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream);
 
+/* Keep n_sms SMs free of the persistent tensor-core GEMM grids from now on (0 = use every SM).  New (no reference
+ * counterpart): while parallel.GradSync has a gradient bucket in flight, NCCL's CTAs run on the reserved SMs instead of
+ * displacing CTAs of a 148-wide persistent GEMM.  Host-side state, takes effect at the next nsd_gemm_bf16* call. */
+int nsd_set_gemm_sm_reserve(int n_sms);
+
 /* n small f32 vectors copied src[i] -> dst[i] (numel[i] elements) in one launch: packs the per-direction nn.GRU bias
  * vectors (model.py:50-57: bias_ih_l{k}[_reverse], bias_hh_l{k}[_reverse]) side by side for the two-direction launches. */
 int nsd_multi_copy_f32(int n_tensors, const void* const* src, void* const* dst, const int64_t* numel, void* stream);

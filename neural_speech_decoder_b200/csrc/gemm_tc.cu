@@ -16,6 +16,12 @@
 namespace nsd {
 namespace tc {
 
+// SMs the persistent GEMM grids may occupy: all of them, minus the reserve set with nsd_set_gemm_sm_reserve (data-parallel
+// training keeps a few SMs free for NCCL's CTAs while a gradient bucket is being all-reduced under the backward GEMMs, so
+// that neither kernel has to wait for the other's CTAs to leave)
+static int g_sm_reserve = 0;
+static int gemm_sms() { return std::max(2, sm_count() - g_sm_reserve); }
+
 constexpr int BM = 128;          // UMMA M (cta_group::1, all 128 TMEM lanes)
 constexpr int THREADS = 256;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int ACC_STAGES = 2;
@@ -562,7 +568,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc
         attr_set = true;
     }
     const int tiles = cdiv(M, BM) * cdiv(N, BN);
-    const int grid = std::min(tiles, sm_count());
+    const int grid = std::min(tiles, gemm_sms());
     kern<<<grid, THREADS, cfg::SMEM, s>>>(ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
@@ -579,7 +585,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
         attr_set = true;
     }
     const int items = cdiv(cdiv(M, BM), 2) * cdiv(N, cfg::BN) * nprob;     // 256 x BN tiles
-    const int grid = std::min(items, sm_count() / 2) * 2;
+    const int grid = std::min(items, gemm_sms() / 2) * 2;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = s;
     cudaLaunchAttribute attr[1];
@@ -593,7 +599,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 
 // tile width of the pair form: the one whose last round of clusters wastes less
 static int pair_tile_width(int M, int N, int nprob) {
-    const int clusters = std::max(1, sm_count() / 2);
+    const int clusters = std::max(1, gemm_sms() / 2);
     const long long mp = cdiv(cdiv(M, BM), 2);
     const long long c256 = cdivz((size_t)(mp * cdiv(N, 256) * nprob), (size_t)clusters) * 256;
     const long long c128 = cdivz((size_t)(mp * cdiv(N, 128) * nprob), (size_t)clusters) * 128;
@@ -628,6 +634,13 @@ static int dispatch_layout(bool a_mn, bool b_mn, const CUtensorMap& ta, const CU
     if (!a_mn && b_mn) return launch<BN, OutT, false, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
     if (a_mn && b_mn) return launch<BN, OutT, true, true>(ta, tb, C, ldc, bias, beta, M, N, K, s);
     return launch<BN, OutT, true, false>(ta, tb, C, ldc, bias, beta, M, N, K, s);
+}
+
+extern "C" int nsd_set_gemm_sm_reserve(int n_sms) {
+    using namespace nsd;
+    NSD_CHECK_ARG(n_sms >= 0 && n_sms < sm_count(), "set_gemm_sm_reserve: %d not in [0, %d)", n_sms, sm_count());
+    nsd::tc::g_sm_reserve = n_sms;
+    return NSD_OK;
 }
 
 extern "C" int nsd_gemm_bf16(int transa, int transb, int M, int N, int K, const void* A, int lda, const void* B, int ldb,

@@ -34,7 +34,7 @@ namespace rts {
 using namespace nsd::tc;
 
 constexpr int NG = 32;                  // batch rows per epilogue warpgroup pass (one TMEM column block)
-constexpr int CTRL_THREADS = 128;       // warp 0: zone polls + TMA, warp 1: MMA issue, warp 2: TMEM alloc, warp 3: idle
+constexpr int CTRL_THREADS = 128;       // warp 0: zone polls + TMA, warp 1: MMA issue, warps 2 / 3: publishers of warpgroups 0 / 1 (warp 2 also allocates TMEM)
 constexpr int WG_THREADS = 128;         // epilogue warpgroup
 constexpr int THREADS = CTRL_THREADS + 2 * WG_THREADS;
 constexpr int TMEM_COLS = 512;
@@ -93,6 +93,14 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
 __device__ __forceinline__ void red_release_add(unsigned int* p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
+// publish hand-off: the 128 epilogue threads of warpgroup w ARRIVE (no wait) once their state stores are issued; the warpgroup's
+// publisher warp (control warp 2 + w) syncs on the same barrier and performs the release fence + counter add.  The fence
+// (~0.7 us: it waits for the stores' L2 acknowledgements) then stalls an otherwise idle warp instead of warp 0 of the
+// warpgroup, which can go on to its deferred stores and -- with two chains per warpgroup -- to the other chain's exchange.
+// Two barrier ids alternate per warpgroup, so a thread can never arrive twice on a barrier whose phase is still open.
+constexpr int PUB_THREADS = WG_THREADS + 32;
+__device__ __forceinline__ void pub_arrive(int w, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(3 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
+__device__ __forceinline__ void pub_sync(int w, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(3 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
 __device__ __forceinline__ void wg_bar_sync(int w) { asm volatile("bar.sync %0, %1;" ::"r"(1 + w), "n"(WG_THREADS) : "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]: A = stationary weights, lane = row, two bf16 of consecutive k per 32-bit column
@@ -157,12 +165,12 @@ struct Smem {
     uint8_t* ring; uint8_t* inbox; uint8_t* outbox; float* self;
     uint64_t* full; uint64_t* empty;                               // [MAX_STAGES] each
     uint64_t* tmem_full;                                           // [2] one per chain in flight
-    uint64_t* inbox_bar;                                           // [8] one per message slot (x step parity in the LL kernels)
+    uint64_t* inbox_bar;                                           // [4] one per message slot
     uint32_t* tmem_slot;
     long long* trace;
     float* bsum;                                                   // BPTT: [2 warpgroups][32 values][128 threads] bias-gradient partial sums
 };
-constexpr int BAR_WORDS = 2 * MAX_STAGES + 2 + 8 + 2;             // uint64 slots in the barrier block
+constexpr int BAR_WORDS = 2 * MAX_STAGES + 2 + 4 + 2;             // uint64 slots in the barrier block
 __device__ __forceinline__ Smem carve(uint8_t* raw, int ring_bytes, int nslot, int msgs_bytes, int self_bytes) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     Smem s;
@@ -172,7 +180,7 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int ring_bytes, int nslot, i
     s.self = reinterpret_cast<float*>(s.outbox + nslot * msgs_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.self) + 2 * self_bytes);
     s.full = bars; s.empty = bars + MAX_STAGES; s.tmem_full = bars + 2 * MAX_STAGES; s.inbox_bar = bars + 2 * MAX_STAGES + 2;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 10);
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
     s.trace = reinterpret_cast<long long*>(bars + BAR_WORDS);
     s.bsum = reinterpret_cast<float*>(s.trace + (TRACE_STEPS + 1) * 8);
     return s;
@@ -238,6 +246,26 @@ __device__ __forceinline__ void load_a_row(uint32_t taddr_row, const __nv_bfloat
 //     once and issues the stage(s) as their empty barriers allow.
 //   warp 1: waits for each stage in order and issues its MMAs; a tcgen05.commit per stage frees it, one per item wakes the
 //     chain's epilogue.
+// Control warps 2 and 3: publisher of warpgroup w = warp - 2.  Walks the (chain pair, step, chain) items in the order the
+// warpgroup finalises them.
+template <int WPC>
+__device__ __forceinline__ void publisher_warp(const Smem& sm, const Common& c, int d, int my_zone, int w, int lane) {
+    const int npair = (c.nchain + 1) / 2;
+    uint32_t n = 0;
+    for (int pr = 0; pr < npair; ++pr)
+        for (int s = 0; s < c.Tp; ++s)
+            for (int k = 0; k < WPC; ++k) {
+                const int chain = 2 * pr + (WPC == 1 ? w : k);
+                if (chain >= c.nchain) continue;
+                pub_sync(w, n++);
+                if (lane == 0) {
+                    publish(c, zone_counter(c, d, chain, my_zone));
+                    if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
+                }
+                __syncwarp();
+            }
+}
+
 template <int NT, int WPC>
 __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, const CUtensorMap* tmB3, int warp, int lane, uint32_t tmem_base,
                                               const Common& c, int d, int my_zone, int k_lo, int k_hi, int nslab, int nbox,
@@ -276,8 +304,12 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                     const int row = t_src * c.B + chain * NROW + c.row_off;
                     for (int sub = 0; sub < nsub; ++sub, ++seq) {
                         const uint32_t stage = seq & 1u, use = seq >> 1;
-                        if (lane == 0) mbar_wait(&sm.empty[stage], (use & 1u) ^ 1u);
-                        __syncwarp();
+                        if (nsub > 1) {
+                            // a step's operand spans both stages: wait until the MMAs that read this stage last have completed.  (With
+                            // one stage per item the own-cluster wait above already implies it: the chain's previous step is finished.)
+                            if (lane == 0) mbar_wait(&sm.empty[stage], (use & 1u) ^ 1u);
+                            __syncwarp();
+                        }
                         uint8_t* dst = sm.ring + (size_t)stage * bps * BOXB;
                         const int nb = min(bps, nbox - sub * bps);              // boxes in this stage
                         if (nbox == 0) {
@@ -327,10 +359,10 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                                         if (ns > 3) umma_ts_bf16(dcol, acol + 24u, bdesc + 6u, idesc, 1u);
                                     }
                                 }
-                                umma_commit(&sm.empty[stage]);
+                                if (nsub > 1) umma_commit(&sm.empty[stage]);
                                 if (sub == nsub - 1) umma_commit(&sm.tmem_full[ch]);
                             } else {
-                                mbar_arrive(&sm.empty[stage]);
+                                if (nsub > 1) mbar_arrive(&sm.empty[stage]);
                                 if (sub == nsub - 1) mbar_arrive(&sm.tmem_full[ch]);
                             }
                         }
@@ -340,6 +372,8 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                 }
             }
         }
+    } else {
+        publisher_warp<WPC>(sm, c, d, my_zone, warp - 2, lane);
     }
 }
 
@@ -428,7 +462,6 @@ struct FwdParams {
     float* r; float* z; float* n; float* hn;         // [D][Tp*B][H] or null
     const float* h0;                                 // [B, ldh] initial state (fp32) or null; its bf16 copy = first B rows of hseq_bf
     __nv_bfloat16* hdrop; uint32_t drop_thresh; float inv_keep; uint64_t seed;   // fused inter-layer dropout output (or null)
-    uint2* ll; int bpad;                  // LL form: [D][2][bpad rows][H/2] words {2 x bf16 state, step tag}; bpad = nchain * 32 * WPC
 };
 
 template <int WPC>
@@ -477,7 +510,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         float bh[3][4];
 #pragma unroll
         for (int g = 0; g < 3; ++g) ld4g(p.b_hh + d * 3 * H + g * H + ub, bh[g]);
-        uint32_t it[WPC];
+        uint32_t it[WPC], npub = 0;
 #pragma unroll
         for (int k = 0; k < WPC; ++k) it[k] = 0;
         const int npair = (c.nchain + 1) / 2;
@@ -555,11 +588,8 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                         st4_bf16(p.hseq_bf + (m + c.row_off) * p.ldh + d * H + ub, k_h[k]);
                     }
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
-                    wg_bar_sync(w);                              // (the consumer fences generic->async proxy after its acquire)
-                    if (te == 0) {
-                        publish(c, zone_counter(c, d, chain, my_zone));
-                        if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
-                    }
+                    pub_arrive(w, npub++);                       // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
+                    if (WPC > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
                     if (row_ok) {                                // off the critical path: nobody else reads these during the launch
                         st4(p.hseq + m * p.ldh + d * H + ub, k_h[k]);
                         if (p.r) {
@@ -577,325 +607,6 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                             st4_bf16(p.hdrop + el, o);
                         }
                     }
-                }
-            }
-        }
-    }
-    teardown(warp, tmem_base, c, sm);
-}
-
-// ----------------------------------------------------------------------------------------------- forward, LL exchange
-// Same decomposition (4-CTA clusters, weights stationary in TMEM, DSMEM partial-sum exchange), but the recurrent state
-// travels between clusters as FLAG-IN-DATA words -- the NCCL "LL" protocol: every 8-byte word of the exchange buffer is
-// {two bf16 state values, 32-bit step tag}, written with one 16-byte volatile store per (row, 4 units) and read with
-// 16-byte volatile loads; a word whose tag equals the consuming step is valid.  This removes, per step, the release
-// fence + counter add of the publish (0.76 us of 4.4 measured), the acquire polls, the proxy fence and the TMA round
-// trip: the state is in the consumer's hands one L2 write + one L2 read after it was computed.  The epilogue warpgroup
-// of a chain is also its loader (it is idle between publishing step s and the MMAs of step s+1): 16 threads first poll
-// one sentinel chunk of each producing CTA (so that waiting costs 512 B per round, not the 32 KB that made a first
-// attempt L2-bound), then all 128 threads pull the chain's K share (2x the bf16 bytes) straight into the 128B-swizzled
-// UMMA operand layout and arrive on the MMA warp's barrier.  The buffer has two step-parity halves: producing step s+1
-// anywhere needs, through the cluster exchange, every CTA's step-s output, hence every CTA has finished reading step s-1.
-// In/outboxes are double-buffered by step parity for the same reason (a peer can run at most one step ahead of me).
-__device__ __forceinline__ uint4 ld_volatile_16(const void* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_16(void* p, uint4 v) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// Load the chunk list [q0, q0 + n * WG_THREADS) (stride WG_THREADS) of one chain half: chunk q = (row q / ncr, chunk-in-row q % ncr),
-// 32 bytes = 4 LL words = 8 consecutive k; valid words go, tags stripped, into the swizzled operand tile.
-template <int NCH>
-__device__ __forceinline__ void ll_pull(const uint2* __restrict__ src_rows, int ld_words, uint32_t tag, int q0, int total, int ncr,
-                                        uint8_t* tile, int row0, int boxb) {
-    uint4 a[NCH], b[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        const int q = q0 + i * WG_THREADS;
-        if (q < total) {
-            const int r = q / ncr, cr = q - r * ncr;
-            const uint2* addr = src_rows + (size_t)r * ld_words + 4 * cr;
-            a[i] = ld_volatile_16(addr); b[i] = ld_volatile_16(addr + 2);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        const int q = q0 + i * WG_THREADS;
-        if (q >= total) continue;
-        const int r = q / ncr, cr = q - r * ncr;
-        if (!(a[i].y == tag && a[i].w == tag && b[i].y == tag && b[i].w == tag)) {
-            const uint2* addr = src_rows + (size_t)r * ld_words + 4 * cr;
-            const long long t0 = clock64();
-            unsigned int spins = 0;
-            do {
-                a[i] = ld_volatile_16(addr); b[i] = ld_volatile_16(addr + 2);
-                if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
-                    printf("nsd gru_ll: state word timeout (block %d thread %d tag %u have %u)\n", blockIdx.x, threadIdx.x, tag, a[i].y);
-                    __trap();
-                }
-            } while (!(a[i].y == tag && a[i].w == tag && b[i].y == tag && b[i].w == tag));
-        }
-        const int rr = row0 + r;
-        uint8_t* dst = tile + (size_t)(cr >> 3) * boxb + (rr >> 3) * 1024 + (rr & 7) * 128 + (((cr & 7) ^ (rr & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(a[i].x, a[i].z, b[i].x, b[i].z);
-    }
-}
-
-template <int WPC>
-__global__ void __launch_bounds__(THREADS, 1)
-gru_fwd_ll_kernel(const FwdParams p) {
-    constexpr int CS = 4, NT = 2, NGATE = 3, U = 16, NROW = NG * WPC, NSLOT = 2 * WPC;
-    constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
-    constexpr int BOXB = NROW * 128;
-    constexpr uint32_t A_COL0 = 2 * NT * NROW;
-    extern __shared__ uint8_t smem_raw[];
-    const Common& c = p.c;
-    const int H = c.H, B = c.B;
-    const int me = (int)cluster_rank();
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int d = blockIdx.x / c.nper;
-    const int my_zone = (blockIdx.x - d * c.nper) / CS;
-    const int uc0 = my_zone * (CS * U);                                  // first unit of the cluster
-    const bool rev = (d == 1) || (c.reverse0 != 0);
-    const int k_lo = min(me * c.kper, c.ktot), k_hi = min(k_lo + c.kper, c.ktot);
-    const int nslab = (k_hi - k_lo) / UMMA_K, nbox = (k_hi - k_lo + BK - 1) / BK;
-    const int kc = c.kper / 2;
-    const int npair = (c.nchain + 1) / 2;
-    // shared memory: [operand tiles: 2 chains x bps boxes][inbox: NSLOT x 2 parities x MSGS][outbox: same][self: 2][barriers]
-    const Smem sm = carve(smem_raw, 2 * c.bps * BOXB, 2 * NSLOT, MSGS, SELF);
-    uint64_t* inbox_bar = sm.inbox_bar;                                  // [NSLOT][2 parities] (8 slots reserved)
-    if (c.trace != nullptr)
-        for (int i = threadIdx.x; i < (TRACE_STEPS + 1) * 8; i += blockDim.x) sm.trace[i] = 0;
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.full[i], WG_THREADS * WPC); mbar_init(&sm.empty[i], 1); mbar_init(&sm.tmem_full[i], 1); }
-        for (int i = 0; i < 8; ++i) mbar_init(&inbox_bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    __syncwarp();
-    cluster_sync_all();                 // every CTA's barriers exist before any peer pushes into its inbox
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *sm.tmem_slot;
-
-    if (warp >= 4) {
-        // stationary weights: tile t = units uc0 + 32t .. +32, lanes [r | z | n | unused] x 32 units, my quarter of K
-        const int e = warp - 4, w4 = e & 3, t = e >> 2;
-        const int unit = uc0 + 32 * t + lane;
-        const __nv_bfloat16* row = (w4 < 3 && unit < H) ? p.w + (size_t)(d * 3 * H + w4 * H + unit) * H : nullptr;
-        load_a_row(tmem_base + ((uint32_t)(w4 * 32) << 16) + A_COL0 + (uint32_t)(t * kc), row, k_lo, k_hi, kc, 0, 1);
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-
-    if (warp == 1) {
-        // MMA warp: item (s, ch) starts when the chain's loader warpgroup(s) have filled its operand tile
-        constexpr uint32_t idesc = make_idesc_bf16(128, NROW);
-        uint32_t n[2] = {0u, 0u};
-        for (int pr = 0; pr < npair; ++pr) {
-            if (pr > 0) cluster_sync_all();
-            for (int s = c.s0; s < c.Tp; ++s) {
-                for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch) {
-                    mbar_wait(&sm.full[ch], n[ch] & 1);
-                    ++n[ch];
-                    if (lane == 0 && 2 * pr + ch == 0) stamp(c, sm.trace, s, 2);
-                    tcgen05_fence_after();
-                    if (elect_one()) {
-                        if (nslab > 0) {
-#pragma unroll
-                            for (int t = 0; t < NT; ++t) {
-                                const uint32_t dcol = tmem_base + (uint32_t)((ch * NT + t) * NROW);
-                                uint32_t acol = tmem_base + A_COL0 + (uint32_t)(t * kc);
-                                uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sm.ring + (size_t)ch * c.bps * BOXB));
-                                for (int sl = 0; sl < nslab; sl += 4, acol += 32u, bdesc += (uint64_t)(BOXB >> 4)) {   // one box = 4 slabs
-                                    const int ns = nslab - sl;
-                                    umma_ts_bf16(dcol, acol, bdesc, idesc, sl != 0);
-                                    if (ns > 1) umma_ts_bf16(dcol, acol + 8u, bdesc + 2u, idesc, 1u);
-                                    if (ns > 2) umma_ts_bf16(dcol, acol + 16u, bdesc + 4u, idesc, 1u);
-                                    if (ns > 3) umma_ts_bf16(dcol, acol + 24u, bdesc + 6u, idesc, 1u);
-                                }
-                            }
-                            umma_commit(&sm.tmem_full[ch]);
-                        } else {
-                            mbar_arrive(&sm.tmem_full[ch]);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0 && 2 * pr + ch == 0) stamp(c, sm.trace, s, 3);
-                }
-            }
-        }
-    } else if (warp < 4) {
-        for (int pr = 1; pr < npair; ++pr) cluster_sync_all();      // idle warps: the barrier counts every thread of the cluster
-    } else {
-        // ------------------------------------------------------------ loader + epilogue warpgroup w
-        const int e = warp - 4, w4 = e & 3, w = e >> 2, te = w4 * 32 + lane;
-        const int bl = te >> 2, uo4 = te & 3;
-        const int ub = uc0 + me * U + 4 * uo4;             // first of this thread's 4 units
-        const bool unit_ok = ub < H;                       // H % 64 == 0: a CTA's 16 units are all inside or all outside
-        float* self = sm.self + w * (SELF / 4);
-        const int hw = H / 2;                              // LL words per row
-        const int ncr = (k_hi - k_lo) / 8;                 // 32-byte chunks per row of my K share
-        const int row0 = WPC == 1 ? 0 : w * NG;            // my rows inside the chain's operand tile
-        float bh[3][4];
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            if (unit_ok) ld4g(p.b_hh + d * 3 * H + g * H + ub, bh[g]);
-            else { bh[g][0] = bh[g][1] = bh[g][2] = bh[g][3] = 0.f; }
-        }
-        uint32_t it[WPC], itp[WPC][2];                     // uses of the chain's accumulator barrier / of its two inbox barriers
-#pragma unroll
-        for (int k = 0; k < WPC; ++k) it[k] = itp[k][0] = itp[k][1] = 0;
-        for (int pr = 0; pr < npair; ++pr) {
-            // chain pairs are separated by a cluster barrier: a peer must not start the next pair's exchange (same message
-            // buffers, unrelated step parity) while this CTA still gathers the last step of the current pair
-            if (pr > 0) cluster_sync_all();
-            float k_h[WPC][4];                             // h_{t-1} of this thread's (row, 4 units) per chain, fp32, in registers
-#pragma unroll
-            for (int k = 0; k < WPC; ++k) {
-                const int ch = WPC == 1 ? w : k;
-                const int chain = 2 * pr + ch;
-                const int b = chain * NROW + row0 + bl;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) k_h[k][i] = 0.f;
-                if (p.h0 != nullptr && chain < c.nchain) {
-                    if (b < B && unit_ok) ld4g(p.h0 + (size_t)b * p.ldh + d * H + ub, k_h[k]);
-                    // the initial state is the "output of step -1": consumed at step 0 (tag 1, parity 0)
-                    if (unit_ok)
-                        st_volatile_16(p.ll + ((size_t)(d * 2 + 0) * p.bpad + b) * hw + (ub >> 1),
-                                       make_uint4(pack_bf16(k_h[k][0], k_h[k][1]), 1u, pack_bf16(k_h[k][2], k_h[k][3]), 1u));
-                }
-            }
-            for (int s = 0; s < c.Tp; ++s) {
-                const int t = rev ? (c.Tp - 1 - s) : s;
-                // ---- loader: pull h_{s-1} of my chain(s) into the operand tile(s) and release the MMA warp
-                if (s >= c.s0) {
-#pragma unroll
-                    for (int k = 0; k < WPC; ++k) {
-                        const int ch = WPC == 1 ? w : k;
-                        const int chain = 2 * pr + ch;
-                        if (chain >= c.nchain) continue;
-                        if (nslab > 0) {
-                            const uint32_t tag = (uint32_t)(s + 1);
-                            const uint2* src = p.ll + ((size_t)(d * 2 + (s & 1)) * p.bpad + chain * NROW + row0) * hw + (k_lo >> 1);
-                            // sentinels: one chunk of each producing CTA (16 units = 2 chunks), rows spread over the producers' warps
-                            if (te < nslab) {
-                                const uint2* sp = src + (size_t)((te * 5) & (NG - 1)) * hw + 8 * te;
-                                const long long t0 = clock64();
-                                unsigned int spins = 0;
-                                for (;;) {
-                                    const uint4 a = ld_volatile_16(sp), b2 = ld_volatile_16(sp + 2);
-                                    if (a.y == tag && a.w == tag && b2.y == tag && b2.w == tag) break;
-                                    if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > SPIN_CYCLES) {
-                                        printf("nsd gru_ll: sentinel timeout (block %d thread %d step %d)\n", blockIdx.x, threadIdx.x, s);
-                                        __trap();
-                                    }
-                                }
-                            }
-                            wg_bar_sync(w);
-                            if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 0);
-                            uint8_t* tile = sm.ring + (size_t)ch * c.bps * BOXB;
-                            const int total = NG * ncr;
-                            constexpr int NCH = WPC == 1 ? 8 : 4;          // chunks in flight per thread (64 / 32 registers)
-                            for (int q0 = te; q0 < total; q0 += NCH * WG_THREADS) ll_pull<NCH>(src, hw, tag, q0, total, ncr, tile, row0, BOXB);
-                            fence_proxy_async_smem();            // generic-proxy tile writes -> tcgen05.mma (async proxy) reads
-                            if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 1);
-                        }
-                        mbar_arrive(&sm.full[ch]);
-                    }
-                }
-                // ---- epilogue
-#pragma unroll
-                for (int k = 0; k < WPC; ++k) {
-                    const int ch = WPC == 1 ? w : k;
-                    const int chain = 2 * pr + ch;
-                    if (chain >= c.nchain) continue;
-                    const int slot = (WPC == 1 ? w : 2 * w + k) * 2 + (s & 1);      // message buffers alternate with the step parity
-                    uint8_t* inbox = sm.inbox + slot * MSGS;
-                    uint8_t* outbox = sm.outbox + slot * MSGS;
-                    const int b = chain * NROW + row0 + bl;
-                    const bool row_ok = b < B && unit_ok;
-                    const size_t m = (size_t)t * B + b;
-                    float gi[3][4];
-                    if (row_ok) {
-#pragma unroll
-                        for (int g = 0; g < 3; ++g) {
-                            ld4g(p.gi + m * p.ldgi + d * 3 * H + g * H + ub, gi[g]);
-                            if (g < 2) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) gi[g][i] += bh[g][i];
-                            }
-                        }
-                    }
-                    float acc[3][4];
-#pragma unroll
-                    for (int g = 0; g < 3; ++g)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
-                    if (s >= c.s0) {
-                        if (te == 0) mbar_expect_tx(&inbox_bar[slot], (uint32_t)MSGS);
-                        mbar_wait(&sm.tmem_full[ch], it[k] & 1);
-                        tcgen05_fence_after();
-                        if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 4);
-                        if (w4 < 3) {
-#pragma unroll
-                            for (int t2 = 0; t2 < NT; ++t2)
-                                stage_row<CS, NGATE, U>(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)((ch * NT + t2) * NROW + row0),
-                                                        nslab > 0, w4, 32 * t2 + lane, me, self, outbox);
-                        }
-                        tcgen05_fence_before();
-                        fence_proxy_async_smem();
-                        wg_bar_sync(w);
-                        if (te < CS - 1) send_message<CS, NGATE, U>(outbox, inbox, &inbox_bar[slot], me, te);
-                        mbar_wait_cluster(&inbox_bar[slot], itp[k][s & 1] & 1);
-                        ++itp[k][s & 1];
-                        if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 5);
-#pragma unroll
-                        for (int g = 0; g < 3; ++g) gather<CS, NGATE, U>(self, inbox, g, 4 * uo4, bl, acc[g]);
-                        ++it[k];
-                    }
-                    float rr[4], zz[4], nn[4], gn[4];
-                    if (row_ok) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            rr[i] = fast_sigmoid(gi[0][i] + acc[0][i]);
-                            zz[i] = fast_sigmoid(gi[1][i] + acc[1][i]);
-                            gn[i] = acc[2][i] + bh[2][i];
-                            nn[i] = fast_tanh(fmaf(rr[i], gn[i], gi[2][i]));
-                            k_h[k][i] = fmaf(zz[i], k_h[k][i] - nn[i], nn[i]);        // (1-z)*n + z*h_prev
-                        }
-                    }
-                    // publish: the state with the tag of the step that consumes it (rows past B carry zeros: consumers pull whole tiles)
-                    if (unit_ok && s + 1 < c.Tp)
-                        st_volatile_16(p.ll + ((size_t)(d * 2 + ((s + 1) & 1)) * p.bpad + b) * hw + (ub >> 1),
-                                       make_uint4(pack_bf16(k_h[k][0], k_h[k][1]), (uint32_t)(s + 2), pack_bf16(k_h[k][2], k_h[k][3]), (uint32_t)(s + 2)));
-                    if (te == 0 && chain == 0 && w == 0) { stamp(c, sm.trace, s, 6); stamp(c, sm.trace, s, 7); }
-                    if (row_ok) {                                // off the critical path: nobody else reads these during the launch
-                        st4_bf16(p.hseq_bf + (m + c.row_off) * p.ldh + d * H + ub, k_h[k]);
-                        st4(p.hseq + m * p.ldh + d * H + ub, k_h[k]);
-                        if (p.r) {
-                            const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
-                            st4(p.r + o, rr); st4(p.z + o, zz); st4(p.n + o, nn); st4(p.hn + o, gn);
-                        }
-                        if (p.hdrop) {                           // same mask and rounding as nsd_dropout on the bf16 [Tp*B, ldh] tensor
-                            const size_t el = m * p.ldh + d * H + ub;
-                            const uint4 bits = dropout_bits(el >> 2, p.seed);
-                            const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
-                            float o[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                o[i] = bw[i] >= p.drop_thresh ? __bfloat162float(__float2bfloat16_rn(k_h[k][i])) * p.inv_keep : 0.f;
-                            st4_bf16(p.hdrop + el, o);
-                        }
-                    }
-                    wg_bar_sync(w);      // gather(self / inbox) of every thread is done before the next stage_row overwrites `self`
                 }
             }
         }
@@ -960,7 +671,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         float* bsum = sm.bsum + (size_t)w * 16 * NP * WG_THREADS + te;
         if (p.db_ih)
             for (int v = 0; v < 16 * NP; ++v) bsum[v * WG_THREADS] = 0.f;
-        uint32_t it[WPC];
+        uint32_t it[WPC], npub = 0;
 #pragma unroll
         for (int k = 0; k < WPC; ++k) it[k] = 0;
         const int npair = (c.nchain + 1) / 2;
@@ -1049,11 +760,8 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                         }
                     }
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
-                    wg_bar_sync(w);                              // (the consumer fences generic->async proxy after its acquire)
-                    if (te == 0) {
-                        publish(c, zone_counter(c, d, chain, my_zone));
-                        if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
-                    }
+                    pub_arrive(w, npub++);                       // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
+                    if (WPC > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {               // off the critical path
                         const int ub = ub0 + 16 * q;
@@ -1093,8 +801,8 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 }
 
 // ---------------------------------------------------------------- host side
-template <typename Kern, typename... Args>
-static int launch_cluster_coop_impl(Kern kern, int grid, int cs, size_t smem, cudaStream_t s, const Args&... args) {
+template <typename Kern, typename P>
+static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1, const P& p, cudaStream_t s) {
     NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1110,18 +818,9 @@ static int launch_cluster_coop_impl(Kern kern, int grid, int cs, size_t smem, cu
     int max_clusters = 0;
     NSD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters * cs < grid) { set_error("gru_ts: %d CTAs in clusters of %d cannot be co-resident (max %d clusters)", grid, cs, max_clusters); return NSD_ERR_INVALID; }
-    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    NSD_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, p));
     count_launch(1);
     return NSD_OK;
-}
-
-template <typename Kern, typename P>
-static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const CUtensorMap& m0, const CUtensorMap& m1, const P& p, cudaStream_t s) {
-    return launch_cluster_coop_impl(kern, grid, cs, smem, s, m0, m1, p);
-}
-template <typename Kern, typename P>
-static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const P& p, cudaStream_t s) {
-    return launch_cluster_coop_impl(kern, grid, cs, smem, s, p);
 }
 
 // Debug aid: NSD_GRU_TRACE=1 prints block 0's per-step event times of batch chain 0 (SM cycles relative to the step's barrier pass).
@@ -1190,13 +889,8 @@ static int check_shape(const char* who, int Tp, int B, int H, int D, int cs, int
 
 extern "C" {
 
-// [zone step counters | LL state-exchange buffer [D][2][round_up(B, 64)][H/2] x 8 B]; zeroed by every launch
-static size_t counters_bytes(int B, int H, int D) {
-    const size_t n = 256 + (size_t)D * nsd::rts::n_chains(B, 1) * nsd::cdiv(H, 64) * nsd::rts::CNT_STRIDE * sizeof(unsigned int);
-    return (n + 255) / 256 * 256;
-}
 size_t nsd_gru_tc_workspace(int B, int H, int D) {
-    return counters_bytes(B, H, D) + (size_t)D * 2 * ((B + 63) / 64 * 64) * (H / 2) * 8;
+    return 256 + (size_t)D * nsd::rts::n_chains(B, 1) * nsd::cdiv(H, 64) * nsd::rts::CNT_STRIDE * sizeof(unsigned int);
 }
 
 int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const float* b_hh, int Tp, int B, int H, int D,
@@ -1232,19 +926,9 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.hdrop = reinterpret_cast<__nv_bfloat16*>(hdrop_bf16); p.drop_thresh = dropout_threshold(p_drop); p.inv_keep = 1.0f / (1.0f - p_drop); p.seed = seed;
-    static const bool use_ll = [] { const char* e = getenv("NSD_GRU_LL"); return !(e && e[0] == '0'); }();     // NSD_GRU_LL=0: counter + TMA form
-    if (use_ll) {
-        p.ll = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + counters_bytes(B, H, D));
-        p.bpad = p.c.nchain * NG * wpc;
-        const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, 4 * wpc, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
-        rc = wpc == 1 ? launch_cluster_coop(gru_fwd_ll_kernel<1>, D * nper, CS, smem, p, s)
-                      : launch_cluster_coop(gru_fwd_ll_kernel<2>, D * nper, CS, smem, p, s);
-    } else {
-        p.ll = nullptr; p.bpad = 0;
-        const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, 2 * wpc, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
-        rc = wpc == 1 ? launch_cluster_coop(gru_fwd_ts_kernel<1>, D * nper, CS, smem, tmH, tmH3, p, s)
-                      : launch_cluster_coop(gru_fwd_ts_kernel<2>, D * nper, CS, smem, tmH, tmH3, p, s);
-    }
+    const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, 2 * wpc, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
+    rc = wpc == 1 ? launch_cluster_coop(gru_fwd_ts_kernel<1>, D * nper, CS, smem, tmH, tmH3, p, s)
+                  : launch_cluster_coop(gru_fwd_ts_kernel<2>, D * nper, CS, smem, tmH, tmH3, p, s);
     trace_end("gru_fwd_bf16", tr, s, D * nper);
     return rc;
 }
@@ -1263,7 +947,7 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
     NSD_CHECK_ARG((lddh % 4) == 0 && (ldh % 4) == 0 && (ldg % 8) == 0, "gru_bwd_bf16: leading dimensions must be multiples of 4 (f32) / 8 (bf16)");
     if (workspace_bytes < nsd_gru_tc_workspace(B, H, D)) { set_error("gru_bwd_bf16: workspace too small"); return NSD_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
-    NSD_CUDA(cudaMemsetAsync(workspace, 0, counters_bytes(B, H, D), s));
+    NSD_CUDA(cudaMemsetAsync(workspace, 0, nsd_gru_tc_workspace(B, H, D), s));
     const int wpc = wg_per_chain(B);
     CUtensorMap tmG;
     rc = make_bf16_map(&tmG, dgh_bf16, (long long)Tp * B, D * 3 * H, ldg, NG * wpc);

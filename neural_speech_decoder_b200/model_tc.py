@@ -180,6 +180,12 @@ def decoder_backward_tc(ctx, dlogits):
             else:
                 ops.gemm(True, False, 3 * H, H, Mh, dgh, D * 3 * H, hseq_bf, D * H, v_whh, H,
                          a_off=offs[0][0], b_off=offs[0][1], c_off=offs[0][2])
+        # the layer's bucket is final once its wgrads are enqueued.  With SMs reserved for NCCL (GradSync.reserve_sms) the
+        # all-reduce starts now and runs under the dgrad GEMM below; without a reserve NCCL's CTAs would displace CTAs of the
+        # 148-wide persistent GEMM, so the bucket is released after it (measured: no gain at 8 GPUs)
+        early = gs is not None and getattr(gs, "reserve_sms", 0) > 0
+        if early:
+            gs.bucket_ready(v_wih._base)
         dinp = None
         if l > 0 or day_w.requires_grad:
             dinp = torch.empty((M, in_l), device=dev, dtype=torch.float32 if l > 0 else torch.bfloat16)
@@ -188,7 +194,7 @@ def decoder_backward_tc(ctx, dlogits):
             base = (l * D + d) * 4
             ggru[base:base + 4] = [v_wih[d * 3 * H:(d + 1) * 3 * H], v_whh[d * 3 * H:(d + 1) * 3 * H],
                                    v_bih[d * 3 * H:(d + 1) * 3 * H], v_bhh[d * 3 * H:(d + 1) * 3 * H]]
-        if gs is not None:
+        if gs is not None and not early:
             gs.bucket_ready(v_wih._base)
         ctx.layers[l] = None
         dh = dinp

@@ -16,11 +16,14 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, world_size: Optional[int] = None, group=None):
+    def __init__(self, world_size: Optional[int] = None, group=None, reserve_sms: int = 0):
+        """``reserve_sms``: SMs the persistent GEMMs leave to NCCL between ``begin()`` and ``finish()`` (pair it with
+        ``NCCL_MAX_CTAS=<reserve_sms>`` in the environment before the process group is created); 0 = share all SMs."""
         self.group = group
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.handles: List = []
         self.bytes = 0
+        self.reserve_sms = int(reserve_sms) if self.world > 1 else 0
 
     @property
     def grad_scale(self) -> float:
@@ -28,6 +31,9 @@ class GradSync:
 
     def begin(self) -> None:
         self.handles, self.bytes = [], 0
+        if self.reserve_sms:
+            from ._lib import call
+            call("nsd_set_gemm_sm_reserve", self.reserve_sms)
 
     def bucket_ready(self, flat: torch.Tensor) -> None:
         """Called by the backward with a flat buffer whose gradients are final.  The collective is enqueued on
@@ -41,3 +47,6 @@ class GradSync:
         for h in self.handles:
             h.wait()                      # current stream waits for the collective; no host block on NCCL
         self.handles = []
+        if self.reserve_sms:
+            from ._lib import call
+            call("nsd_set_gemm_sm_reserve", 0)
