@@ -203,6 +203,19 @@ int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, 
                   void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream);
 
+/* Streaming inference step for B <= 8 (new: the reference's forward has no state API, model.py:104-119 always starts from
+ * h0 = 0 and drops h_n): one cooperative launch advances the whole unidirectional GRU stack by ONE output frame --
+ * per layer l: gi = x_l W_ih^T + b_ih, gh = bf16(h_l) W_hh^T + b_hh, gates r,z,n, h_l <- (1-z) n + z h_l (model.py:50-57, 119),
+ * then logits = h_{L-1} fc_w^T + fc_b (model.py:122) and ids[b] = argmax_c logits[b,c] (ties -> lowest index, trainer:314).
+ *   x0_bf16 [B, ldx >= F0] bf16 patch rows of the new frame; w_ih/w_hh/b_ih/b_hh: HOST arrays of L device pointers
+ *   (bf16 [3H,in_l] / bf16 [3H,H] / f32 [3H] / f32 [3H], gate rows r|z|n); h f32 [L][B][H] carried state, updated in
+ *   place; logits f32 [B,C]; ids i32 [B] or NULL.  H and F0 multiples of 256, L <= 8. */
+size_t nsd_gru_stream_step_workspace(int B, int H, int L);
+int nsd_gru_stream_step(const void* x0_bf16, int ldx, int B, int F0, int H, int L, int C, const void* const* w_ih_bf16,
+                        const void* const* w_hh_bf16, const void* const* b_ih, const void* const* b_hh, float* h,
+                        const void* fc_w_bf16, const float* fc_b, float* logits, int* ids, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* Keep n_sms SMs free of the persistent tensor-core GEMM grids from now on (0 = use every SM).  New (no reference
  * counterpart): while parallel.GradSync has a gradient bucket in flight, NCCL's CTAs run on the reserved SMs instead of
  * displacing CTAs of a 148-wide persistent GEMM.  Host-side state, takes effect at the next nsd_gemm_bf16* call. */

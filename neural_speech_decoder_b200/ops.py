@@ -228,6 +228,21 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
          float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), stream())
 
 
+def gru_stream_step(x0_bf16, w_ih_bf, w_hh_bf, b_ih, b_hh, h, fc_w_bf, fc_b, logits, ids, ws):
+    """One output frame of the whole unidirectional stack for B <= 8 in one launch (nsd_gru_stream_step): ``x0_bf16`` [B,F0]
+    bf16 (row stride free), per-layer lists of bf16 weights / f32 biases, ``h`` f32 [L,B,H] updated in place, ``logits`` f32
+    [B,C] and ``ids`` i32 [B] written.  ``ws`` = uint8 workspace of nsd_gru_stream_step_workspace bytes."""
+    import ctypes as C
+    L, B, H = h.shape
+    F0 = x0_bf16.shape[1]
+    assert x0_bf16.dtype == torch.bfloat16 and x0_bf16.stride(1) == 1 and h.dtype == torch.float32 and h.is_contiguous()
+    tab = lambda ts: (C.c_void_p * L)(*[t.data_ptr() for t in ts])
+    for l in range(L):
+        assert w_ih_bf[l].is_contiguous() and w_hh_bf[l].is_contiguous() and b_ih[l].is_contiguous() and b_hh[l].is_contiguous()
+    call("nsd_gru_stream_step", ptr(x0_bf16), x0_bf16.stride(0), B, F0, H, L, fc_w_bf.shape[0], tab(w_ih_bf), tab(w_hh_bf), tab(b_ih),
+         tab(b_hh), ptr(h), ptr(fc_w_bf), ptr(fc_b), ptr(logits), ptr(ids), ptr(ws), ws.numel(), stream())
+
+
 def multi_copy(srcs, dsts):
     """Copy the f32 tensors ``srcs[i]`` into the equally sized contiguous views ``dsts[i]`` in one launch."""
     import ctypes as C

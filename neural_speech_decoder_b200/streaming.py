@@ -1,9 +1,15 @@
 """Stateful streaming inference for the unidirectional GRUDecoder (BASELINE configs[3]).
 
 The reference has no streaming API: ``forward`` always starts from h0 = 0 and drops the final state
-(model.py:104-119).  ``StreamingDecoder`` feeds the SAME kernels incrementally and reproduces the offline logits
-bit for bit: it carries the fp32 hidden state of every layer between calls and keeps the raw bins a future frame still
-needs.  Frame j covers bins [4j, 4j+32) (kernel 32 / stride 4, model.py:37-39) of the smoothed signal, and the 20-tap
+(model.py:104-119).  ``StreamingDecoder`` carries the fp32 hidden state of every layer between calls and keeps the raw
+bins a future frame still needs.  Two execution forms:
+  * exact (any batch, any chunking): the SAME time-batched kernels fed incrementally; logits bit-identical to the offline
+    forward;
+  * fast (batch <= 8, steady pushes of one stride = one new frame): K1 on the 54-bin window + ONE launch of
+    ``nsd_gru_stream_step`` for the whole 5-layer stack, logits and greedy id, replayed as a captured CUDA graph, so a push
+    costs one graph launch instead of ~15 enqueued calls; the 107 MB of bf16 weights are streamed once per push and stay
+    resident in the 126 MB L2 between pushes.  Same arithmetic up to fp32 summation order (checked against the
+    reference-operator oracle with carried state, tests/test_gpu_streaming.py).  Frame j covers bins [4j, 4j+32) (kernel 32 / stride 4, model.py:37-39) of the smoothed signal, and the 20-tap
 Gaussian is padded 9 left / 10 right (augmentations.py:91), so frame j can be emitted once bin 4j+41 has arrived: a
 fixed look-ahead of 10 bins (200 ms).  ``finish()`` flushes the frames the offline model would still produce by zero
 padding past the end of the utterance, exactly as the offline smoothing does.
@@ -14,7 +20,7 @@ from typing import List, Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import NsdError
 
 
@@ -34,7 +40,7 @@ def window_for(j0: int, stride_len: int, halo: int):
 
 
 class StreamingDecoder:
-    def __init__(self, model, batch_size: int, dayIdx: torch.Tensor):
+    def __init__(self, model, batch_size: int, dayIdx: torch.Tensor, fast: Optional[bool] = None, use_graph: bool = True):
         if model.bidirectional:
             raise NsdError("streaming needs the unidirectional GRUDecoder (the reverse direction reads the future)")
         if model.precision != "bf16":
@@ -51,15 +57,118 @@ class StreamingDecoder:
         self.left = (taps.numel() - 1) // 2                     # 9
         self.right = taps.numel() - 1 - self.left               # 10
         self.halo = -(-self.left // self.S) * self.S            # left context re-read per call, a multiple of the stride (12)
+        fast_ok = (self.B <= 8 and model.hidden_dim % 256 == 0 and (self.N * self.K) % 256 == 0 and model.layer_dim <= 8)
+        if fast and not fast_ok:
+            raise NsdError("the fast streaming form needs batch <= 8, hidden size and neural_dim*kernelLen multiples of 256, <= 8 layers")
+        self.fast = fast_ok if fast is None else bool(fast)
+        self.use_graph = use_graph
+        self.last_ids: Optional[torch.Tensor] = None           # greedy phoneme id(s) of the last emitted frame (fast form), i32 [B] on the device
+        self._graph = None
         self.reset()
 
     def reset(self) -> None:
         m = self.m
-        self.h: List[torch.Tensor] = [torch.zeros(self.B, m.hidden_dim, device=self.dev) for _ in range(m.layer_dim)]
+        if getattr(self, "hs", None) is None:
+            self.hs = torch.zeros(m.layer_dim, self.B, m.hidden_dim, device=self.dev)   # fp32 state of every layer, carried between calls
+        else:
+            self.hs.zero_()            # in place: a captured graph of the fast form holds this buffer's address
         self.hist = torch.empty(self.B, 0, self.N, device=self.dev)
         self.hist_start = 0            # absolute bin index of hist[:, 0]
         self.n_bins = 0                # bins received so far
         self.next_frame = 0            # first frame not yet emitted
+        self._steady = False           # fast form engaged: the last bins live in the static window instead of ``hist``
+
+    # ------------------------------------------------------------------------------------------------------------ fast form
+    def _fast_setup(self, extra: int) -> None:
+        """Static buffers of the fast form (allocated once per alignment ``extra`` = bins received beyond the newest frame's
+        look-ahead; constant while every push is one stride long)."""
+        m, B = self.m, self.B
+        W = self.halo + self.K + self.right
+        if getattr(self, "_extra", None) == extra and getattr(self, "_win", None) is not None:
+            return
+        self._extra = extra
+        self._win = torch.zeros(B, W + extra, self.N, device=self.dev)       # last W + extra raw bins
+        self._tmp = torch.empty(B, W + extra - self.S, self.N, device=self.dev)
+        self._bins_in = torch.zeros(B, self.S, self.N, device=self.dev)
+        C = m.fc_decoder_out.weight.shape[0]
+        self._logits = torch.zeros(B, C, device=self.dev)
+        self.last_ids = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        nbytes = _lib.lib().nsd_gru_stream_step_workspace(B, m.hidden_dim, m.layer_dim)
+        self._ws = torch.empty(nbytes, device=self.dev, dtype=torch.uint8)
+        gw = m._gru_weights()
+        L = m.layer_dim
+        self._w_ih = [m._shadows.stacked(("ih", l), [gw[4 * l]]) for l in range(L)]
+        self._w_hh = [m._shadows.stacked(("hh", l), [gw[4 * l + 1]]) for l in range(L)]
+        self._b_ih = [gw[4 * l + 2].detach().contiguous() for l in range(L)]
+        self._b_hh = [gw[4 * l + 3].detach().contiguous() for l in range(L)]
+        self._fc_w = m._shadows.stacked(("fc", 0), [m.fc_decoder_out.weight])
+        self._fc_b = m.fc_decoder_out.bias.detach().contiguous()
+        self._taps = m.gaussianSmoother.weight[0, 0].contiguous()
+        self._day_w = m.dayWeights.detach().contiguous()
+        self._day_b = m.dayBias.detach().contiguous()
+        self._graph = None
+
+    def _fast_compute(self) -> None:
+        """K1 on the window's first halo+K+right bins -> the frame that starts ``halo`` bins in -> one stack step."""
+        m, B = self.m, self.B
+        W = self.halo + self.K + self.right
+        patches, _, _ = ops.frontend_fwd(self._win[:, :W], self.day, self._day_w, self._day_b, self._taps, self.K, self.S,
+                                         torch.bfloat16, m._err_flag)
+        skip = self.halo // self.S
+        ops.gru_stream_step(patches[skip * B:(skip + 1) * B], self._w_ih, self._w_hh, self._b_ih, self._b_hh, self.hs,
+                            self._fc_w, self._fc_b, self._logits, self.last_ids, self._ws)
+
+    def _fast_shift_compute(self) -> None:
+        """window <- [window[S:], bins_in]; then compute.  The unit that is captured as a CUDA graph."""
+        n = self._win.shape[1] - self.S
+        self._tmp.copy_(self._win[:, self.S:])
+        self._win[:, :n].copy_(self._tmp)
+        self._win[:, n:].copy_(self._bins_in)
+        self._fast_compute()
+
+    @torch.no_grad()
+    def _push_fast(self, bins: torch.Tensor) -> torch.Tensor:
+        self._bins_in.copy_(bins, non_blocking=True)
+        if self.use_graph and self._graph is None:
+            try:                                               # warm up on a side stream, then capture (torch's capture protocol)
+                snap_h, snap_w = self.hs.clone(), self._win.clone()
+                side = torch.cuda.Stream(self.dev)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+                with torch.cuda.stream(side):
+                    self._fast_shift_compute()
+                torch.cuda.current_stream(self.dev).wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                self.hs.copy_(snap_h); self._win.copy_(snap_w)
+                with torch.cuda.graph(g):
+                    self._fast_shift_compute()
+                self.hs.copy_(snap_h); self._win.copy_(snap_w)     # capture does not execute; the warm-up did: restore
+                self._graph = g
+            except Exception as e:                             # noqa: BLE001 -- capture unsupported: stay eager (still one launch per stage)
+                self._graph, self.use_graph = None, False
+                self._graph_error = repr(e)
+                torch.cuda.synchronize(self.dev)
+                self.hs.copy_(snap_h); self._win.copy_(snap_w)
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._fast_shift_compute()
+        self.n_bins += self.S
+        self.next_frame += 1
+        return self._logits.clone().unsqueeze(1)
+
+    def _enter_fast(self, j: int) -> None:
+        """Engage the fast form at frame j (complete, not yet emitted): its window = bins [S*j - halo, n_bins)."""
+        W = self.halo + self.K + self.right
+        r0 = self.S * j - self.halo
+        self._fast_setup(self.n_bins - r0 - W)
+        self._win.copy_(self.hist[:, r0 - self.hist_start:self.n_bins - self.hist_start])
+        self._steady = True
+        self.hist = None
+
+    def _leave_fast(self) -> None:
+        self.hist = self._win.clone()
+        self.hist_start = self.n_bins - self._win.shape[1]
+        self._steady = False
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -84,8 +193,8 @@ class StreamingDecoder:
             gi = torch.empty((M, 3 * H), device=self.dev, dtype=torch.float32)
             in_l = inp.shape[1]
             ops.gemm(False, True, M, 3 * H, in_l, inp, in_l, w_ih_bf, in_l, gi, 3 * H, bias=b_ih.detach().contiguous())
-            hseq, hseq_bf, _ = ops.gru_fwd_bf16(gi, w_hh_bf, b_hh.detach().contiguous(), k, B, H, 1, False, False, h0=self.h[l])
-            self.h[l] = hseq[(k - 1) * B:].clone()              # fp32 state carried to the next call
+            hseq, hseq_bf, _ = ops.gru_fwd_bf16(gi, w_hh_bf, b_hh.detach().contiguous(), k, B, H, 1, False, False, h0=self.hs[l])
+            self.hs[l].copy_(hseq[(k - 1) * B:])                # fp32 state carried to the next call
             inp = hseq_bf
         fc = m.fc_decoder_out
         C = fc.weight.shape[0]
@@ -107,12 +216,25 @@ class StreamingDecoder:
             raise RuntimeError(f"bins must be [{self.B}, n, {self.N}], got {tuple(bins.shape)}")
         if self.m._err_flag is None:
             self.m._err_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        if self._steady:
+            if bins.shape[1] == self.S:
+                with torch.cuda.device(self.dev):
+                    return self._push_fast(bins.to(self.dev, torch.float32))
+            self._leave_fast()
         self.hist = torch.cat([self.hist, bins.to(self.dev, torch.float32)], dim=1)
         self.n_bins += bins.shape[1]
         # frame j needs smoothed bins up to S*j+K-1, i.e. raw bins up to S*j+K-1+right
         j1 = complete_frames(self.n_bins, self.K, self.S, self.right) - 1
         if j1 < self.next_frame:
             return None
+        if (self.fast and bins.shape[1] == self.S and j1 == self.next_frame and self.S * j1 >= self.halo
+                and self.S * j1 - self.halo >= self.hist_start):
+            # steady streaming: one stride per push, one new frame per push -> the single-launch step from here on
+            with torch.cuda.device(self.dev):
+                self._enter_fast(j1)
+                self._fast_compute()
+            self.next_frame = j1 + 1
+            return self._logits.clone().unsqueeze(1)
         with torch.cuda.device(self.dev):
             out = self._emit(self.next_frame, j1, self.S * j1 + self.K + self.right)
         self.next_frame = j1 + 1
@@ -122,6 +244,8 @@ class StreamingDecoder:
     @torch.no_grad()
     def finish(self) -> Optional[torch.Tensor]:
         """End of utterance: the frames the offline forward still produces (it zero-pads the smoothing past the last bin)."""
+        if self._steady:
+            self._leave_fast()
         if self.n_bins < self.K:
             if self.next_frame == 0 and self.n_bins > 0:
                 raise RuntimeError(f"utterance shorter than kernelLen={self.K} bins")     # the reference raises too (nn.Unfold)

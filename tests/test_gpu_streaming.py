@@ -1,6 +1,7 @@
-"""StreamingDecoder (stateful incremental inference; BASELINE configs[3]) against the offline forward of
-the same module: identical kernels, carried fp32 state, 10-bin look-ahead -> logits must be BIT-IDENTICAL to
-GRUDecoder.forward on the whole utterance, whatever the chunking."""
+"""StreamingDecoder (stateful incremental inference; BASELINE configs[3]).
+Exact form: identical kernels, carried fp32 state, 10-bin look-ahead -> logits BIT-IDENTICAL to GRUDecoder.forward on the
+whole utterance, whatever the chunking.  Fast form (batch <= 8, one stride per push: nsd_gru_stream_step, CUDA graph): against
+an oracle built from the reference's operators with the state carried between calls, and against the offline forward."""
 import numpy as np
 import pytest
 import torch
@@ -39,7 +40,7 @@ def test_streaming_equals_offline(kw, B, T, chunks):
     day = torch.randint(0, kw["nDays"], (B,), generator=g).to(DEV)
     with torch.no_grad():
         ref = m.forward(X, day)                                          # [B, T', C]
-    sd = nsd.StreamingDecoder(m, B, day)
+    sd = nsd.StreamingDecoder(m, B, day, fast=False)                      # the exact form: same kernels as the offline forward
     outs, pos, emitted_after = [], 0, []
     for n in chunks:
         o = sd.push(X[:, pos:pos + n])
@@ -121,3 +122,54 @@ def test_streaming_vs_reference_operators_with_carried_state():
     agree = (got.argmax(-1) == ref.argmax(-1)).mean()
     print(f"streaming vs chunked reference operators: logits max abs err {err:.3e} (|ref| max {np.abs(ref).max():.2f}), argmax agreement {agree:.4f}")
     assert err < 0.12 and agree >= 0.985
+
+
+@pytest.mark.parametrize("B,use_graph", [(1, True), (3, True), (8, False)])
+def test_streaming_fast_form(B, use_graph):
+    """The single-launch step (nsd_gru_stream_step) engaged by steady 4-bin pushes, with and without CUDA-graph replay:
+    vs the chunked reference-operator oracle (bf16 tolerance), vs the offline forward of the module (same bf16 arithmetic,
+    different fp32 summation order -> a tight bound), greedy ids == argmax of the returned logits, and a mid-stream irregular
+    push falls back to the exact form and re-engages."""
+    from oracle import torch_port as P
+    kw = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, strideLen=4, kernelLen=32, gaussianSmoothWidth=2.0)
+    T = 232
+    m = build(**kw)
+    port = P.PortGRUDecoder(bidirectional=False, dropout=0.0, **kw)
+    port.load_reference_state({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    port = port.double().eval()
+    g = torch.Generator().manual_seed(5 + B)
+    X = torch.randn(B, T, 256, generator=g)
+    day = torch.randint(0, 24, (B,), generator=g)
+    ref = port_streaming_oracle(port, X.double(), day, frames_per_call=1).numpy()
+    with torch.no_grad():
+        off = m.forward(X.to(DEV), day.to(DEV)).cpu().numpy().astype(np.float64)
+    sd = nsd.StreamingDecoder(m, B, day.to(DEV), use_graph=use_graph)
+    assert sd.fast
+    outs, fast_frames, pos = [], 0, 0
+    sizes = [4] * 30 + [6] + [4] * 100                     # one irregular push in the middle
+    for n in sizes:
+        if pos >= T:
+            break
+        n = min(n, T - pos)
+        o = sd.push(X[:, pos:pos + n].to(DEV))
+        pos += n
+        if o is not None:
+            outs.append(o)
+            if sd._steady:
+                fast_frames += o.shape[1]
+                assert torch.equal(sd.last_ids.long(), o[:, -1].argmax(-1))
+    o = sd.finish()
+    if o is not None:
+        outs.append(o)
+    got = torch.cat(outs, dim=1).cpu().numpy().astype(np.float64)
+    assert got.shape == ref.shape and fast_frames >= 30
+    if use_graph:
+        assert sd._graph is not None, getattr(sd, "_graph_error", "no graph captured")
+    e_ref, e_off = np.abs(got - ref).max(), np.abs(got - off).max()
+    agree = (got.argmax(-1) == ref.argmax(-1)).mean()
+    print(f"fast streaming B={B} graph={use_graph}: {fast_frames} frames through the step kernel; vs oracle {e_ref:.3e}, vs offline forward {e_off:.3e}, argmax agreement {agree:.4f}")
+    # greedy decisions may differ from the fp64 oracle only at near ties (top-2 margin of the oracle below twice the logit error)
+    top2 = np.sort(ref, axis=-1)[..., -2:]
+    flips = got.argmax(-1) != ref.argmax(-1)
+    assert not (flips & ((top2[..., 1] - top2[..., 0]) > 2 * e_ref)).any()
+    assert e_ref < 0.12 and agree >= 0.95 and e_off < 0.06
