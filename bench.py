@@ -498,33 +498,51 @@ def run_stream(a):
     nsd.set_default_precision("bf16")
     torch.manual_seed(0)
     model = nsd.GRUDecoder(device="cuda", bidirectional=False, **{**MODEL_KW, "dropout": 0.0}).to(dev).eval()
-    for B in (1, 32):
+    for B in (1, 8, 32):
         X, y, X_len, y_len, day = make_batch(B, a.T, seed=2)
         X = X.pin_memory()
         sd = nsd.StreamingDecoder(model, B, day)
-        lat = []
-        for rep in range(2):                                    # first pass warms up
+        lat, dev_us = [], []
+        for rep in range(2):                                    # first pass warms up (and captures the graph)
             sd.reset()
             lat = []
             for pos in range(0, a.T, 4):
                 t0 = time.perf_counter()
-                o = sd.push(X[:, pos:pos + 4].to(dev, non_blocking=True))
-                if o is None:
+                ids = sd.push_decode(X[:, pos:pos + 4])         # pinned host bins in -> greedy ids on the host (synchronises)
+                if ids is None:
                     torch.cuda.synchronize()
-                elif sd._steady:
-                    ids = sd.last_ids.cpu()                 # greedy id computed inside the step kernel
-                else:
-                    ids = o.argmax(-1).cpu()
                 lat.append(time.perf_counter() - t0)
+            sd.finish()
+        if sd.fast and sd._graph is not None:                   # device time of one replay (the push kernel + the two read-backs)
+            sd.reset()
+            for pos in range(0, a.T, 4):
+                steady = sd._steady
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if steady:
+                    sd._bins_in.copy_(X[:, pos:pos + 4], non_blocking=True)
+                    e0.record(); sd._graph.replay(); e1.record()
+                    sd.n_bins += 4; sd.next_frame += 1
+                    torch.cuda.synchronize()
+                    dev_us.append(e0.elapsed_time(e1) * 1e3)
+                else:
+                    sd.push(X[:, pos:pos + 4])
             sd.finish()
         steady = sorted(lat[len(lat) // 4:])
         med, p99 = steady[len(steady) // 2], steady[int(len(steady) * 0.99) - 1]
-        print(json.dumps({"metric": "streaming inference latency per 4-bin (80 ms) push, unidirectional GRUDecoder, greedy id out",
-                          "batch": B, "dtype": "bf16", "us_per_push_median": round(med * 1e6, 1), "us_per_push_p99": round(p99 * 1e6, 1),
-                          "us_per_20ms_bin": round(med * 1e6 / 4, 1), "real_time_factor": round(0.080 / med, 1),
-                          "lookahead_bins": 10, "pushes": len(steady), "impl": "ours", "data": "synthetic",
-                          "form": ("single-launch stack step, CUDA graph replay" if (sd.fast and sd._graph is not None) else
-                                   "single-launch stack step" if sd.fast else "time-batched kernels (exact form)")}), flush=True)
+        line = {"metric": "streaming inference latency per 4-bin (80 ms) push, unidirectional GRUDecoder, greedy id out",
+                "batch": B, "dtype": "bf16", "us_per_push_median": round(med * 1e6, 1), "us_per_push_p99": round(p99 * 1e6, 1),
+                "us_per_20ms_bin": round(med * 1e6 / 4, 1), "real_time_factor": round(0.080 / med, 1),
+                "lookahead_bins": 10, "pushes": len(steady), "impl": "ours", "data": "synthetic",
+                "protocol": "pinned host bins -> H2D -> push -> greedy ids D2H -> stream synchronise, wall clock per push",
+                "form": ("nsd_stream_push: one launch per push (front end + 5-layer stack + logits + argmax), CUDA graph replay"
+                         if (sd.fast and sd._graph is not None) else
+                         "nsd_stream_push: one launch per push" if sd.fast else "time-batched kernels (exact form)")}
+        if dev_us:
+            dev_us.sort()
+            line["device_us_per_push_median"] = round(dev_us[len(dev_us) // 2], 1)
+            line["weights_streamed_mb_per_push"] = round(sum(w.numel() * 2 for w in sd._w_ih + sd._w_hh) / 1e6, 1)
+            line["weight_stream_gbps"] = round(line["weights_streamed_mb_per_push"] * 1e-3 / (line["device_us_per_push_median"] * 1e-6), 0)
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -203,18 +203,27 @@ int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, 
                   void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream);
 
-/* Streaming inference step for B <= 8 (new: the reference's forward has no state API, model.py:104-119 always starts from
- * h0 = 0 and drops h_n): one cooperative launch advances the whole unidirectional GRU stack by ONE output frame --
- * per layer l: gi = x_l W_ih^T + b_ih, gh = bf16(h_l) W_hh^T + b_hh, gates r,z,n, h_l <- (1-z) n + z h_l (model.py:50-57, 119),
- * then logits = h_{L-1} fc_w^T + fc_b (model.py:122) and ids[b] = argmax_c logits[b,c] (ties -> lowest index, trainer:314).
- *   x0_bf16 [B, ldx >= F0] bf16 patch rows of the new frame; w_ih/w_hh/b_ih/b_hh: HOST arrays of L device pointers
- *   (bf16 [3H,in_l] / bf16 [3H,H] / f32 [3H] / f32 [3H], gate rows r|z|n); h f32 [L][B][H] carried state, updated in
- *   place; logits f32 [B,C]; ids i32 [B] or NULL.  H and F0 multiples of 256, L <= 8. */
-size_t nsd_gru_stream_step_workspace(int B, int H, int L);
-int nsd_gru_stream_step(const void* x0_bf16, int ldx, int B, int F0, int H, int L, int C, const void* const* w_ih_bf16,
-                        const void* const* w_hh_bf16, const void* const* b_ih, const void* const* b_hh, float* h,
-                        const void* fc_w_bf16, const float* fc_b, float* logits, int* ids, void* workspace, size_t workspace_bytes,
-                        void* stream);
+/* Streaming inference push for B <= 8 (new: the reference's forward has no state API, model.py:104-119 always starts from
+ * h0 = 0 and drops h_n).  ONE cooperative launch consumes S new bins and advances the whole unidirectional decoder by one
+ * output frame: smoothing of the S bins that became computable (augmentations.py:91; left/right reach (ntaps-1)/2 and
+ * ntaps-1-(ntaps-1)/2), day affine + softsign (model.py:89-93; bf16 operands, fp32 accumulate, like nsd_frontend_fwd's bf16
+ * form), slide of the k/s patch (model.py:96-101), per layer l: gi = x_l W_ih^T + b_ih, gh = bf16(h_l) W_hh^T + b_hh, gates
+ * r,z,n, h_l <- (1-z) n + z h_l (model.py:50-57, 119), logits = h_{L-1} fc_w^T + fc_b (model.py:122) and
+ * ids[b] = argmax_c logits[b,c] (ties -> lowest index, trainer:314).  State carried between calls, all on the device:
+ *   rawring f32 [B][ring_rows][N]  raw bins by absolute index mod ring_rows (ring_rows >= ntaps-1+2S);
+ *   x0buf bf16 [2][B][N*K]         patch row of frame j in half (j & 1), feature order c*K + k;
+ *   n_bins i32 [1]                 bins received so far (the launch adds S);   extra = n_bins - (S*j + K + right) in [0, S)
+ *                                  for the newest emitted frame j (constant while every push is S bins);
+ *   h f32 [L][B][H], h_bf16 [L][B][H]   state of every layer and its bf16 operand copy, updated in place.
+ * bins_in f32 [B][S][N]; w_ih/w_hh/b_ih/b_hh: HOST arrays of L device pointers (bf16 [3H,in_l] / bf16 [3H,H] / f32 [3H] / f32
+ * [3H], gate rows r|z|n); logits f32 [B,C]; ids i32 [B] or NULL; err_flag: set to 1 on a day index out of range.
+ * H and N*K multiples of 512, N a multiple of 32, S <= 8, L <= 8. */
+size_t nsd_stream_push_workspace(int B, int F0, int H, int L);
+int nsd_stream_push(const float* bins_in, float* rawring, int ring_rows, const int64_t* day_idx, const float* day_w, const float* day_b,
+                    int n_days, const float* taps, int ntaps, void* x0buf_bf16, int* n_bins, int extra, int B, int N, int K, int S, int H,
+                    int L, int C, const void* const* w_ih_bf16, const void* const* w_hh_bf16, const void* const* b_ih,
+                    const void* const* b_hh, float* h, void* h_bf16, const void* fc_w_bf16, const float* fc_b, float* logits, int* ids,
+                    int* err_flag, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Keep n_sms SMs free of the persistent tensor-core GEMM grids from now on (0 = use every SM).  New (no reference
  * counterpart): while parallel.GradSync has a gradient bucket in flight, NCCL's CTAs run on the reserved SMs instead of

@@ -49,8 +49,9 @@ SIGNATURES = {
     "nsd_log_softmax_f32": (i32, [vp, vp, i64, i32, vp]),
     "nsd_adam_step": (i32, [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, vp]),
     "nsd_set_gemm_sm_reserve": (i32, [i32]),
-    "nsd_gru_stream_step_workspace": (sz, [i32, i32, i32]),
-    "nsd_gru_stream_step": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "nsd_stream_push_workspace": (sz, [i32, i32, i32, i32]),
+    "nsd_stream_push": (i32, [vp, vp, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                              vp, vp, vp, vp, vp, vp, sz, vp]),
     "nsd_multi_copy_f32": (i32, [i32, vp, vp, vp, vp]),
     "nsd_greedy_decode": (i32, [vp, i64, i64, i64, vp, i32, i32, i32, i32, vp, vp, vp]),
     "nsd_edit_distance": (i32, [vp, i32, vp, vp, i32, vp, i32, vp, vp, sz, vp]),

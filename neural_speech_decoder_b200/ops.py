@@ -228,19 +228,25 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
          float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), stream())
 
 
-def gru_stream_step(x0_bf16, w_ih_bf, w_hh_bf, b_ih, b_hh, h, fc_w_bf, fc_b, logits, ids, ws):
-    """One output frame of the whole unidirectional stack for B <= 8 in one launch (nsd_gru_stream_step): ``x0_bf16`` [B,F0]
-    bf16 (row stride free), per-layer lists of bf16 weights / f32 biases, ``h`` f32 [L,B,H] updated in place, ``logits`` f32
-    [B,C] and ``ids`` i32 [B] written.  ``ws`` = uint8 workspace of nsd_gru_stream_step_workspace bytes."""
+def stream_push(bins_in, rawring, day, day_w, day_b, taps, x0buf, n_bins, extra, K, S, w_ih_bf, w_hh_bf, b_ih, b_hh, h, hbf, fc_w_bf, fc_b,
+                logits, ids, err_flag, ws):
+    """One streaming push for B <= 8 in one launch (nsd_stream_push): ``bins_in`` f32 [B,S,N] new bins -> front end of the
+    bins that became computable, slide of the patch row in ``x0buf`` bf16 [2,B,N*K], every layer of the unidirectional stack
+    (``h`` f32 / ``hbf`` bf16 [L,B,H] updated in place), ``logits`` f32 [B,C] and ``ids`` i32 [B].  ``rawring`` f32 [B,R,N],
+    ``n_bins`` i32 [1] and ``extra`` describe the stream position (see include/nsd_b200.h)."""
     import ctypes as C
     L, B, H = h.shape
-    F0 = x0_bf16.shape[1]
-    assert x0_bf16.dtype == torch.bfloat16 and x0_bf16.stride(1) == 1 and h.dtype == torch.float32 and h.is_contiguous()
+    N = bins_in.shape[2]
+    for t in (bins_in, rawring, day_w, day_b, taps, x0buf, h, hbf, fc_w_bf, fc_b, logits, ids, ws):
+        assert t.is_contiguous()
+    assert bins_in.shape == (B, S, N) and rawring.shape[0] == B and rawring.shape[2] == N and x0buf.shape == (2, B, N * K)
+    assert x0buf.dtype == torch.bfloat16 and hbf.dtype == torch.bfloat16 and h.dtype == torch.float32 and day.dtype == torch.int64
     tab = lambda ts: (C.c_void_p * L)(*[t.data_ptr() for t in ts])
     for l in range(L):
         assert w_ih_bf[l].is_contiguous() and w_hh_bf[l].is_contiguous() and b_ih[l].is_contiguous() and b_hh[l].is_contiguous()
-    call("nsd_gru_stream_step", ptr(x0_bf16), x0_bf16.stride(0), B, F0, H, L, fc_w_bf.shape[0], tab(w_ih_bf), tab(w_hh_bf), tab(b_ih),
-         tab(b_hh), ptr(h), ptr(fc_w_bf), ptr(fc_b), ptr(logits), ptr(ids), ptr(ws), ws.numel(), stream())
+    call("nsd_stream_push", ptr(bins_in), ptr(rawring), rawring.shape[1], ptr(day), ptr(day_w), ptr(day_b), day_w.shape[0], ptr(taps),
+         taps.numel(), ptr(x0buf), ptr(n_bins), int(extra), B, N, int(K), int(S), H, L, fc_w_bf.shape[0], tab(w_ih_bf), tab(w_hh_bf),
+         tab(b_ih), tab(b_hh), ptr(h), ptr(hbf), ptr(fc_w_bf), ptr(fc_b), ptr(logits), ptr(ids), ptr(err_flag), ptr(ws), ws.numel(), stream())
 
 
 def multi_copy(srcs, dsts):

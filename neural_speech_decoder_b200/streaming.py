@@ -5,11 +5,12 @@ The reference has no streaming API: ``forward`` always starts from h0 = 0 and dr
 bins a future frame still needs.  Two execution forms:
   * exact (any batch, any chunking): the SAME time-batched kernels fed incrementally; logits bit-identical to the offline
     forward;
-  * fast (batch <= 8, steady pushes of one stride = one new frame): K1 on the 54-bin window + ONE launch of
-    ``nsd_gru_stream_step`` for the whole 5-layer stack, logits and greedy id, replayed as a captured CUDA graph, so a push
-    costs one graph launch instead of ~15 enqueued calls; the 107 MB of bf16 weights are streamed once per push and stay
-    resident in the 126 MB L2 between pushes.  Same arithmetic up to fp32 summation order (checked against the
-    reference-operator oracle with carried state, tests/test_gpu_streaming.py).  Frame j covers bins [4j, 4j+32) (kernel 32 / stride 4, model.py:37-39) of the smoothed signal, and the 20-tap
+  * fast (batch <= 8, steady pushes of one stride = one new frame): ONE launch of ``nsd_stream_push`` per push -- front end
+    of the bins that became computable, slide of the patch row, the whole 5-layer stack, logits and greedy id -- replayed as
+    a captured CUDA graph together with the read-back of the ids into pinned memory; all stream state (a ring of the last 64
+    raw bins, the patch row, fp32 + bf16 hidden states, the bin counter) lives on the device, the 107 MB of bf16 weights are
+    streamed once per push and stay resident in the 126 MB L2 between pushes.  Same arithmetic up to fp32 summation order
+    (checked against the reference operators with carried state, tests/test_gpu_streaming.py).  Frame j covers bins [4j, 4j+32) (kernel 32 / stride 4, model.py:37-39) of the smoothed signal, and the 20-tap
 Gaussian is padded 9 left / 10 right (augmentations.py:91), so frame j can be emitted once bin 4j+41 has arrived: a
 fixed look-ahead of 10 bins (200 ms).  ``finish()`` flushes the frames the offline model would still produce by zero
 padding past the end of the utterance, exactly as the offline smoothing does.
@@ -57,9 +58,12 @@ class StreamingDecoder:
         self.left = (taps.numel() - 1) // 2                     # 9
         self.right = taps.numel() - 1 - self.left               # 10
         self.halo = -(-self.left // self.S) * self.S            # left context re-read per call, a multiple of the stride (12)
-        fast_ok = (self.B <= 8 and model.hidden_dim % 256 == 0 and (self.N * self.K) % 256 == 0 and model.layer_dim <= 8)
+        fast_ok = (self.B <= 8 and model.hidden_dim % 512 == 0 and (self.N * self.K) % 512 == 0 and self.N % 32 == 0 and model.layer_dim <= 8
+                   and self.S <= 8 and self.K > self.S and taps.numel() - 1 + 2 * self.S <= self.RING
+                   and self.halo + self.K + self.right + 2 * self.S <= self.RING)
         if fast and not fast_ok:
-            raise NsdError("the fast streaming form needs batch <= 8, hidden size and neural_dim*kernelLen multiples of 256, <= 8 layers")
+            raise NsdError("the fast streaming form needs batch <= 8, hidden size and neural_dim*kernelLen multiples of 512, neural_dim a "
+                           "multiple of 32, stride <= 8, <= 8 layers")
         self.fast = fast_ok if fast is None else bool(fast)
         self.use_graph = use_graph
         self.last_ids: Optional[torch.Tensor] = None           # greedy phoneme id(s) of the last emitted frame (fast form), i32 [B] on the device
@@ -79,24 +83,32 @@ class StreamingDecoder:
         self._steady = False           # fast form engaged: the last bins live in the static window instead of ``hist``
 
     # ------------------------------------------------------------------------------------------------------------ fast form
+    RING = 64                          # raw bins kept on the device (>= halo + K + right + S: enough to fall back to the exact form)
+
     def _fast_setup(self, extra: int) -> None:
-        """Static buffers of the fast form (allocated once per alignment ``extra`` = bins received beyond the newest frame's
-        look-ahead; constant while every push is one stride long)."""
+        """Device state of the fast form (allocated once; ``extra`` = bins received beyond the newest frame's look-ahead,
+        constant while every push is one stride long -- it is a kernel argument, so a change re-captures the graph)."""
         m, B = self.m, self.B
-        W = self.halo + self.K + self.right
-        if getattr(self, "_extra", None) == extra and getattr(self, "_win", None) is not None:
-            return
+        if getattr(self, "_extra", None) != extra:
+            self._graph = None
         self._extra = extra
-        self._win = torch.zeros(B, W + extra, self.N, device=self.dev)       # last W + extra raw bins
-        self._tmp = torch.empty(B, W + extra - self.S, self.N, device=self.dev)
-        self._bins_in = torch.zeros(B, self.S, self.N, device=self.dev)
+        if getattr(self, "_rawring", None) is not None:
+            return
+        L, H, F0 = m.layer_dim, m.hidden_dim, self.N * self.K
         C = m.fc_decoder_out.weight.shape[0]
-        self._logits = torch.zeros(B, C, device=self.dev)
-        self.last_ids = torch.zeros(B, dtype=torch.int32, device=self.dev)
-        nbytes = _lib.lib().nsd_gru_stream_step_workspace(B, m.hidden_dim, m.layer_dim)
-        self._ws = torch.empty(nbytes, device=self.dev, dtype=torch.uint8)
+        dev = self.dev
+        self._bins_in = torch.zeros(B, self.S, self.N, device=dev)
+        self._rawring = torch.zeros(B, self.RING, self.N, device=dev)
+        self._x0buf = torch.zeros(2, B, F0, device=dev, dtype=torch.bfloat16)
+        self._nbins_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._hbf = torch.zeros(L, B, H, device=dev, dtype=torch.bfloat16)
+        self._logits = torch.zeros(B, C, device=dev)
+        self.last_ids = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._logits_host = torch.zeros(B, C).pin_memory()
+        self._ids_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+        nbytes = _lib.lib().nsd_stream_push_workspace(B, F0, H, L)
+        self._ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         gw = m._gru_weights()
-        L = m.layer_dim
         self._w_ih = [m._shadows.stacked(("ih", l), [gw[4 * l]]) for l in range(L)]
         self._w_hh = [m._shadows.stacked(("hh", l), [gw[4 * l + 1]]) for l in range(L)]
         self._b_ih = [gw[4 * l + 2].detach().contiguous() for l in range(L)]
@@ -106,69 +118,83 @@ class StreamingDecoder:
         self._taps = m.gaussianSmoother.weight[0, 0].contiguous()
         self._day_w = m.dayWeights.detach().contiguous()
         self._day_b = m.dayBias.detach().contiguous()
-        self._graph = None
 
-    def _fast_compute(self) -> None:
-        """K1 on the window's first halo+K+right bins -> the frame that starts ``halo`` bins in -> one stack step."""
-        m, B = self.m, self.B
-        W = self.halo + self.K + self.right
-        patches, _, _ = ops.frontend_fwd(self._win[:, :W], self.day, self._day_w, self._day_b, self._taps, self.K, self.S,
-                                         torch.bfloat16, m._err_flag)
-        skip = self.halo // self.S
-        ops.gru_stream_step(patches[skip * B:(skip + 1) * B], self._w_ih, self._w_hh, self._b_ih, self._b_hh, self.hs,
-                            self._fc_w, self._fc_b, self._logits, self.last_ids, self._ws)
+    def _fast_state(self):
+        return [self.hs, self._hbf, self._rawring, self._x0buf, self._nbins_dev]
 
-    def _fast_shift_compute(self) -> None:
-        """window <- [window[S:], bins_in]; then compute.  The unit that is captured as a CUDA graph."""
-        n = self._win.shape[1] - self.S
-        self._tmp.copy_(self._win[:, self.S:])
-        self._win[:, :n].copy_(self._tmp)
-        self._win[:, n:].copy_(self._bins_in)
-        self._fast_compute()
+    def _fast_launch(self) -> None:
+        """One launch for the whole push + the read-back of logits and greedy ids into pinned host memory: the unit that is
+        captured as a CUDA graph."""
+        ops.stream_push(self._bins_in, self._rawring, self.day, self._day_w, self._day_b, self._taps, self._x0buf, self._nbins_dev,
+                        self._extra, self.K, self.S, self._w_ih, self._w_hh, self._b_ih, self._b_hh, self.hs, self._hbf, self._fc_w,
+                        self._fc_b, self._logits, self.last_ids, self.m._err_flag, self._ws)
+        self._ids_host.copy_(self.last_ids, non_blocking=True)
+        self._logits_host.copy_(self._logits, non_blocking=True)
 
-    @torch.no_grad()
-    def _push_fast(self, bins: torch.Tensor) -> torch.Tensor:
-        self._bins_in.copy_(bins, non_blocking=True)
+    def _fast_step(self, bins: torch.Tensor) -> None:
+        self._bins_in.copy_(bins, non_blocking=True)               # pinned host (fastest), pageable host or device source
         if self.use_graph and self._graph is None:
+            snap = [t.clone() for t in self._fast_state()]
             try:                                               # warm up on a side stream, then capture (torch's capture protocol)
-                snap_h, snap_w = self.hs.clone(), self._win.clone()
                 side = torch.cuda.Stream(self.dev)
                 side.wait_stream(torch.cuda.current_stream(self.dev))
                 with torch.cuda.stream(side):
-                    self._fast_shift_compute()
+                    self._fast_launch()
                 torch.cuda.current_stream(self.dev).wait_stream(side)
+                for t, v in zip(self._fast_state(), snap):
+                    t.copy_(v)
                 g = torch.cuda.CUDAGraph()
-                self.hs.copy_(snap_h); self._win.copy_(snap_w)
                 with torch.cuda.graph(g):
-                    self._fast_shift_compute()
-                self.hs.copy_(snap_h); self._win.copy_(snap_w)     # capture does not execute; the warm-up did: restore
-                self._graph = g
-            except Exception as e:                             # noqa: BLE001 -- capture unsupported: stay eager (still one launch per stage)
+                    self._fast_launch()
+                self._graph = g                                # capture does not execute; the warm-up did and was undone above
+            except Exception as e:                             # noqa: BLE001 -- capture unsupported: stay eager (still one launch per push)
                 self._graph, self.use_graph = None, False
                 self._graph_error = repr(e)
                 torch.cuda.synchronize(self.dev)
-                self.hs.copy_(snap_h); self._win.copy_(snap_w)
+                for t, v in zip(self._fast_state(), snap):
+                    t.copy_(v)
         if self._graph is not None:
             self._graph.replay()
         else:
-            self._fast_shift_compute()
+            self._fast_launch()
         self.n_bins += self.S
         self.next_frame += 1
-        return self._logits.clone().unsqueeze(1)
 
     def _enter_fast(self, j: int) -> None:
-        """Engage the fast form at frame j (complete, not yet emitted): its window = bins [S*j - halo, n_bins)."""
-        W = self.halo + self.K + self.right
-        r0 = self.S * j - self.halo
-        self._fast_setup(self.n_bins - r0 - W)
-        self._win.copy_(self.hist[:, r0 - self.hist_start:self.n_bins - self.hist_start])
+        """Engage the fast form after frame j went through the exact form: ring <- the last raw bins, patch row of frame j,
+        bf16 copy of the carried states, stream position."""
+        n, R = self.n_bins, self.RING
+        self._fast_setup(n - (self.S * j + self.K + self.right))
+        self._ring_from = max(self.hist_start, n - R)              # oldest bin the ring really holds
+        a = torch.arange(self._ring_from, n, device=self.dev)
+        self._rawring.zero_()
+        self._rawring[:, a % R] = self.hist[:, a - self.hist_start]
+        self._x0buf[j & 1].copy_(self._last_patch)
+        self._hbf.copy_(self.hs)
+        self._nbins_dev.fill_(n)
         self._steady = True
         self.hist = None
 
     def _leave_fast(self) -> None:
-        self.hist = self._win.clone()
-        self.hist_start = self.n_bins - self._win.shape[1]
+        n, R = self.n_bins, self.RING
+        self.hist_start = max(self._ring_from, n - R)
+        a = torch.arange(self.hist_start, n, device=self.dev)
+        self.hist = self._rawring[:, a % R].contiguous()
         self._steady = False
+
+    @torch.no_grad()
+    def push_decode(self, bins: torch.Tensor) -> Optional[torch.Tensor]:
+        """``push`` + greedy phoneme ids on the host: int32 CPU tensor [B, f] for the f frames that became complete (None if
+        f == 0).  In the steady fast form this is the low-latency call: one graph replay (H2D of the bins is enqueued in front
+        of it, the ids come back through pinned memory), one stream synchronisation.  The returned tensor is reused by the
+        next call."""
+        if self._steady and bins.dim() == 3 and bins.shape == (self.B, self.S, self.N):
+            with torch.cuda.device(self.dev):
+                self._fast_step(bins)
+                torch.cuda.current_stream(self.dev).synchronize()
+            return self._ids_host.unsqueeze(1)
+        out = self.push(bins)
+        return None if out is None else out.argmax(-1).to(torch.int32).cpu()
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -183,6 +209,7 @@ class StreamingDecoder:
         patches, _, _ = ops.frontend_fwd(x, self.day, m.dayWeights.detach().contiguous(), m.dayBias.detach().contiguous(), taps,
                                          K, S, torch.bfloat16, m._err_flag if m._err_flag is not None else None)
         inp = patches[skip * B:(skip + k) * B]                  # time-major rows: a contiguous block of frames
+        self._last_patch = patches[(skip + k - 1) * B:(skip + k) * B]   # bf16 [B, N*K]: the fast form slides it from here on
         H, L = m.hidden_dim, m.layer_dim
         M = k * B
         gw = m._gru_weights()
@@ -219,7 +246,8 @@ class StreamingDecoder:
         if self._steady:
             if bins.shape[1] == self.S:
                 with torch.cuda.device(self.dev):
-                    return self._push_fast(bins.to(self.dev, torch.float32))
+                    self._fast_step(bins)
+                    return self._logits.clone().unsqueeze(1)
             self._leave_fast()
         self.hist = torch.cat([self.hist, bins.to(self.dev, torch.float32)], dim=1)
         self.n_bins += bins.shape[1]
@@ -227,16 +255,15 @@ class StreamingDecoder:
         j1 = complete_frames(self.n_bins, self.K, self.S, self.right) - 1
         if j1 < self.next_frame:
             return None
-        if (self.fast and bins.shape[1] == self.S and j1 == self.next_frame and self.S * j1 >= self.halo
-                and self.S * j1 - self.halo >= self.hist_start):
-            # steady streaming: one stride per push, one new frame per push -> the single-launch step from here on
-            with torch.cuda.device(self.dev):
-                self._enter_fast(j1)
-                self._fast_compute()
-            self.next_frame = j1 + 1
-            return self._logits.clone().unsqueeze(1)
         with torch.cuda.device(self.dev):
             out = self._emit(self.next_frame, j1, self.S * j1 + self.K + self.right)
+            if self.fast and bins.shape[1] == self.S and j1 == self.next_frame and self.S * j1 >= self.halo:
+                # steady streaming: one stride per push, one new frame per push -> the single-launch push from here on
+                self.next_frame = j1 + 1
+                self._trim()
+                self._enter_fast(j1)
+                self.last_ids.copy_(out[:, -1].argmax(-1))
+                return out
         self.next_frame = j1 + 1
         self._trim()
         return out

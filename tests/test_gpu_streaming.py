@@ -1,6 +1,6 @@
 """StreamingDecoder (stateful incremental inference; BASELINE configs[3]).
 Exact form: identical kernels, carried fp32 state, 10-bin look-ahead -> logits BIT-IDENTICAL to GRUDecoder.forward on the
-whole utterance, whatever the chunking.  Fast form (batch <= 8, one stride per push: nsd_gru_stream_step, CUDA graph): against
+whole utterance, whatever the chunking.  Fast form (batch <= 8, one stride per push: nsd_stream_push, CUDA graph): against
 an oracle built from the reference's operators with the state carried between calls, and against the offline forward."""
 import numpy as np
 import pytest
@@ -121,12 +121,15 @@ def test_streaming_vs_reference_operators_with_carried_state():
     err = np.abs(got - ref).max()
     agree = (got.argmax(-1) == ref.argmax(-1)).mean()
     print(f"streaming vs chunked reference operators: logits max abs err {err:.3e} (|ref| max {np.abs(ref).max():.2f}), argmax agreement {agree:.4f}")
-    assert err < 0.12 and agree >= 0.985
+    top2 = np.sort(ref, axis=-1)[..., -2:]                    # greedy decisions may differ only at near ties of the oracle
+    flips = got.argmax(-1) != ref.argmax(-1)
+    assert not (flips & ((top2[..., 1] - top2[..., 0]) > 2 * err)).any()
+    assert err < 0.12 and agree >= 0.95
 
 
 @pytest.mark.parametrize("B,use_graph", [(1, True), (3, True), (8, False)])
 def test_streaming_fast_form(B, use_graph):
-    """The single-launch step (nsd_gru_stream_step) engaged by steady 4-bin pushes, with and without CUDA-graph replay:
+    """The single-launch push (nsd_stream_push: front end + stack + logits + greedy id) engaged by steady 4-bin pushes, with and without CUDA-graph replay:
     vs the chunked reference-operator oracle (bf16 tolerance), vs the offline forward of the module (same bf16 arithmetic,
     different fp32 summation order -> a tight bound), greedy ids == argmax of the returned logits, and a mid-stream irregular
     push falls back to the exact form and re-engages."""
@@ -173,3 +176,26 @@ def test_streaming_fast_form(B, use_graph):
     flips = got.argmax(-1) != ref.argmax(-1)
     assert not (flips & ((top2[..., 1] - top2[..., 0]) > 2 * e_ref)).any()
     assert e_ref < 0.12 and agree >= 0.95 and e_off < 0.06
+
+
+def test_streaming_push_decode_host_path():
+    """push_decode (pinned host bins in, greedy ids back through pinned memory, one graph replay + one synchronisation per
+    push) returns exactly the argmax of the logits that push() returns for the same stream."""
+    kw = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, strideLen=4, kernelLen=32, gaussianSmoothWidth=2.0)
+    B, T = 2, 160
+    m = build(**kw)
+    g = torch.Generator().manual_seed(11)
+    X = torch.randn(B, T, 256, generator=g)
+    day = torch.randint(0, 24, (B,), generator=g).to(DEV)
+    a, b = nsd.StreamingDecoder(m, B, day), nsd.StreamingDecoder(m, B, day)
+    Xp = X.pin_memory()
+    n_fast = 0
+    for pos in range(0, T, 4):
+        o = a.push(X[:, pos:pos + 4].to(DEV))
+        ids = b.push_decode(Xp[:, pos:pos + 4])
+        assert (o is None) == (ids is None)
+        if o is not None:
+            assert ids.dtype == torch.int32 and not ids.is_cuda
+            assert torch.equal(ids.long(), o.argmax(-1).cpu())
+            n_fast += int(b._steady)
+    assert n_fast >= 20 and b._graph is not None
