@@ -1,10 +1,13 @@
 """Pin the numpy oracle against fixtures produced by the reference itself
 (tests/golden/make_golden.py).  CPU only."""
+import os
 import numpy as np
 import pytest
 
 from conftest import golden_ctor, golden_state, load_golden
 from oracle import nsd_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 SMALL = ["small_uni", "small_bi"]
 
@@ -136,3 +139,57 @@ def test_compiled_reference_equals_port():
     with torch.no_grad():
         a, b = ref(X, day), port(X, day)
     assert torch.allclose(a, b, rtol=0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------- Conformer
+CONFORMER_CFG = {
+    "conformer_small": dict(n_layers=6, n_heads=4, temporal_kernel=16, temporal_stride=4, conv_kernel=7),
+    "conformer_shallow": dict(n_layers=2, n_heads=2, temporal_kernel=8, temporal_stride=2, conv_kernel=5),
+}
+
+
+def _load_conformer(name, dtype):
+    import torch
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]).to(dtype) for k in g.files if k.startswith("sd/")}
+    return g, sd
+
+
+@pytest.mark.parametrize("name", sorted(CONFORMER_CFG))
+def test_conformer_port_matches_reference_fixture(name):
+    """oracle/conformer_port.py (functional restatement over torch operators) against outputs of the imported reference
+    (tests/golden/make_golden_conformer.py): fp64 log-probs 1e-12, loss 1e-12, every gradient 1e-9 relative to its tensor's
+    largest entry; eval-mode forward; output lengths exact."""
+    import torch
+    from oracle import conformer_port as CP
+    g, sd = _load_conformer(name, torch.float64)
+    cfg = CONFORMER_CFG[name]
+    X, day = torch.from_numpy(g["X"]).double(), torch.from_numpy(g["day"])
+    X_len, y, y_len = torch.from_numpy(g["X_len"]), torch.from_numpy(g["y"]), torch.from_numpy(g["y_len"])
+    with torch.no_grad():
+        lp_eval, olen, inter = CP.forward(sd, X, day, X_len, training=False, **cfg)
+    assert inter is None and olen.dtype == torch.int32 and olen.tolist() == g["out_lens"].tolist()
+    np.testing.assert_allclose(lp_eval.numpy(), g["eval_log_probs"], rtol=0, atol=1e-12)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if ("grad/" + k) in g.files}
+    lp, olen, inter = CP.forward({**sd, **params}, X, day, X_len, training=True, **cfg)
+    np.testing.assert_allclose(lp.detach().numpy(), g["log_probs"], rtol=0, atol=1e-12)
+    assert (inter is not None) == ("inter_log_probs" in g.files)
+    if inter is not None:
+        np.testing.assert_allclose(inter.detach().numpy(), g["inter_log_probs"], rtol=0, atol=1e-12)
+    loss = CP.training_loss(lp, inter, y, olen, y_len, label_smoothing=float(g["label_smoothing"]), interctc_weight=float(g["interctc_weight"]))
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-12)
+    loss.backward()
+    for k, p in params.items():
+        ref = g["grad/" + k]
+        got = p.grad.numpy() if p.grad is not None else np.zeros_like(ref)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9 * max(1.0, np.abs(ref).max()), err_msg=k)
+    gn = np.sqrt(sum((p.grad.numpy() ** 2).sum() for p in params.values() if p.grad is not None))
+    np.testing.assert_allclose(gn, float(g["grad_norm"]), rtol=1e-10)
+
+
+def test_conformer_lr_schedule_matches_trainer_lambda():
+    """trainer:154-158 warm-up + cosine factor."""
+    from oracle import conformer_port as CP
+    assert CP.lr_factor(0, 1000, 15000) == 1 / 1000 and CP.lr_factor(999, 1000, 15000) == 1.0
+    assert abs(CP.lr_factor(1000, 1000, 15000) - 1.0) < 1e-15 and abs(CP.lr_factor(8000, 1000, 15000) - 0.5) < 1e-12
+    assert abs(CP.lr_factor(15000, 1000, 15000)) < 1e-15
