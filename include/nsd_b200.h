@@ -225,6 +225,81 @@ int nsd_stream_push(const float* bins_in, float* rawring, int ring_rows, const i
                     const void* const* b_hh, float* h, void* h_bf16, const void* fc_w_bf16, const float* fc_b, float* logits, int* ids,
                     int* err_flag, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ==== Conformer path (BASELINE configs[2]; reference src/neural_decoder/transformer_ctc.py:333-501 and the transformer branch of
+ * neural_decoder_trainer.py:137-162, 206-260).  Activations are row-major [rows = B*T', D] f32 (batch-major rows b*T' + t);
+ * every kernel that feeds a tensor-core GEMM can also emit the bf16 operand copy.  Stochastic regularisers are counter-based
+ * masks keyed by (seed, element index) -- distributional, not bit, parity with torch's generator; the backward regenerates them.
+ * act codes: 0 identity, 1 SiLU, 2 GELU (erf form), 3 ReLU. ================================================================== */
+
+/* y = dropout_p(act(LayerNorm(x) * gamma + beta)); nn.LayerNorm(eps) over the last dimension (transformer_ctc.py:97, 156, 167,
+ * 202, 212, 219, 231, 411), optionally followed by SiLU (:168) or GELU + Dropout (:412-413).  mean/rstd [M] are saved for the
+ * backward.  y_f32 and/or y_bf16.  D % 4 == 0, D <= 2048. */
+int nsd_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed, float* y_f32,
+                      void* y_bf16, float* mean, float* rstd, int M, int D, void* stream);
+/* dx, dgamma, dbeta of the above (dgamma/dbeta overwritten; two fixed-order stages: deterministic). */
+int nsd_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
+                      float p_drop, uint64_t seed, float* dx, float* dgamma, float* dbeta, int M, int D, void* workspace, size_t workspace_bytes,
+                      void* stream);
+size_t nsd_layernorm_bwd_workspace(int M, int D);
+/* y = dropout_p(act(x)) over n contiguous elements (n % 4 == 0): SiLU + Dropout of the feed-forward modules (transformer_ctc.py:204-205,
+ * 223-224), ReLU of the bottleneck MLP (:140); and its backward dx = dy * mask/(1-p) * act'(x). */
+int nsd_act_fwd(const float* x, int act, float p_drop, uint64_t seed, float* y_f32, void* y_bf16, size_t n, void* stream);
+int nsd_act_bwd(const void* dy, int dy_dtype, const float* x, int act, float p_drop, uint64_t seed, float* dx, size_t n, void* stream);
+/* nn.GLU(dim=-1) (transformer_ctc.py:160, 179): g[M,D] = u[:, :D] * sigmoid(u[:, D:]) for u [M, 2D]; and its backward. */
+int nsd_glu_fwd(const float* u, float* g, int M, int D, void* stream);
+int nsd_glu_bwd(const float* dg, const float* u, float* du, int M, int D, void* stream);
+/* out = x + scale * DropPath_{p_path}(dropout_{p_drop}(y)) (transformer_ctc.py:14-23, 190, 245, 251, 257; DropPath keeps a whole sample,
+ * sample = elems_per_sample consecutive elements).  x == NULL gives the gradient w.r.t. y when y holds d(out). */
+int nsd_residual(const float* x, const float* y, float scale, float p_drop, uint64_t seed, float p_path, uint64_t path_seed, int64_t elems_per_sample,
+                 float* out, size_t n, void* stream);
+/* Depthwise convolution over time inside each utterance, zero padding k/2 (nn.Conv1d(groups=D, padding=k//2), transformer_ctc.py:162-166, 183;
+ * the Gaussian smoothing F.conv1d(groups=C, padding=k//2) :104-109 with w_shared != 0: one [k] tap vector for all channels):
+ * y[b,t,d] = bias[d] + sum_j w[d][j] x[b, t+j-k/2, d]; flip != 0 uses w[d][k-1-j] (the data gradient).  x,y [B,T,D]; odd k <= 32. */
+int nsd_dwconv_fwd(const float* x, const float* w, const float* bias, float* y, int B, int T, int D, int k, int flip, int w_shared, void* stream);
+/* dw[d][j] = sum_{b,t} dy[b,t,d] x[b,t+j-k/2,d]; db[d] = sum dy (db may be NULL). */
+int nsd_dwconv_bwd_w(const float* dy, const float* x, float* dw, float* db, int B, int T, int D, int k, void* workspace, size_t workspace_bytes, void* stream);
+size_t nsd_dwconv_bwd_w_workspace(int B, int D, int k);
+/* Strided depthwise convolution without padding or bias (NeuralFrontend.temporal_conv, transformer_ctc.py:81-91, 112-114):
+ * y[b,j,c] = sum_k w[c][k] x[b, j*S+k, c], j < (T-K)/S+1; x [B,T,N] -> y [B,T',N] (f32 and/or bf16).  Backward: dx [B,T,N] and dw [N,K]. */
+int nsd_strided_dwconv_fwd(const float* x, const float* w, float* y_f32, void* y_bf16, int B, int T, int N, int K, int S, void* stream);
+int nsd_strided_dwconv_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, int B, int T, int N, int K, int S, void* workspace,
+                           size_t workspace_bytes, void* stream);
+size_t nsd_strided_dwconv_bwd_workspace(int B, int N, int K);
+/* SpecAugment + positional encoding (transformer_ctc.py:266-308, 311-330, 467-471): out[b,t,d] = (in a masked band ? 0 : z[b,t,d]) + pe[t,d].
+ * bands8 (HOST) = {f0,f1, f0,f1, t0,t1, t0,t1}: feature / frame intervals [lo,hi) set to zero for every utterance (empty: lo >= hi).
+ * pe == NULL: no addition (the backward: dz = band-masked dout). */
+int nsd_posenc_mask(const float* z, const float* pe, const int* bands8, float* out, int B, int T, int D, void* stream);
+/* Strided batched GEMM  C_z[M,N] = alpha * A_z[M,K] B_z[K,N] (+ bias_z[N]),  z = (z0 < nb0, z1 < nb1):
+ *   A_z(m,k) = A[z0*a_b0 + z1*a_b1 + m*a_rs + k*a_cs],  B_z(k,n) = B[zb*b_b0 + z1*b_b1 + k*b_rs + n*b_cs],  zb = b_index ? b_index[z0] : z0,
+ *   C_z(m,n) = C[z0*c_b0 + z1*c_b1 + m*c_rs + n],  bias_z = bias + zb*bias_b0  (strides in elements).
+ * The attention products of nn.MultiheadAttention (transformer_ctc.py:216, 250: Q K^T, P V and their four gradients, read in place from the
+ * packed [B*T', 3D] projection) and the per-day affine x W[day] + b[day] (transformer_ctc.py:41-49; b_index = day ids) and its gradients.
+ * tc_mode < 0: any bf16 operand -> mma.sync tensor-core path (operands rounded to bf16 in shared memory, fp32 accumulate), all-f32
+ * operands -> FFMA parity path; tc_mode = 1 / 0 forces the tensor-core / FFMA path. */
+int nsd_bgemm(const void* A, int a_dtype, int64_t a_rs, int64_t a_cs, int64_t a_b0, int64_t a_b1, const void* B, int b_dtype, int64_t b_rs, int64_t b_cs,
+              int64_t b_b0, int64_t b_b1, const int64_t* b_index, void* C, int c_dtype, int64_t c_rs, int64_t c_b0, int64_t c_b1, const float* bias,
+              int64_t bias_b0, int M, int N, int K, int nb0, int nb1, float alpha, int tc_mode, void* stream);
+/* Attention weights: S [B*H*T, T] f32 scores, in place -> P = softmax over the keys j < lens[b] (key_padding_mask, transformer_ctc.py:250, 475-477;
+ * lens == NULL: no mask); Pd (optional, f32 or bf16) = dropout_p(P) (nn.MultiheadAttention(dropout=p), :216).  Backward: dPd (in place) -> dS. */
+int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, int B, int H, int T, float p_drop, uint64_t seed, void* stream);
+int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, float p_drop, uint64_t seed, void* stream);
+/* out[d, :] = sum of partial[b, :] over the rows b with index[b] == d, in row order (index_select backward for day_weights / day_bias). */
+int nsd_index_reduce(const float* partial, const int64_t* index, int B, size_t n, int n_out, float* out, void* stream);
+/* y = a*x + b;  *out = (accumulate ? *out : 0) + scale * sum(x) + add (one CTA, fixed order: the KL term of the label-smoothed loss, trainer:235-240);
+ * dlogits = dlp - exp(lp) * sum_c dlp (log_softmax backward, rows of C). */
+int nsd_axpb(const float* x, float a, float b, float* y, size_t n, void* stream);
+int nsd_sum_f32(const float* x, size_t n, float scale, float add, int accumulate, float* out, void* stream);
+int nsd_log_softmax_bwd(const float* lp, const float* dlp, float* dlogits, int64_t rows, int C, void* stream);
+/* *out = sum over all listed tensors of g^2 (clip_grad_norm_, trainer:255-257); HOST pointer tables; fixed-order two-stage reduction. */
+int nsd_sqnorm_multi(int n_tensors, const void* const* grads, const int64_t* numel, float* out, void* workspace, size_t workspace_bytes, void* stream);
+size_t nsd_sqnorm_workspace(int n_tensors, const int64_t* numel);
+/* torch.optim.AdamW semantics (trainer:144-151): p *= 1 - lr*wd; m,v EMA of g*grad_scale*clip; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * grad_sqnorm != NULL (device scalar from nsd_sqnorm_multi): clip = min(1, max_norm / (sqrt(*grad_sqnorm)*grad_scale + 1e-6)) without a host
+ * synchronisation.  Same tables and bf16 shadow rewrite as nsd_adam_step. */
+int nsd_adamw_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                   const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_scale, const float* grad_sqnorm, float max_norm, void* stream);
+
 /* Keep n_sms SMs free of the persistent tensor-core GEMM grids from now on (0 = use every SM).  New (no reference
  * counterpart): while parallel.GradSync has a gradient bucket in flight, NCCL's CTAs run on the reserved SMs instead of
  * displacing CTAs of a 148-wide persistent GEMM.  Host-side state, takes effect at the next nsd_gemm_bf16* call. */

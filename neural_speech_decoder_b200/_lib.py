@@ -49,6 +49,31 @@ SIGNATURES = {
     "nsd_log_softmax_f32": (i32, [vp, vp, i64, i32, vp]),
     "nsd_adam_step": (i32, [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, vp]),
     "nsd_set_gemm_sm_reserve": (i32, [i32]),
+    "nsd_layernorm_fwd": (i32, [vp, vp, vp, f32, i32, f32, u64, vp, vp, vp, vp, i32, i32, vp]),
+    "nsd_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, f32, u64, vp, vp, vp, i32, i32, vp, sz, vp]),
+    "nsd_layernorm_bwd_workspace": (sz, [i32, i32]),
+    "nsd_act_fwd": (i32, [vp, i32, f32, u64, vp, vp, sz, vp]),
+    "nsd_act_bwd": (i32, [vp, i32, vp, i32, f32, u64, vp, sz, vp]),
+    "nsd_glu_fwd": (i32, [vp, vp, i32, i32, vp]),
+    "nsd_glu_bwd": (i32, [vp, vp, vp, i32, i32, vp]),
+    "nsd_residual": (i32, [vp, vp, f32, f32, u64, f32, u64, i64, vp, sz, vp]),
+    "nsd_dwconv_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "nsd_dwconv_bwd_w": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
+    "nsd_dwconv_bwd_w_workspace": (sz, [i32, i32, i32]),
+    "nsd_strided_dwconv_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "nsd_strided_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
+    "nsd_strided_dwconv_bwd_workspace": (sz, [i32, i32, i32]),
+    "nsd_posenc_mask": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "nsd_bgemm": (i32, [vp, i32, i64, i64, i64, i64, vp, i32, i64, i64, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i32, i32, i32, i32, i32, f32, i32, vp]),
+    "nsd_softmax_mask_fwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, u64, vp]),
+    "nsd_softmax_mask_bwd": (i32, [vp, vp, i32, i32, i32, f32, u64, vp]),
+    "nsd_index_reduce": (i32, [vp, vp, i32, sz, i32, vp, vp]),
+    "nsd_axpb": (i32, [vp, f32, f32, vp, sz, vp]),
+    "nsd_sum_f32": (i32, [vp, sz, f32, f32, i32, vp, vp]),
+    "nsd_log_softmax_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
+    "nsd_sqnorm_multi": (i32, [i32, vp, vp, vp, vp, sz, vp]),
+    "nsd_sqnorm_workspace": (sz, [i32, vp]),
+    "nsd_adamw_step": (i32, [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp]),
     "nsd_stream_push_workspace": (sz, [i32, i32, i32, i32]),
     "nsd_stream_push": (i32, [vp, vp, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
                               vp, vp, vp, vp, vp, vp, sz, vp]),

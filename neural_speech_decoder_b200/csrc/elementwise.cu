@@ -37,8 +37,9 @@ struct AdamTable {
 };
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float wd,
-                                         float gs, float step_size, float inv_sqrt_bc2, float eps) {
-    g = fmaf(wd, p, g * gs);
+                                         float gs, float step_size, float inv_sqrt_bc2, float eps, float decay_mul) {
+    g = fmaf(wd, p, g * gs);                 // Adam: L2 term in the gradient (wd = 0 for AdamW)
+    p *= decay_mul;                          // AdamW: decoupled decay p *= 1 - lr*wd (1 for Adam)
     m = fmaf(b1, m, (1.0f - b1) * g);
     v = fmaf(b2, v, (1.0f - b2) * g * g);
     const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
@@ -46,7 +47,12 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tab, float b1, float b2, float wd, float gs,
-                                                   float step_size, float inv_sqrt_bc2, float eps) {
+                                                   float step_size, float inv_sqrt_bc2, float eps, float decay_mul,
+                                                   const float* __restrict__ grad_sqnorm, float max_norm) {
+    if (grad_sqnorm != nullptr) {            // clip_grad_norm_(max_norm): coefficient from the device-resident squared norm, no host sync
+        const float norm = sqrtf(*grad_sqnorm) * gs;
+        gs *= fminf(1.0f, max_norm / (norm + 1e-6f));
+    }
     // locate this CTA's tensor (count <= 48: linear scan by one thread is cheap, but all threads can do it)
     int ti = 0;
     while (ti + 1 < tab.count && (int)blockIdx.x >= tab.chunk_start[ti + 1]) ++ti;
@@ -62,10 +68,10 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
         for (long long i = base + 4LL * threadIdx.x; i < e4; i += 4LL * blockDim.x) {
             float4 p = *reinterpret_cast<float4*>(P + i), m = *reinterpret_cast<float4*>(M + i), v = *reinterpret_cast<float4*>(V + i);
             const float4 g = __ldcs(reinterpret_cast<const float4*>(G + i));
-            adam_one(p.x, g.x, m.x, v.x, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
-            adam_one(p.y, g.y, m.y, v.y, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
-            adam_one(p.z, g.z, m.z, v.z, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
-            adam_one(p.w, g.w, m.w, v.w, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            adam_one(p.x, g.x, m.x, v.x, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps, decay_mul);
+            adam_one(p.y, g.y, m.y, v.y, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps, decay_mul);
+            adam_one(p.z, g.z, m.z, v.z, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps, decay_mul);
+            adam_one(p.w, g.w, m.w, v.w, b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps, decay_mul);
             *reinterpret_cast<float4*>(P + i) = p; *reinterpret_cast<float4*>(M + i) = m; *reinterpret_cast<float4*>(V + i) = v;
             if (S) {
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
@@ -73,12 +79,12 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
             }
         }
         for (long long i = e4 + threadIdx.x; i < end; i += blockDim.x) {
-            adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps, decay_mul);
             if (S) S[i] = __float2bfloat16_rn(P[i]);
         }
     } else {
         for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-            adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps);
+            adam_one(P[i], G[i], M[i], V[i], b1, b2, wd, gs, step_size, inv_sqrt_bc2, eps, decay_mul);
             if (S) S[i] = __float2bfloat16_rn(P[i]);
         }
     }
@@ -123,11 +129,11 @@ int nsd_multi_copy_f32(int n_tensors, const void* const* src, void* const* dst, 
     return NSD_OK;
 }
 
-int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
-                  void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, int step, float grad_scale, void* stream) {
+static int adam_impl(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                     const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps, float wd_l2, float decay_mul,
+                     int step, float grad_scale, const float* grad_sqnorm, float max_norm, void* stream, const char* who) {
     using namespace nsd;
-    NSD_CHECK_ARG(n_tensors >= 0 && step >= 1, "adam_step: bad n_tensors=%d step=%d", n_tensors, step);
+    NSD_CHECK_ARG(n_tensors >= 0 && step >= 1, "%s: bad n_tensors=%d step=%d", who, n_tensors, step);
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     for (int t0 = 0; t0 < n_tensors; t0 += ADAM_MAX_TENSORS) {
@@ -135,7 +141,7 @@ int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, 
         tab.count = std::min(ADAM_MAX_TENSORS, n_tensors - t0);
         int chunks = 0;
         for (int i = 0; i < tab.count; ++i) {
-            NSD_CHECK_ARG(params[t0 + i] && grads[t0 + i] && exp_avg[t0 + i] && exp_avg_sq[t0 + i] && numel[t0 + i] >= 0, "adam_step: null tensor %d", t0 + i);
+            NSD_CHECK_ARG(params[t0 + i] && grads[t0 + i] && exp_avg[t0 + i] && exp_avg_sq[t0 + i] && numel[t0 + i] >= 0, "%s: null tensor %d", who, t0 + i);
             tab.p[i] = (float*)params[t0 + i]; tab.g[i] = (const float*)grads[t0 + i];
             tab.m[i] = (float*)exp_avg[t0 + i]; tab.v[i] = (float*)exp_avg_sq[t0 + i];
             tab.n[i] = numel[t0 + i];
@@ -145,10 +151,25 @@ int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, 
         }
         tab.chunk_start[tab.count] = chunks;
         if (chunks == 0) continue;
-        adam_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(tab, beta1, beta2, weight_decay, grad_scale, step_size, inv_sqrt_bc2, eps);
+        adam_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(tab, beta1, beta2, wd_l2, grad_scale, step_size, inv_sqrt_bc2, eps, decay_mul, grad_sqnorm,
+                                                               max_norm);
         NSD_LAUNCH_CHECK();
     }
     return NSD_OK;
+}
+
+int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                  void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float grad_scale, void* stream) {
+    return adam_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, shadow_bf16, lr, beta1, beta2, eps, weight_decay, 1.0f, step, grad_scale,
+                     nullptr, 0.f, stream, "adam_step");
+}
+
+int nsd_adamw_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                   const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_scale, const float* grad_sqnorm, float max_norm, void* stream) {
+    return adam_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, shadow_bf16, lr, beta1, beta2, eps, 0.f, 1.0f - lr * weight_decay, step,
+                     grad_scale, grad_sqnorm, max_norm, stream, "adamw_step");
 }
 
 int nsd_dropout(const void* x, void* out, int dtype, size_t n, float p, uint64_t seed, void* stream) {

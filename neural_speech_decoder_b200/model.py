@@ -31,6 +31,10 @@ def set_default_precision(p: str) -> None:
     _DEFAULT_PRECISION = p
 
 
+def default_precision() -> str:
+    return _DEFAULT_PRECISION
+
+
 def bf16_available() -> bool:
     """True once the tensor-core (bf16) path of the library is built in."""
     try:

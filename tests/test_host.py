@@ -117,3 +117,32 @@ def test_streaming_frame_arithmetic():
             r0, skip = window_for(j0, S, halo)
             assert r0 % S == 0 and r0 + skip * S == S * j0           # the kept frames start exactly at frame j0
             assert r0 == 0 or S * j0 - r0 >= left                    # ... with the smoothing's full left reach in the window
+
+
+def test_conformer_same_seed_same_weights_as_reference():
+    """Drop-in contract of the Conformer (SURVEY 8b applied to transformer_ctc.py:333-420): same constructor, same parameter /
+    buffer names, same RNG consumption order -> the same seed gives a bit-identical state dict, and strict load works both ways."""
+    ref_src = "/root/reference/src"
+    if not os.path.isdir(ref_src):
+        pytest.skip("the reference tree only exists in the build container")
+    import sys
+    sys.path.insert(0, ref_src)
+    from neural_decoder.transformer_ctc import NeuralTransformerCTCModel as Ref
+    kw = dict(n_channels=32, n_classes=11, n_days=3, frontend_dim=64, latent_dim=64, autoencoder_hidden_dim=32, transformer_layers=6,
+              transformer_heads=4, transformer_ff_dim=128)
+    torch.manual_seed(0)
+    a = Ref(device="cpu", **kw)
+    torch.manual_seed(0)
+    b = nsd.NeuralTransformerCTCModel(device="cpu", **kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    a.load_state_dict(sb, strict=True)
+    b.load_state_dict(sa, strict=True)
+    assert [n for n, _ in a.named_parameters()] == [n for n, _ in b.named_parameters()]
+    with pytest.raises(nsd.NsdError):
+        b(torch.zeros(2, 40, 32), torch.zeros(2, dtype=torch.int64), torch.tensor([40, 40]))      # no CPU fallback
+    x_len = torch.tensor([500, 501, 503, 504, 32, 35, 36], dtype=torch.int32)
+    c = nsd.NeuralTransformerCTCModel(device="cpu", **{**kw, "temporal_kernel": 32})
+    assert c.compute_output_lengths(x_len, 118).tolist() == [117, 117, 117, 118, 0, 0, 1]
