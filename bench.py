@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--nccl-ctas", type=int, default=int(os.environ.get("NSD_NCCL_CTAS", "0")),
                     help="N > 1 GPUs: cap NCCL at this many CTAs (NCCL_MAX_CTAS) and keep as many SMs free of the persistent GEMMs during the backward; 0 = off")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
-    ap.add_argument("--mode", default="train", choices=["train", "infer", "stream"],
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "stream", "conformer"],
                     help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32; "
                          "stream: the same model fed 4 bins (80 ms) at a time through StreamingDecoder")
     return ap.parse_args()
@@ -545,9 +545,148 @@ def run_stream(a):
         print(json.dumps(line), flush=True)
 
 
+def _conformer_batch(a, seed=1):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    B, T = a.batch, a.T
+    X = torch.randn(B, T, 256, generator=g)
+    day = torch.randint(0, 24, (B,), generator=g)
+    X_len = torch.full((B,), T, dtype=torch.int32)
+    y_len = torch.randint(10, 50, (B,), generator=g).to(torch.int32)
+    y = torch.zeros(B, int(y_len.max()), dtype=torch.int32)
+    for b in range(B):
+        y[b, :y_len[b]] = torch.randint(1, 41, (int(y_len[b]),), generator=g).to(torch.int32)
+    return X, y, X_len, y_len, day
+
+
+CONFORMER_TRAIN = dict(lr=4e-4, eps=1e-6, weight_decay=1e-3, label_smoothing=0.1, interctc_weight=0.3, max_norm=1.0)   # scripts/train_conformer.py
+
+
+def _conformer_port_step_fn(a, device, autocast_bf16=False):
+    """The reference's Conformer train step restated over torch operators (oracle/conformer_port.py; regularisers are the identity
+    there) + torch.optim.AdamW + clip_grad_norm_ (trainer:144-151, 255-259) on ``device``."""
+    import torch
+    import neural_speech_decoder_b200 as nsd
+    from oracle import conformer_port as CP
+    torch.manual_seed(0)
+    shell = nsd.NeuralTransformerCTCModel(n_channels=256, n_classes=41, n_days=24, device="cpu")      # parameter container only (same init as the reference)
+    sd = {k: v.detach().clone().to(device) for k, v in shell.state_dict().items()}
+    params = {k: sd[k].requires_grad_(True) for k, _ in shell.named_parameters()}
+    opt = torch.optim.AdamW(list(params.values()), lr=CONFORMER_TRAIN["lr"], betas=(0.9, 0.999), eps=CONFORMER_TRAIN["eps"], weight_decay=CONFORMER_TRAIN["weight_decay"])
+    X, y, X_len, y_len, day = [t.to(device) for t in _conformer_batch(a)]
+    cfg = dict(n_layers=8, n_heads=8, temporal_kernel=32, temporal_stride=4, conv_kernel=31)
+
+    def step():
+        Xn = X + torch.randn(X.shape, device=device) * NOISE["white_noise_sd"] + torch.randn([X.shape[0], 1, X.shape[2]], device=device) * NOISE["constant_offset_sd"]
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=autocast_bf16):
+            lp, olen, inter = CP.forward({**sd, **params}, Xn, day, X_len, training=True, **cfg)
+        loss = CP.training_loss(lp.float(), inter.float(), y, olen, y_len, label_smoothing=CONFORMER_TRAIN["label_smoothing"], interctc_weight=CONFORMER_TRAIN["interctc_weight"])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), max_norm=CONFORMER_TRAIN["max_norm"])
+        opt.step()
+        return loss
+    return step
+
+
+def run_conformer(a):
+    """BASELINE configs[2]: Conformer (transformer_ctc.py) train step, synthetic B=64 T=500: our CUDA path (device-resident and
+    host-in end to end), the torch-operator port on the host cores (bounded) and, with --impl reference-cuda, the port on the GPU."""
+    import torch
+    import neural_speech_decoder_b200 as nsd
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    metric = f"train utterances/sec (Conformer CTC 8x1024, B={a.batch}, T={a.T})"
+    workload = ("NeuralTransformerCTCModel 256 feats, 24 days, d=1024, 8 blocks x 8 heads, FF 2048, conv k31, k32/s4, 41 classes, dropout 0.3, "
+                "DropPath 0.1, SpecAugment, InterCTC 0.3, label smoothing 0.1; train step noise+fwd+CTC+bwd+clip+AdamW; "
+                f"B={a.batch} T={a.T} (BASELINE configs[2])")
+    if a.impl == "reference-cuda":
+        for tag, ac in (("fp32 (TF32 allowed)", False), ("bf16 autocast", True)):
+            torch.backends.cuda.matmul.allow_tf32 = True
+            step = _conformer_port_step_fn(a, dev, ac)
+            for _ in range(a.warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                step()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.steps
+            print(json.dumps({"metric": metric, "impl": "reference-cuda", "note": "torch-operator port of the reference on the GPU (cuBLAS / SDPA-free explicit attention / torch kernels); "
+                              "regularisers off in the port; the beat-this bar, never the headline ratio", "precision": tag, "value": round(a.batch / ms * 1e3, 1),
+                              "unit": "utterances/s", "ms_per_step": round(ms, 3), "steps": a.steps, "warmup": a.warmup, "config": {"workload": workload}}), flush=True)
+        return
+    nsd.set_default_precision(a.precision)
+    torch.manual_seed(0)
+    model = nsd.NeuralTransformerCTCModel(n_channels=256, n_classes=41, n_days=24, device="cuda").to(dev)
+    model.check_day_ids = False
+    opt = nsd.FusedAdamW(model.parameters(), lr=CONFORMER_TRAIN["lr"], betas=(0.9, 0.999), eps=CONFORMER_TRAIN["eps"], weight_decay=CONFORMER_TRAIN["weight_decay"],
+                         max_grad_norm=CONFORMER_TRAIN["max_norm"])
+    opt.attach_shadows(model._shadows)
+    host = _conformer_batch(a)
+    pinned = [t.pin_memory() for t in host]
+    X, y, X_len, y_len, day = [t.to(dev) for t in host]
+
+    def step(batch, i):
+        return nsd.conformer_train_step(model, opt, *batch, label_smoothing=CONFORMER_TRAIN["label_smoothing"], interctc_weight=CONFORMER_TRAIN["interctc_weight"],
+                                        white_noise_sd=NOISE["white_noise_sd"], constant_offset_sd=NOISE["constant_offset_sd"], noise_seed=1000 + i)
+    for i in range(a.warmup):
+        step((X, y, X_len, y_len, day), i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0); clocks.start()
+    n0 = nsd.lib().nsd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(a.steps):
+        loss = step((X, y, X_len, y_len, day), a.warmup + i)
+    e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / a.steps       # host time to enqueue the steps (before the synchronisation)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = (nsd.lib().nsd_launch_count() - n0) // a.steps
+    # end to end: pinned host batch -> H2D -> step -> loss read back, every step
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        batch = [t.to(dev, non_blocking=True) for t in pinned]
+        lv = step(batch, 2 * a.warmup + a.steps + i).item()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    ck = clocks.stop()
+    line = {"metric": metric, "value": round(a.batch / ms * 1e3, 1), "unit": "utterances/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3),
+            "host_enqueue_ms_per_step": round(host_ms, 3), "higher_is_better": True, "dtype": a.precision, "data": "synthetic", "config": {"workload": workload},
+            "clocks": ck, "e2e": {"value": round(a.batch / e2e_ms * 1e3, 1), "unit": "utterances/s", "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in pinned)),
+                                  "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "loss": round(float(lv), 5), "impl": "ours"}
+    if a.breakdown:
+        from neural_speech_decoder_b200 import _lib
+        _lib.profile_begin(None)
+        step((X, y, X_len, y_len, day), 9999)
+        torch.cuda.synchronize()
+        tot = 0.0
+        for k, (n, t) in sorted(_lib.profile_end().items(), key=lambda kv: -kv[1][1]):
+            print(f"  {k:28s} calls {n:5d}  {t:9.3f} ms", file=sys.stderr)
+            tot += t
+        print(f"  {'sum of entry points':28s}              {tot:9.3f} ms", file=sys.stderr)
+    if not a.no_cpu_baseline:
+        import copy
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        a2 = copy.copy(a); a2.batch = min(a.batch, 16)
+        cstep = _conformer_port_step_fn(a2, torch.device("cpu"))
+        cstep()
+        t0 = time.perf_counter(); cstep(); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": round(a2.batch / dt, 2), "unit": "utterances/s", "cores": cores, "kind": "port",
+                                "sample": f"1 timed step (after 1 warm-up) on {a2.batch} of the {a.batch} utterances, T={a.T}, torch {cores} threads; regularisers off in the port"}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     args = parse()
-    if args.mode == "stream":
+    if args.mode == "conformer":
+        run_conformer(args)
+    elif args.mode == "stream":
         run_stream(args)
     elif args.mode == "infer":
         run_infer(args)

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // backward: dx per row (warp per row) + per-CTA partial column sums of dgamma / dbeta over the CTA's rows (fixed order),
 // reduced by layernorm_param_reduce_kernel: deterministic.
-constexpr int LNB_ROWS = 64;    // rows per CTA (8 warps x 8 rows)
+constexpr int LNB_ROWS = 16;    // rows per CTA (8 warps x 2 rows): ~470 CTAs at M = 7552, three resident per SM
 
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x,
@@ -243,13 +243,17 @@ __global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------ depthwise convolution over time
 // y[b,t,d] = bias[d] + sum_j w[d][j] x[b, t + j - k/2, d]   (flip: w[d][k-1-j], the data gradient).  A thread owns one channel
 // and DW_TT consecutive frames: the input window lives in registers, the taps in shared memory (tap-major: conflict-free).
-constexpr int DW_TT = 8, DW_MAXK = 32;
+constexpr int DW_TT = 16, DW_MAXK = 32;
 __global__ void __launch_bounds__(128) dwconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ y, int T, int D, int k, int flip, int w_shared) {
-    extern __shared__ float ws[];                       // [k][128]
+    extern __shared__ float ws[];                       // [128][k] as stored (odd k: a thread's taps sit 'k' words apart -> conflict-free)
     const int d = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z, t0 = blockIdx.y * DW_TT, pad = k / 2;
-    if (d < D)
-        for (int j = 0; j < k; ++j) ws[j * 128 + threadIdx.x] = w[(w_shared ? 0 : (size_t)d * k) + (flip ? k - 1 - j : j)];
+    {
+        const int nd = min(128, D - blockIdx.x * 128);
+        const float* wsrc = w + (w_shared ? 0 : (size_t)blockIdx.x * 128 * k);
+        for (int i = threadIdx.x; i < nd * k; i += 128) ws[i] = w_shared ? wsrc[i % k] : wsrc[i];      // coalesced
+    }
+    __syncthreads();
     if (d >= D) return;
     float win[DW_TT + DW_MAXK - 1];
     const float* xb = x + (size_t)b * T * D + d;
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(128) dwconv_fwd_kernel(const float* __restrict
         float acc = bv;
 #pragma unroll
         for (int j = 0; j < DW_MAXK; ++j)
-            if (j < k) acc = fmaf(ws[j * 128 + threadIdx.x], win[tt + j], acc);
+            if (j < k) acc = fmaf(ws[threadIdx.x * k + (flip ? k - 1 - j : j)], win[tt + j], acc);
         if (t0 + tt < T) y[((size_t)b * T + t0 + tt) * D + d] = acc;
     }
 }
@@ -493,7 +497,7 @@ int nsd_dwconv_fwd(const float* x, const float* w, const float* bias, float* y, 
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
-static int dw_parts(int B) { return std::min(B, 16); }
+static int dw_parts(int B) { return std::min(B, 64); }
 size_t nsd_dwconv_bwd_w_workspace(int B, int D, int k) { return sizeof(float) * (size_t)dw_parts(std::max(B, 1)) * D * (k + 1); }
 int nsd_dwconv_bwd_w(const float* dy, const float* x, float* dw, float* db, int B, int T, int D, int k, void* workspace, size_t workspace_bytes,
                      void* stream) {
