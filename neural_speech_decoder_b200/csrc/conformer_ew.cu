@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // backward: dx per row (warp per row) + per-CTA partial column sums of dgamma / dbeta over the CTA's rows (fixed order),
 // reduced by layernorm_param_reduce_kernel: deterministic.
-constexpr int LNB_ROWS = 16;    // rows per CTA (8 warps x 2 rows): ~470 CTAs at M = 7552, three resident per SM
+constexpr int LNB_ROWS = 32;    // rows per CTA (8 warps x 4 rows): 236 CTAs at M = 7552
 
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x,
@@ -248,6 +248,13 @@ __global__ void __launch_bounds__(128) dwconv_fwd_kernel(const float* __restrict
                                                          float* __restrict__ y, int T, int D, int k, int flip, int w_shared) {
     extern __shared__ float ws[];                       // [128][k] as stored (odd k: a thread's taps sit 'k' words apart -> conflict-free)
     const int d = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z, t0 = blockIdx.y * DW_TT, pad = k / 2;
+    float win[DW_TT + DW_MAXK - 1], wreg[DW_MAXK];
+    const float* xb = x + (size_t)b * T * D + min(d, D - 1);
+#pragma unroll
+    for (int i = 0; i < DW_TT + DW_MAXK - 1; ++i) {     // the input window is requested first: it arrives while the taps are staged
+        const int t = t0 + i - pad;
+        win[i] = (i < DW_TT + k - 1 && t >= 0 && t < T) ? xb[(size_t)t * D] : 0.f;
+    }
     {
         const int nd = min(128, D - blockIdx.x * 128);
         const float* wsrc = w + (w_shared ? 0 : (size_t)blockIdx.x * 128 * k);
@@ -255,20 +262,14 @@ __global__ void __launch_bounds__(128) dwconv_fwd_kernel(const float* __restrict
     }
     __syncthreads();
     if (d >= D) return;
-    float win[DW_TT + DW_MAXK - 1];
-    const float* xb = x + (size_t)b * T * D + d;
 #pragma unroll
-    for (int i = 0; i < DW_TT + DW_MAXK - 1; ++i) {
-        const int t = t0 + i - pad;
-        win[i] = (i < DW_TT + k - 1 && t >= 0 && t < T) ? xb[(size_t)t * D] : 0.f;
-    }
+    for (int j = 0; j < DW_MAXK; ++j) wreg[j] = j < k ? ws[threadIdx.x * k + (flip ? k - 1 - j : j)] : 0.f;   // taps beyond k are zero: branch-free inner loop
     const float bv = bias ? bias[d] : 0.f;
 #pragma unroll
     for (int tt = 0; tt < DW_TT; ++tt) {
         float acc = bv;
 #pragma unroll
-        for (int j = 0; j < DW_MAXK; ++j)
-            if (j < k) acc = fmaf(ws[threadIdx.x * k + (flip ? k - 1 - j : j)], win[tt + j], acc);
+        for (int j = 0; j < DW_MAXK; ++j) acc = fmaf(wreg[j], win[tt + j], acc);
         if (t0 + tt < T) y[((size_t)b * T + t0 + tt) * D + d] = acc;
     }
 }
