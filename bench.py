@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--strong", action="store_true", help="strong scaling: --batch is the GLOBAL batch, split evenly over the GPUs (default: weak, --batch per GPU)")
     ap.add_argument("--nccl-ctas", type=int, default=int(os.environ.get("NSD_NCCL_CTAS", "0")),
                     help="N > 1 GPUs: cap NCCL at this many CTAs (NCCL_MAX_CTAS) and keep as many SMs free of the persistent GEMMs during the backward; 0 = off")
+    ap.add_argument("--graph", action="store_true", help="--mode conformer: replay the whole training step as one captured CUDA graph (GraphedConformerStep)")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
     ap.add_argument("--mode", default="train", choices=["train", "infer", "stream", "conformer"],
                     help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32; "
@@ -628,7 +629,15 @@ def run_conformer(a):
     pinned = [t.pin_memory() for t in host]
     X, y, X_len, y_len, day = [t.to(dev) for t in host]
 
+    graphed = None
+    if a.graph:
+        graphed = nsd.GraphedConformerStep(model, opt, a.batch, a.T, int(host[1].shape[1]), label_smoothing=CONFORMER_TRAIN["label_smoothing"],
+                                           interctc_weight=CONFORMER_TRAIN["interctc_weight"], white_noise_sd=NOISE["white_noise_sd"],
+                                           constant_offset_sd=NOISE["constant_offset_sd"], base_lr=CONFORMER_TRAIN["lr"], warmup_steps=1000, total_steps=15000)
+
     def step(batch, i):
+        if graphed is not None:
+            return graphed.step(*batch)
         return nsd.conformer_train_step(model, opt, *batch, label_smoothing=CONFORMER_TRAIN["label_smoothing"], interctc_weight=CONFORMER_TRAIN["interctc_weight"],
                                         white_noise_sd=NOISE["white_noise_sd"], constant_offset_sd=NOISE["constant_offset_sd"], noise_seed=1000 + i)
     for i in range(a.warmup):
@@ -645,7 +654,7 @@ def run_conformer(a):
     host_ms = (time.perf_counter() - t0) * 1e3 / a.steps       # host time to enqueue the steps (before the synchronisation)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    launches = (nsd.lib().nsd_launch_count() - n0) // a.steps
+    launches = graphed.kernels_per_replay if graphed is not None else (nsd.lib().nsd_launch_count() - n0) // a.steps
     # end to end: pinned host batch -> H2D -> step -> loss read back, every step
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -658,7 +667,8 @@ def run_conformer(a):
             "host_enqueue_ms_per_step": round(host_ms, 3), "higher_is_better": True, "dtype": a.precision, "data": "synthetic", "config": {"workload": workload},
             "clocks": ck, "e2e": {"value": round(a.batch / e2e_ms * 1e3, 1), "unit": "utterances/s", "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in pinned)),
                                   "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "loss": round(float(lv), 5), "impl": "ours"}
+            "gpu_launches": int(launches), "loss": round(float(lv), 5), "impl": "ours",
+            "form": "one captured CUDA graph per step (GraphedConformerStep)" if graphed is not None else "eager: one C-ABI call per kernel from Python autograd"}
     if a.breakdown:
         from neural_speech_decoder_b200 import _lib
         _lib.profile_begin(None)

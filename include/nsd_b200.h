@@ -225,6 +225,11 @@ int nsd_stream_push(const float* bins_in, float* rawring, int ring_rows, const i
                     const void* const* b_hh, float* h, void* h_bf16, const void* fc_w_bf16, const float* fc_b, float* logits, int* ids,
                     int* err_flag, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Device-resident seed offset (uint64, or NULL to clear): added to the seed argument of every Conformer kernel that draws a mask and of
+ * nsd_input_noise at RUN time, so that a captured CUDA graph of the training step (neural_decoder_trainer.py:181-260 as one replay)
+ * sees fresh dropout / DropPath / noise on every replay.  Host-side state, takes effect at the next launch. */
+int nsd_set_seed_offset_ptr(const void* dev_u64);
+
 /* ==== Conformer path (BASELINE configs[2]; reference src/neural_decoder/transformer_ctc.py:333-501 and the transformer branch of
  * neural_decoder_trainer.py:137-162, 206-260).  Activations are row-major [rows = B*T', D] f32 (batch-major rows b*T' + t);
  * every kernel that feeds a tensor-core GEMM can also emit the bf16 operand copy.  Stochastic regularisers are counter-based
@@ -267,8 +272,13 @@ int nsd_strided_dwconv_bwd(const float* dy, const float* x, const float* w, floa
 size_t nsd_strided_dwconv_bwd_workspace(int B, int N, int K);
 /* SpecAugment + positional encoding (transformer_ctc.py:266-308, 311-330, 467-471): out[b,t,d] = (in a masked band ? 0 : z[b,t,d]) + pe[t,d].
  * bands8 (HOST) = {f0,f1, f0,f1, t0,t1, t0,t1}: feature / frame intervals [lo,hi) set to zero for every utterance (empty: lo >= hi).
- * pe == NULL: no addition (the backward: dz = band-masked dout). */
-int nsd_posenc_mask(const float* z, const float* pe, const int* bands8, float* out, int B, int T, int D, void* stream);
+ * pe == NULL: no addition (the backward: dz = band-masked dout).  bands8_dev != NULL: the eight bounds are read from DEVICE memory
+ * instead (a captured CUDA graph of the training step draws new bands for every replay). */
+int nsd_posenc_mask(const float* z, const float* pe, const int* bands8, const int* bands8_dev, float* out, int B, int T, int D, void* stream);
+/* dst = bf16(src) (row stride ld_dst) and colsum[n] = sum_m src[m,n] from one read of the f32 [M,N] gradient: the operand copy and the
+ * bias gradient of an nn.Linear backward.  N % 4 == 0; two fixed-order stages. */
+int nsd_cast_colsum(const float* src, int M, int N, void* dst_bf16, int ld_dst, float* colsum, void* workspace, size_t workspace_bytes, void* stream);
+size_t nsd_cast_colsum_workspace(int M, int N);
 /* Strided batched GEMM  C_z[M,N] = alpha * A_z[M,K] B_z[K,N] (+ bias_z[N]),  z = (z0 < nb0, z1 < nb1):
  *   A_z(m,k) = A[z0*a_b0 + z1*a_b1 + m*a_rs + k*a_cs],  B_z(k,n) = B[zb*b_b0 + z1*b_b1 + k*b_rs + n*b_cs],  zb = b_index ? b_index[z0] : z0,
  *   C_z(m,n) = C[z0*c_b0 + z1*c_b1 + m*c_rs + n],  bias_z = bias + zb*bias_b0  (strides in elements).
@@ -295,10 +305,11 @@ int nsd_sqnorm_multi(int n_tensors, const void* const* grads, const int64_t* num
 size_t nsd_sqnorm_workspace(int n_tensors, const int64_t* numel);
 /* torch.optim.AdamW semantics (trainer:144-151): p *= 1 - lr*wd; m,v EMA of g*grad_scale*clip; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
  * grad_sqnorm != NULL (device scalar from nsd_sqnorm_multi): clip = min(1, max_norm / (sqrt(*grad_sqnorm)*grad_scale + 1e-6)) without a host
- * synchronisation.  Same tables and bf16 shadow rewrite as nsd_adam_step. */
+ * synchronisation.  hyper_dev != NULL (device float[3] = {lr/(1-b1^t), 1/sqrt(1-b2^t), 1-lr*wd}) overrides the values derived from lr / step /
+ * weight_decay: the schedule of a replayed CUDA graph.  Same tables and bf16 shadow rewrite as nsd_adam_step. */
 int nsd_adamw_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                    const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                   float grad_scale, const float* grad_sqnorm, float max_norm, void* stream);
+                   float grad_scale, const float* grad_sqnorm, float max_norm, const float* hyper_dev, void* stream);
 
 /* Keep n_sms SMs free of the persistent tensor-core GEMM grids from now on (0 = use every SM).  New (no reference
  * counterpart): while parallel.GradSync has a gradient bucket in flight, NCCL's CTAs run on the reserved SMs instead of

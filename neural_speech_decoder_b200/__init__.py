@@ -16,7 +16,7 @@ from .ctc import (CTCLoss, ctc_loss_from_logits, greedy_decode, decoded_to_lists
 from .trainer import train_step, eval_batch, make_optimizer  # noqa: F401
 from .ops import input_noise  # noqa: F401   trainer:194-201 as one kernel
 from .streaming import StreamingDecoder  # noqa: F401   stateful incremental inference (no counterpart in the reference)
-from .conformer import (NeuralTransformerCTCModel, conformer_loss, conformer_train_step, FusedAdamW, lr_lambda)  # noqa: F401   transformer_ctc.py:333-501
+from .conformer import (NeuralTransformerCTCModel, conformer_loss, conformer_train_step, FusedAdamW, lr_lambda, GraphedConformerStep)  # noqa: F401   transformer_ctc.py:333-501
 from .data import BatchPrefetcher  # noqa: F401   trainer:185-191 (H2D copies) overlapped with the previous step
 
 __version__ = "0.1.0"

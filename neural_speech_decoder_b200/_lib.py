@@ -63,7 +63,10 @@ SIGNATURES = {
     "nsd_strided_dwconv_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "nsd_strided_dwconv_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
     "nsd_strided_dwconv_bwd_workspace": (sz, [i32, i32, i32]),
-    "nsd_posenc_mask": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "nsd_posenc_mask": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "nsd_set_seed_offset_ptr": (i32, [vp]),
+    "nsd_cast_colsum": (i32, [vp, i32, i32, vp, i32, vp, vp, sz, vp]),
+    "nsd_cast_colsum_workspace": (sz, [i32, i32]),
     "nsd_bgemm": (i32, [vp, i32, i64, i64, i64, i64, vp, i32, i64, i64, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i32, i32, i32, i32, i32, f32, i32, vp]),
     "nsd_softmax_mask_fwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, u64, vp]),
     "nsd_softmax_mask_bwd": (i32, [vp, vp, i32, i32, i32, f32, u64, vp]),
@@ -73,7 +76,7 @@ SIGNATURES = {
     "nsd_log_softmax_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
     "nsd_sqnorm_multi": (i32, [i32, vp, vp, vp, vp, sz, vp]),
     "nsd_sqnorm_workspace": (sz, [i32, vp]),
-    "nsd_adamw_step": (i32, [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp]),
+    "nsd_adamw_step": (i32, [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, vp, f32, vp, vp]),
     "nsd_stream_push_workspace": (sz, [i32, i32, i32, i32]),
     "nsd_stream_push": (i32, [vp, vp, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
                               vp, vp, vp, vp, vp, vp, sz, vp]),

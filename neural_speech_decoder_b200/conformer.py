@@ -65,20 +65,26 @@ class _Linear(torch.autograd.Function):
         dx = None
         dw = torch.empty((N, K), device=dev, dtype=_f32)
         db = torch.empty((N,), device=dev, dtype=_f32)
-        ops.colsum(dy, M, N, N, db)
         if x.dtype == _bf16:
             Np = (N + 7) // 8 * 8
             if dy.dtype == _bf16 and Np == N:
                 dyb = dy
+                ops.colsum(dy, M, N, N, db)
+            elif dy.dtype == _f32 and N % 4 == 0:          # operand copy + bias gradient from one read of dy
+                dyb = torch.empty((M, Np), device=dev, dtype=_bf16)
+                ws = _ws(_lib.lib().nsd_cast_colsum_workspace(M, N), dev)
+                call("nsd_cast_colsum", ptr(dy), M, N, ptr(dyb), Np, ptr(db), ptr(ws), ws.numel(), stream())
             else:
                 dyb = torch.empty((M, Np), device=dev, dtype=_bf16)
                 ops.cast_transpose_into(dy, dyb[:, :N], None)
+                ops.colsum(dy, M, N, N, db)
             if ctx.needs_input_grad[0]:
                 dx = torch.empty((M, K), device=dev, dtype=_bf16)
                 ops.gemm(False, False, M, K, N, dyb, Np, ctx.wb, K, dx, K)
             ops.gemm(True, False, N, K, M, dyb, Np, x, K, dw, K)
         else:
             dyf = dy if dy.dtype == _f32 else dy.float()
+            ops.colsum(dyf, M, N, N, db)
             if ctx.needs_input_grad[0]:
                 dx = torch.empty((M, K), device=dev, dtype=_f32)
                 ops.gemm(False, False, M, K, N, dyf, N, w.detach(), K, dx, K)
@@ -208,23 +214,23 @@ class _Residual(torch.autograd.Function):
 
 class _PosEncMask(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, pe, bands, B, T):
+    def forward(ctx, z, pe, bands, bands_dev, B, T):
         import ctypes as C
         D = z.shape[1]
         out = torch.empty_like(z)
         arr = (C.c_int * 8)(*bands)
-        call("nsd_posenc_mask", ptr(z), ptr(pe), arr, ptr(out), B, T, D, stream())
-        ctx.cfg = (bands, B, T, D)
+        call("nsd_posenc_mask", ptr(z), ptr(pe), arr, ptr(bands_dev), ptr(out), B, T, D, stream())
+        ctx.cfg = (bands, bands_dev, B, T, D)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         import ctypes as C
-        bands, B, T, D = ctx.cfg
+        bands, bands_dev, B, T, D = ctx.cfg
         dout = dout.contiguous()
         dz = torch.empty_like(dout)
-        call("nsd_posenc_mask", ptr(dout), None, (C.c_int * 8)(*bands), ptr(dz), B, T, D, stream())
-        return dz, None, None, None, None
+        call("nsd_posenc_mask", ptr(dout), None, (C.c_int * 8)(*bands), ptr(bands_dev), ptr(dz), B, T, D, stream())
+        return dz, None, None, None, None, None
 
 
 def _bgemm(A, a_str, Bm, b_str, Cm, c_str, M, N, K, nb0, nb1, alpha=1.0, b_index=None, bias=None, bias_b0=0, a_off=0, b_off=0, c_off=0, tc=-1):
@@ -494,6 +500,7 @@ class NeuralTransformerCTCModel(nn.Module):
             raise NsdError("NeuralTransformerCTCModel (B200): the depthwise kernel must be odd and <= 32 (reference: 31)")
         self._shadows = Bf16Shadows()
         self._calls = 0
+        self._bands_dev = None             # int32[8] device array of SpecAugment bounds (set by GraphedConformerStep)
         self.check_day_ids = True          # validate day_ids like index_select does (costs a device->host sync per call; a trainer that owns its ids can switch it off)
 
     # ---------------------------------------------------------------------------------------------------------------
@@ -564,11 +571,14 @@ class NeuralTransformerCTCModel(nn.Module):
         z = self._lin(z, self.encoder.net[2], ("enc", 2))
         # SpecAugment (training) + positional encoding (transformer_ctc.py:466-471)
         D = z.shape[1]
-        bands = [0] * 8
+        bands, bands_dev = [0] * 8, None
         if self.use_spec_augment and train:
-            bands = self.spec_augment.draw(Tn, D)
+            if self._bands_dev is not None:
+                bands_dev = self._bands_dev                    # graph replay: the host writes this step's draw into the device array
+            else:
+                bands = self.spec_augment.draw(Tn, D)
         pe = self.pos_enc.pe[0, :Tn].contiguous()
-        z = _PosEncMask.apply(z, pe, tuple(bands), B, Tn)
+        z = _PosEncMask.apply(z, pe, tuple(bands), bands_dev, B, Tn)
         lens = None
         if input_lengths is not None:
             out_lengths = self.compute_output_lengths(input_lengths.to(dev), Tn)
@@ -695,6 +705,7 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_grad_norm, self.grad_scale, self.shadows = max_grad_norm, grad_scale, None
         self.grad_sqnorm: Optional[torch.Tensor] = None        # device scalar of the last step (unscaled gradients)
+        self.hyper_dev: Optional[torch.Tensor] = None          # device float[3] schedule (GraphedConformerStep); None = host values
 
     def attach_shadows(self, shadows) -> None:
         self.shadows = shadows
@@ -724,7 +735,7 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.cuda.device(dev):
                 sq = None
                 if self.max_grad_norm is not None:
-                    sq = torch.empty(1, device=dev, dtype=_f32)
+                    sq = self.grad_sqnorm if (self.hyper_dev is not None and self.grad_sqnorm is not None) else torch.empty(1, device=dev, dtype=_f32)
                     ws = _ws(_lib.lib().nsd_sqnorm_workspace(n, numel), dev)
                     call("nsd_sqnorm_multi", n, arr(gs), numel, ptr(sq), ptr(ws), ws.numel(), stream())
                     self.grad_sqnorm = sq
@@ -734,7 +745,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     sh = (C.c_void_p * n)(*[None if s is None else s.data_ptr() for s in sh_list])
                 call("nsd_adamw_step", n, arr(ps), arr(gs), arr(ms), arr(vs), numel, sh, float(group["lr"]), float(group["betas"][0]),
                      float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]), int(step), float(self.grad_scale), ptr(sq),
-                     float(self.max_grad_norm or 0.0), stream())
+                     float(self.max_grad_norm or 0.0), ptr(self.hyper_dev), stream())
             torch.autograd.graph.increment_version(ps)
             if sh_list is not None:
                 for p, s in zip(ps, sh_list):
@@ -756,3 +767,145 @@ def conformer_train_step(model, optimizer, X, y, X_len, y_len, day_idx, label_sm
     loss.backward()
     optimizer.step()
     return loss
+
+
+class GraphedConformerStep:
+    """The whole training step of the transformer branch (neural_decoder_trainer.py:181-260: noise, forward, CTC + InterCTC + label
+    smoothing, backward, gradient clipping, AdamW with the warm-up / cosine schedule) captured ONCE as a CUDA graph and replayed: one
+    launch from the host instead of ~800.  Everything that changes from step to step lives in device memory that the host refreshes
+    with one small copy before the replay: the Philox seed offset (fresh dropout / DropPath / noise masks), the SpecAugment bounds
+    (drawn on the host in the reference's order), and AdamW's step size / bias corrections / decay for the step's learning rate.
+    Shapes are static: batches must be [B, T, N] with targets padded to ``max_tgt``."""
+
+    def __init__(self, model: NeuralTransformerCTCModel, optimizer: FusedAdamW, B: int, T: int, max_tgt: int, *, label_smoothing=0.1,
+                 interctc_weight=0.3, white_noise_sd=0.0, constant_offset_sd=0.0, base_lr: Optional[float] = None, warmup_steps: int = 0,
+                 total_steps: int = 1 << 30, eager_warmup: int = 2):
+        p0 = next(model.parameters())
+        dev = p0.device
+        self.model, self.opt, self.dev = model, optimizer, dev
+        N = model.day_linear.dim
+        self.X = torch.zeros(B, T, N, device=dev)
+        self.y = torch.zeros(B, max_tgt, device=dev, dtype=torch.int32)
+        self.X_len = torch.full((B,), T, device=dev, dtype=torch.int32)
+        self.y_len = torch.ones(B, device=dev, dtype=torch.int32)
+        self.day = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.cfg = (label_smoothing, interctc_weight, white_noise_sd, constant_offset_sd)
+        self.base_lr = optimizer.param_groups[0]["lr"] if base_lr is None else base_lr
+        self.warmup_steps, self.total_steps = warmup_steps, total_steps
+        # per-step device state: [seed offset u64 | hyper f32 x3 + pad | bands i32 x8] in one 64-byte block, staged through pinned memory
+        self._state = torch.zeros(64, device=dev, dtype=torch.uint8)
+        self._stages = [torch.zeros(64, dtype=torch.uint8).pin_memory() for _ in range(4)]      # ring: the host may run a few steps ahead
+        self._stage_events = [None] * 4
+        self._seed = self._state[0:8].view(torch.int64)
+        self._hyper = self._state[8:24].view(torch.float32)
+        self._bands = self._state[24:56].view(torch.int32)
+        self.steps_done = 0
+        self.graph = None
+        self.loss = None
+        self.kernels_per_replay = 0
+        self._eager_warmup = eager_warmup
+        model.check_day_ids = False
+        model.train()
+
+    def _host_state(self):
+        import struct
+        m, g = self.model, self.opt.param_groups[0]
+        t = self.steps_done + 1
+        lr = self.base_lr * lr_lambda(self.steps_done, self.warmup_steps, self.total_steps)
+        # the same float32 / float64 arithmetic nsd_adamw_step does on the host when it gets lr, betas and step by value
+        import numpy as np
+        lr32, b1, b2 = np.float32(lr), float(np.float32(g["betas"][0])), float(np.float32(g["betas"][1]))
+        hyper = (float(np.float32(float(lr32) / (1.0 - b1 ** t))), float(np.float32(1.0 / math.sqrt(1.0 - b2 ** t))),
+                 float(np.float32(1.0) - lr32 * np.float32(g["weight_decay"])))
+        Tn = (self.X.shape[1] - m.temporal_kernel) // m.temporal_stride + 1 if m.temporal_kernel > 0 else self.X.shape[1]
+        bands = m.spec_augment.draw(Tn, m.pos_enc.pe.shape[-1]) if m.use_spec_augment else [0] * 8
+        seed = (self.steps_done * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0x7FFFFFFFFFFFFFFF
+        raw = struct.pack("<q3f4x8i8x", seed, *hyper, *bands)
+        i = self.steps_done % len(self._stages)
+        if self._stage_events[i] is not None:
+            self._stage_events[i].synchronize()             # the copy that last read this staging buffer has run
+        self._stages[i].copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        self._state.copy_(self._stages[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._stage_events[i] = ev
+        for grp in self.opt.param_groups:
+            grp["lr"] = lr
+
+    def _body(self):
+        ls, iw, wsd, csd = self.cfg
+        self.loss = conformer_train_step(self.model, self.opt, self.X, self.y, self.X_len, self.y_len, self.day, ls, iw, wsd, csd, noise_seed=12345)
+
+    def _capture(self):
+        m, opt = self.model, self.opt
+        call("nsd_set_seed_offset_ptr", ptr(self._seed))
+        m._bands_dev = self._bands if m.use_spec_augment else None
+        opt.hyper_dev = self._hyper
+        if opt.max_grad_norm is not None and opt.grad_sqnorm is None:
+            opt.grad_sqnorm = torch.zeros(1, device=self.dev, dtype=_f32)
+        # torch's capture protocol wants a few eager runs on a side stream first.  They must not count as training steps: parameters
+        # and optimizer state are snapshotted before and put back after (the bf16 operand copies are re-made from the restored weights).
+        ps = [p for grp in opt.param_groups for p in grp["params"]]
+        for p in ps:
+            st = opt.state[p]
+            if not st:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        snap = [(p.detach().clone(), opt.state[p]["exp_avg"].clone(), opt.state[p]["exp_avg_sq"].clone(), opt.state[p]["step"]) for p in ps]
+        done0 = self.steps_done
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(self._eager_warmup):
+                self._host_state()
+                self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().nsd_launch_count()
+        with torch.cuda.graph(g):
+            self._body()
+        self.kernels_per_replay = int(_lib.lib().nsd_launch_count() - n0)     # this library's kernels inside one replay
+        self.graph = g
+        with torch.no_grad():
+            for p, (w, m1, m2, st) in zip(ps, snap):
+                p.copy_(w)
+                opt.state[p]["exp_avg"].copy_(m1); opt.state[p]["exp_avg_sq"].copy_(m2); opt.state[p]["step"] = st
+                sl = opt.shadows.slice_for(p) if opt.shadows is not None else None
+                if sl is not None:
+                    ops.cast_transpose_into(p.detach(), sl, None)
+                    opt.shadows.mark_fresh(p)
+        self.steps_done = done0
+        self._host_state()
+        g.replay()                                          # the first real step
+        self.steps_done += 1
+
+    @torch.no_grad()
+    def _load(self, X, y, X_len, y_len, day):
+        if y.shape[1] > self.y.shape[1]:
+            raise RuntimeError(f"targets are padded to {y.shape[1]} > max_tgt={self.y.shape[1]} of the captured step")
+        self.X.copy_(X, non_blocking=True)
+        self.y.zero_()
+        self.y[:, :y.shape[1]].copy_(y, non_blocking=True)
+        self.X_len.copy_(X_len, non_blocking=True)
+        self.y_len.copy_(y_len, non_blocking=True)
+        self.day.copy_(day, non_blocking=True)
+
+    def step(self, X, y, X_len, y_len, day) -> torch.Tensor:
+        """One training step on the given batch (host or device tensors of the captured shapes).  Returns the loss tensor of the captured
+        graph (overwritten by the next step)."""
+        with torch.cuda.device(self.dev):
+            self._load(X, y, X_len, y_len, day)
+            if self.graph is None:
+                self._capture()
+            else:
+                self._host_state()
+                self.graph.replay()
+                self.steps_done += 1
+        return self.loss
+
+    def close(self) -> None:
+        call("nsd_set_seed_offset_ptr", None)
+        self.model._bands_dev = None
+        self.opt.hyper_dev = None

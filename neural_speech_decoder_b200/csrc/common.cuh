@@ -41,6 +41,10 @@ static inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }
 
 int sm_count();   // cached multiProcessorCount of the current device
 
+// Device-resident offset added to every Philox seed of the Conformer kernels and nsd_input_noise (nsd_set_seed_offset_ptr): lets a
+// captured CUDA graph draw fresh masks on every replay.  nullptr = none.
+const unsigned long long* seed_offset_ptr();
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 // tanh via exp, accurate to ~1e-7 relative for the fp32 parity path
 __device__ __forceinline__ float tanhf_(float x) { return tanhf(x); }

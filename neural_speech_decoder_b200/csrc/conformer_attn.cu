@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(128) bgemm_kernel(const BgemmParams p) {
 // S [rows = B*H*T, T]; row r belongs to utterance b = r / (H*T); keys j >= lens[b] are padding (-inf): P = softmax_j(S) over the valid keys.
 // Pd (optional, f32 or bf16): dropout(P) with the mask of element r*T + j.
 __global__ void __launch_bounds__(256) softmax_mask_fwd_kernel(float* __restrict__ S, void* __restrict__ Pd, int pd_dtype, const int32_t* __restrict__ lens,
-                                                               long long rows, int HT, int T, float p, uint64_t seed) {
+                                                               long long rows, int HT, int T, float p, uint64_t seed, const unsigned long long* __restrict__ seed_off) {
+    if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(256) softmax_mask_fwd_kernel(float* __restrict
 }
 // dS = P * (dP - sum_j dP_j P_j), dP = dropout-backward of dPd (in place over dPd)
 __global__ void __launch_bounds__(256) softmax_mask_bwd_kernel(const float* __restrict__ P, float* __restrict__ dPd, long long rows, int T, float p,
-                                                               uint64_t seed) {
+                                                               uint64_t seed, const unsigned long long* __restrict__ seed_off) {
+    if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -261,7 +263,7 @@ int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, 
     NSD_CHECK_ARG(S && B >= 0 && H >= 1 && T >= 1 && p_drop >= 0.f && p_drop < 1.f && (!Pd || pd_dtype == NSD_F32 || pd_dtype == NSD_BF16), "softmax_mask_fwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
-    softmax_mask_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, Pd, pd_dtype, lens, rows, H * T, T, p_drop, seed);
+    softmax_mask_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, Pd, pd_dtype, lens, rows, H * T, T, p_drop, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -269,7 +271,7 @@ int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, float 
     NSD_CHECK_ARG(P && dPd && B >= 0 && H >= 1 && T >= 1 && p_drop >= 0.f && p_drop < 1.f, "softmax_mask_bwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
-    softmax_mask_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, dPd, rows, T, p_drop, seed);
+    softmax_mask_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, dPd, rows, T, p_drop, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

@@ -59,8 +59,10 @@ constexpr int LN_MAXV = 16;     // float4s per lane: D <= 2048 (kernels are inst
 
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float eps, int act, float p, uint64_t seed, float* __restrict__ y32,
-                                                            __nv_bfloat16* __restrict__ y16, float* __restrict__ mean, float* __restrict__ rstd, int M, int D) {
+                                                            float eps, int act, float p, uint64_t seed, const unsigned long long* __restrict__ seed_off,
+                                                            float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean, float* __restrict__ rstd,
+                                                            int M, int D) {
+    if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int nv = D >> 2;
@@ -102,16 +104,22 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 constexpr int LNB_ROWS = 32;    // rows per CTA (8 warps x 4 rows): 236 CTAs at M = 7552
 
 template <int MAXV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            const float* __restrict__ mean, const float* __restrict__ rstd, int act, float p,
-                                                            uint64_t seed, float* __restrict__ dx, float* __restrict__ part, int M, int D) {
-    extern __shared__ float sm[];                      // [8 warps][2][D]
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd, int act, float p,
+                                                               uint64_t seed, const unsigned long long* __restrict__ seed_off, float* __restrict__ dx,
+                                                               float* __restrict__ part, int M, int D) {
+    if (seed_off) seed += *seed_off;
+    extern __shared__ float sm[];                      // [8 warps][2][D]: each warp's running column sums of dgamma / dbeta terms
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nv = D >> 2;
-    float4 ag[MAXV], ab[MAXV];
+    float4* sg = reinterpret_cast<float4*>(sm + (size_t)(warp * 2 + 0) * D);
+    float4* sb = reinterpret_cast<float4*>(sm + (size_t)(warp * 2 + 1) * D);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) sg[c] = sb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     for (int rr = warp; rr < LNB_ROWS; rr += 8) {
         const int row = blockIdx.x * LNB_ROWS + rr;
@@ -134,9 +142,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                     d.x *= act_grad(fmaf(xh[i].x, g.x, b.x), act); d.y *= act_grad(fmaf(xh[i].y, g.y, b.y), act);
                     d.z *= act_grad(fmaf(xh[i].z, g.z, b.z), act); d.w *= act_grad(fmaf(xh[i].w, g.w, b.w), act);
                 }
-                ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-                ag[i].x = fmaf(d.x, xh[i].x, ag[i].x); ag[i].y = fmaf(d.y, xh[i].y, ag[i].y);
-                ag[i].z = fmaf(d.z, xh[i].z, ag[i].z); ag[i].w = fmaf(d.w, xh[i].w, ag[i].w);
+                // this lane's own shared-memory slots (the same ones for every row of the warp): no conflicts, no atomics
+                float4 ab = sb[c], ag = sg[c];
+                ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+                ag.x = fmaf(d.x, xh[i].x, ag.x); ag.y = fmaf(d.y, xh[i].y, ag.y); ag.z = fmaf(d.z, xh[i].z, ag.z); ag.w = fmaf(d.w, xh[i].w, ag.w);
+                sb[c] = ab; sg[c] = ag;
                 dh[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
                 s1 += (dh[i].x + dh[i].y) + (dh[i].z + dh[i].w);
                 s2 += (dh[i].x * xh[i].x + dh[i].y * xh[i].y) + (dh[i].z * xh[i].z + dh[i].w * xh[i].w);
@@ -152,14 +162,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                 o.z = rs * (dh[i].z - s1 - xh[i].z * s2); o.w = rs * (dh[i].w - s1 - xh[i].w * s2);
                 reinterpret_cast<float4*>(dx + (size_t)row * D)[c] = o;
             }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int c = lane + 32 * i;
-        if (c < nv) {
-            reinterpret_cast<float4*>(sm + (size_t)(warp * 2 + 0) * D)[c] = ag[i];
-            reinterpret_cast<float4*>(sm + (size_t)(warp * 2 + 1) * D)[c] = ab[i];
         }
     }
     __syncthreads();
@@ -182,8 +184,9 @@ __global__ void __launch_bounds__(256) layernorm_param_reduce_kernel(const float
 }
 
 // ------------------------------------------------------------------------------------------------ activation (+dropout), GLU
-__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, int act, float p, uint64_t seed, float* __restrict__ y32,
-                                                      __nv_bfloat16* __restrict__ y16, size_t n4) {
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, int act, float p, uint64_t seed, const unsigned long long* __restrict__ seed_off,
+                                                      float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, size_t n4) {
+    if (seed_off) seed += *seed_off;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[q], k = drop4(q, p, inv_keep, seed);
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ 
     }
 }
 __global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x, int act, float p,
-                                                      uint64_t seed, float* __restrict__ dx, size_t n4) {
+                                                      uint64_t seed, const unsigned long long* __restrict__ seed_off, float* __restrict__ dx, size_t n4) {
+    if (seed_off) seed += *seed_off;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[q], k = drop4(q, p, inv_keep, seed), d = load4(dy, dy_dtype, 4 * q);
@@ -229,7 +233,9 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const float* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------ residual: out = x + scale * path[b] * drop(y)
 __global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__ x, const float* __restrict__ y, float scale, float p, uint64_t seed,
-                                                       float p_path, uint64_t path_seed, size_t elems_per_sample, float* __restrict__ out, size_t n4) {
+                                                       float p_path, uint64_t path_seed, const unsigned long long* __restrict__ seed_off, size_t elems_per_sample,
+                                                       float* __restrict__ out, size_t n4) {
+    if (seed_off) { seed += *seed_off; path_seed += *seed_off; }
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
         const float f = scale * path_factor((int)((4 * q) / elems_per_sample), p_path, path_seed);
@@ -273,32 +279,42 @@ __global__ void __launch_bounds__(128) dwconv_fwd_kernel(const float* __restrict
         if (t0 + tt < T) y[((size_t)b * T + t0 + tt) * D + d] = acc;
     }
 }
-// dw[d][j] = sum_{b,t} dy[b,t,d] x[b, t + j - k/2, d], db[d] = sum dy: CTA = (32 channels, a chunk of utterances); warp w owns taps
-// j = w, w+8, ...; per-chunk partials reduced in fixed order by dwconv_w_reduce_kernel.
-__global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part, int B,
+// dw[d][j] = sum_{b,t} dy[b,t,d] x[b, t + j - k/2, d], db[d] = sum dy: CTA = (128 channels, a chunk of utterances); per-chunk partials
+// reduced in fixed order by dwconv_w_reduce_kernel.
+__global__ void __launch_bounds__(128) dwconv_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part, int B,
                                                            int T, int D, int k, int b_per_cta) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, d = blockIdx.x * 32 + lane, pad = k / 2;
+    // thread = one channel; per 16-frame tile the gradient rows and the input window live in registers and feed all k tap sums
+    const int d = blockIdx.x * 128 + threadIdx.x, pad = k / 2;
     if (d >= D) return;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
+    float acc[DW_MAXK], accb = 0.f;
+#pragma unroll
+    for (int j = 0; j < DW_MAXK; ++j) acc[j] = 0.f;
     const int b0 = blockIdx.y * b_per_cta, b1 = min(B, b0 + b_per_cta);
     for (int b = b0; b < b1; ++b) {
         const float* dyb = dy + (size_t)b * T * D + d;
         const float* xb = x + (size_t)b * T * D + d;
-        for (int t = 0; t < T; ++t) {
-            const float g = dyb[(size_t)t * D];
-            if (warp == 0) accb += g;
+        for (int t0 = 0; t0 < T; t0 += DW_TT) {
+            float g[DW_TT], win[DW_TT + DW_MAXK - 1];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = warp + 8 * i, tx = t + j - pad;
-                if (j < k && tx >= 0 && tx < T) acc[i] = fmaf(g, xb[(size_t)tx * D], acc[i]);
+            for (int i = 0; i < DW_TT; ++i) g[i] = t0 + i < T ? dyb[(size_t)(t0 + i) * D] : 0.f;
+#pragma unroll
+            for (int i = 0; i < DW_TT + DW_MAXK - 1; ++i) {
+                const int t = t0 + i - pad;
+                win[i] = (i < DW_TT + k - 1 && t >= 0 && t < T) ? xb[(size_t)t * D] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < DW_TT; ++i) {
+                accb += g[i];
+#pragma unroll
+                for (int j = 0; j < DW_MAXK; ++j) acc[j] = fmaf(g[i], win[i + j], acc[j]);      // taps >= k see zeros of the window
             }
         }
     }
     float* pr = part + (size_t)blockIdx.y * D * (k + 1) + (size_t)d * (k + 1);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (warp + 8 * i < k) pr[warp + 8 * i] = acc[i];
-    if (warp == 0) pr[k] = accb;
+    for (int j = 0; j < DW_MAXK; ++j)
+        if (j < k) pr[j] = acc[j];
+    pr[k] = accb;
 }
 __global__ void __launch_bounds__(256) dwconv_w_reduce_kernel(const float* __restrict__ part, int nparts, int D, int k, float* __restrict__ dw,
                                                               float* __restrict__ db) {
@@ -352,8 +368,12 @@ __global__ void __launch_bounds__(256) strided_dwconv_bwd_w_kernel(const float* 
 // ------------------------------------------------------------------------------------------------ SpecAugment bands + positional encoding
 // out[b,t,d] = (masked ? 0 : z[b,t,d]) + pe[t,d] (pe == NULL: the backward, out = masked ? 0 : z); bands[8] = {f0,f1, f0,f1, t0,t1, t0,t1}
 struct Bands { int v[8]; };
-__global__ void __launch_bounds__(256) posenc_mask_kernel(const float* __restrict__ z, const float* __restrict__ pe, Bands bands, float* __restrict__ out,
-                                                          int T, int D, size_t n4) {
+__global__ void __launch_bounds__(256) posenc_mask_kernel(const float* __restrict__ z, const float* __restrict__ pe, Bands bands,
+                                                          const int* __restrict__ bands_dev, float* __restrict__ out, int T, int D, size_t n4) {
+    if (bands_dev) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bands.v[i] = bands_dev[i];
+    }
     const int d4 = D >> 2;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
         const size_t row = q / d4;
@@ -411,6 +431,41 @@ __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __res
     for (int c = lane; c < C; c += 32) dl[row * C + c] = dlp[row * C + c] - __expf(lp[row * C + c]) * s;
 }
 
+
+// bf16 copy of a f32 [M,N] gradient (the tcgen05 operand of the dgrad / wgrad GEMMs) AND its column sums (the bias gradient) from ONE
+// read: CTA = 128 columns x a chunk of rows, thread = 4 columns x every 8th row; per-chunk partial sums, reduced in fixed order.
+constexpr int CC_CHUNK_ROWS = 256;
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ src, int M, int N, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                                          float* __restrict__ part) {
+    __shared__ float4 red[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 128 + 4 * tx;
+    const int m0 = blockIdx.y * CC_CHUNK_ROWS, m1 = min(M, m0 + CC_CHUNK_ROWS);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) {
+#pragma unroll 4
+        for (int m = m0 + ty; m < m1; m += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)m * N + n);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            store_bf16x4(dst + (size_t)m * ld_dst + n, v);
+        }
+    }
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { const float4 b = red[w][tx]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        *reinterpret_cast<float4*>(part + (size_t)blockIdx.y * N + n) = a;
+    }
+}
+__global__ void __launch_bounds__(256) colsum_chunks_kernel(const float* __restrict__ part, int N, int chunks, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += part[(size_t)c * N + n];
+    out[n] = s;
+}
+
 static inline int ew_blocks(size_t n4) { return (int)std::min<size_t>(std::max<size_t>(cdivz(n4, 256), 1), (size_t)sm_count() * 16); }
 
 }  // namespace nsd
@@ -424,7 +479,7 @@ int nsd_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
     NSD_CHECK_ARG(M >= 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXV, "layernorm_fwd: bad sizes M=%d D=%d (D %% 4 == 0, D <= %d)", M, D, 128 * LN_MAXV);
     NSD_CHECK_ARG(x && gamma && beta && mean && rstd && (y_f32 || y_bf16) && act >= 0 && act <= 3 && p_drop >= 0.f && p_drop < 1.f, "layernorm_fwd: bad argument");
     if (M == 0) return NSD_OK;
-#define NSD_LN_FWD(V) layernorm_fwd_kernel<V><<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, act, p_drop, seed, y_f32, (__nv_bfloat16*)y_bf16, mean, rstd, M, D)
+#define NSD_LN_FWD(V) layernorm_fwd_kernel<V><<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, act, p_drop, seed, seed_offset_ptr(), y_f32, (__nv_bfloat16*)y_bf16, mean, rstd, M, D)
     if (D <= 512) NSD_LN_FWD(4); else if (D <= 1024) NSD_LN_FWD(8); else NSD_LN_FWD(16);
 #undef NSD_LN_FWD
     NSD_LAUNCH_CHECK();
@@ -442,7 +497,7 @@ int nsd_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
 #define NSD_LN_BWD(V)                                                                                                                      \
     do {                                                                                                                                   \
         if (smem > 48 * 1024) NSD_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        layernorm_bwd_kernel<V><<<parts, 256, smem, (cudaStream_t)stream>>>(dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, dx,    \
+        layernorm_bwd_kernel<V><<<parts, 256, smem, (cudaStream_t)stream>>>(dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(), dx, \
                                                                             (float*)workspace, M, D);                                      \
     } while (0)
     if (D <= 512) NSD_LN_BWD(4); else if (D <= 1024) NSD_LN_BWD(8); else NSD_LN_BWD(16);
@@ -456,14 +511,14 @@ int nsd_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
 int nsd_act_fwd(const float* x, int act, float p_drop, uint64_t seed, float* y_f32, void* y_bf16, size_t n, void* stream) {
     NSD_CHECK_ARG(x && (y_f32 || y_bf16) && n % 4 == 0 && act >= 0 && act <= 3 && p_drop >= 0.f && p_drop < 1.f, "act_fwd: bad argument (n %% 4 == 0)");
     if (n == 0) return NSD_OK;
-    act_fwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, act, p_drop, seed, y_f32, (__nv_bfloat16*)y_bf16, n / 4);
+    act_fwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, act, p_drop, seed, seed_offset_ptr(), y_f32, (__nv_bfloat16*)y_bf16, n / 4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_act_bwd(const void* dy, int dy_dtype, const float* x, int act, float p_drop, uint64_t seed, float* dx, size_t n, void* stream) {
     NSD_CHECK_ARG(dy && x && dx && n % 4 == 0 && act >= 0 && act <= 3 && (dy_dtype == NSD_F32 || dy_dtype == NSD_BF16), "act_bwd: bad argument");
     if (n == 0) return NSD_OK;
-    act_bwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, act, p_drop, seed, dx, n / 4);
+    act_bwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, act, p_drop, seed, seed_offset_ptr(), dx, n / 4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -486,7 +541,7 @@ int nsd_residual(const float* x, const float* y, float scale, float p_drop, uint
     NSD_CHECK_ARG(y && out && n % 4 == 0 && elems_per_sample > 0 && elems_per_sample % 4 == 0 && p_drop >= 0.f && p_drop < 1.f && p_path >= 0.f && p_path < 1.f,
                   "residual: bad argument");
     if (n == 0) return NSD_OK;
-    residual_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, y, scale, p_drop, seed, p_path, path_seed, (size_t)elems_per_sample, out, n / 4);
+    residual_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, y, scale, p_drop, seed, p_path, path_seed, seed_offset_ptr(), (size_t)elems_per_sample, out, n / 4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -505,7 +560,7 @@ int nsd_dwconv_bwd_w(const float* dy, const float* x, float* dw, float* db, int 
     NSD_CHECK_ARG(dy && x && dw && B >= 1 && T > 0 && D > 0 && k >= 1 && k <= DW_MAXK && (k & 1), "dwconv_bwd_w: bad argument");
     if (!workspace || workspace_bytes < nsd_dwconv_bwd_w_workspace(B, D, k)) { set_error("dwconv_bwd_w: workspace too small"); return NSD_ERR_WORKSPACE; }
     const int parts = dw_parts(B), per = cdiv(B, parts);
-    dwconv_bwd_w_kernel<<<dim3(cdiv(D, 32), cdiv(B, per)), 256, 0, (cudaStream_t)stream>>>(dy, x, (float*)workspace, B, T, D, k, per);
+    dwconv_bwd_w_kernel<<<dim3(cdiv(D, 128), cdiv(B, per)), 128, 0, (cudaStream_t)stream>>>(dy, x, (float*)workspace, B, T, D, k, per);
     NSD_LAUNCH_CHECK();
     dwconv_w_reduce_kernel<<<cdiv(D * (k + 1), 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, cdiv(B, per), D, k, dw, db);
     NSD_LAUNCH_CHECK();
@@ -533,13 +588,24 @@ int nsd_strided_dwconv_bwd(const float* dy, const float* x, const float* w, floa
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
-int nsd_posenc_mask(const float* z, const float* pe, const int* bands8, float* out, int B, int T, int D, void* stream) {
-    NSD_CHECK_ARG(z && out && bands8 && B >= 0 && T > 0 && D > 0 && D % 4 == 0, "posenc_mask: bad argument");
+size_t nsd_cast_colsum_workspace(int M, int N) { return sizeof(float) * (size_t)cdiv(std::max(M, 1), CC_CHUNK_ROWS) * (size_t)std::max(N, 1); }
+int nsd_cast_colsum(const float* src, int M, int N, void* dst_bf16, int ld_dst, float* colsum, void* workspace, size_t workspace_bytes, void* stream) {
+    NSD_CHECK_ARG(src && dst_bf16 && colsum && M >= 1 && N >= 4 && N % 4 == 0 && ld_dst >= N && ld_dst % 4 == 0, "cast_colsum: bad argument (N %% 4 == 0)");
+    if (!workspace || workspace_bytes < nsd_cast_colsum_workspace(M, N)) { set_error("cast_colsum: workspace too small"); return NSD_ERR_WORKSPACE; }
+    const int chunks = cdiv(M, CC_CHUNK_ROWS);
+    cast_colsum_kernel<<<dim3(cdiv(N, 128), chunks), 256, 0, (cudaStream_t)stream>>>(src, M, N, (__nv_bfloat16*)dst_bf16, ld_dst, (float*)workspace);
+    NSD_LAUNCH_CHECK();
+    colsum_chunks_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, N, chunks, colsum);
+    NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+int nsd_posenc_mask(const float* z, const float* pe, const int* bands8, const int* bands8_dev, float* out, int B, int T, int D, void* stream) {
+    NSD_CHECK_ARG(z && out && (bands8 || bands8_dev) && B >= 0 && T > 0 && D > 0 && D % 4 == 0, "posenc_mask: bad argument");
     if (B == 0) return NSD_OK;
     Bands bd;
-    for (int i = 0; i < 8; ++i) bd.v[i] = bands8[i];
+    for (int i = 0; i < 8; ++i) bd.v[i] = bands8 ? bands8[i] : 0;
     const size_t n4 = (size_t)B * T * D / 4;
-    posenc_mask_kernel<<<ew_blocks(n4), 256, 0, (cudaStream_t)stream>>>(z, pe, bd, out, T, D, n4);
+    posenc_mask_kernel<<<ew_blocks(n4), 256, 0, (cudaStream_t)stream>>>(z, pe, bd, bands8_dev, out, T, D, n4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

@@ -48,7 +48,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tab, float b1, float b2, float wd, float gs,
                                                    float step_size, float inv_sqrt_bc2, float eps, float decay_mul,
-                                                   const float* __restrict__ grad_sqnorm, float max_norm) {
+                                                   const float* __restrict__ grad_sqnorm, float max_norm, const float* __restrict__ hyper) {
+    if (hyper != nullptr) { step_size = hyper[0]; inv_sqrt_bc2 = hyper[1]; decay_mul = hyper[2]; }   // device-resident schedule (graph replay)
     if (grad_sqnorm != nullptr) {            // clip_grad_norm_(max_norm): coefficient from the device-resident squared norm, no host sync
         const float norm = sqrtf(*grad_sqnorm) * gs;
         gs *= fminf(1.0f, max_norm / (norm + 1e-6f));
@@ -131,7 +132,7 @@ int nsd_multi_copy_f32(int n_tensors, const void* const* src, void* const* dst, 
 
 static int adam_impl(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                      const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps, float wd_l2, float decay_mul,
-                     int step, float grad_scale, const float* grad_sqnorm, float max_norm, void* stream, const char* who) {
+                     int step, float grad_scale, const float* grad_sqnorm, float max_norm, const float* hyper, void* stream, const char* who) {
     using namespace nsd;
     NSD_CHECK_ARG(n_tensors >= 0 && step >= 1, "%s: bad n_tensors=%d step=%d", who, n_tensors, step);
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
@@ -152,7 +153,7 @@ static int adam_impl(int n_tensors, void* const* params, const void* const* grad
         tab.chunk_start[tab.count] = chunks;
         if (chunks == 0) continue;
         adam_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(tab, beta1, beta2, wd_l2, grad_scale, step_size, inv_sqrt_bc2, eps, decay_mul, grad_sqnorm,
-                                                               max_norm);
+                                                               max_norm, hyper);
         NSD_LAUNCH_CHECK();
     }
     return NSD_OK;
@@ -162,14 +163,14 @@ int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, 
                   void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream) {
     return adam_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, shadow_bf16, lr, beta1, beta2, eps, weight_decay, 1.0f, step, grad_scale,
-                     nullptr, 0.f, stream, "adam_step");
+                     nullptr, 0.f, nullptr, stream, "adam_step");
 }
 
 int nsd_adamw_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                    const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                   float grad_scale, const float* grad_sqnorm, float max_norm, void* stream) {
+                   float grad_scale, const float* grad_sqnorm, float max_norm, const float* hyper_dev, void* stream) {
     return adam_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, shadow_bf16, lr, beta1, beta2, eps, 0.f, 1.0f - lr * weight_decay, step,
-                     grad_scale, grad_sqnorm, max_norm, stream, "adamw_step");
+                     grad_scale, grad_sqnorm, max_norm, hyper_dev, stream, "adamw_step");
 }
 
 int nsd_dropout(const void* x, void* out, int dtype, size_t n, float p, uint64_t seed, void* stream) {

@@ -707,7 +707,8 @@ __global__ void day_segment_reduce_kernel(const float* __restrict__ pw, const fl
 
 // stand-alone form of the augmentation (same values as the fused path): out = x + white + offset
 __global__ void input_noise_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int T, int N, float white_sd, float offset_sd,
-                                   unsigned long long seed) {
+                                   unsigned long long seed, const unsigned long long* __restrict__ seed_off) {
+    if (seed_off) seed += *seed_off;
     const size_t total = (size_t)B * T * N;
     if ((N & 3) == 0) {
         for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total / 4; q += (size_t)gridDim.x * blockDim.x) {
@@ -791,7 +792,7 @@ int nsd_input_noise(const float* x, float* out, int B, int T, int N, float white
     if (total == 0) return NSD_OK;
     NSD_CHECK_ARG((N & 3) != 0 || ((((uintptr_t)x | (uintptr_t)out) & 15) == 0), "input_noise: x/out must be 16-byte aligned");
     const int blocks = (int)std::min<size_t>(cdivz(cdivz(total, 4), 256), (size_t)sm_count() * 16);
-    input_noise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, B, T, N, white_noise_sd, constant_offset_sd, seed);
+    input_noise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, B, T, N, white_noise_sd, constant_offset_sd, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

@@ -9,6 +9,8 @@ static thread_local char g_err[512] = "";
 
 unsigned long long launches();
 
+void set_seed_offset_ptr(const unsigned long long* p);
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -32,11 +34,20 @@ int sm_count() {
     return cached[dev];
 }
 
+static const unsigned long long* g_seed_off = nullptr;
+const unsigned long long* seed_offset_ptr() { return g_seed_off; }
+void set_seed_offset_ptr(const unsigned long long* p) { g_seed_off = p; }
+
 }  // namespace nsd
 
 extern "C" {
 
 int nsd_version(void) { return 100; }   // 0.1.0
+
+int nsd_set_seed_offset_ptr(const void* dev_u64) {
+    nsd::set_seed_offset_ptr(reinterpret_cast<const unsigned long long*>(dev_u64));
+    return NSD_OK;
+}
 
 unsigned long long nsd_launch_count(void) { return nsd::launches(); }
 

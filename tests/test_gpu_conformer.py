@@ -168,3 +168,40 @@ def test_conformer_competition_architecture_vs_port(precision, B):
         assert e_lp < 1e-5 and e_in < 1e-5 and e_loss < 1e-6 and worst < 5e-5      # measured 2.2e-6 / 3.1e-6 / 1.1e-7 / 1.4e-5
     else:
         assert e_lp < 0.03 and e_in < 0.03 and e_loss < 3e-4 and worst < 0.13       # measured 8.4e-3 / 8.2e-3 / 6.7e-5 / 4.3e-2 (temporal_conv.weight: sums 7.5k frames of bf16-rounded terms)
+
+
+def test_graphed_step_equals_eager_steps_and_redraws_masks():
+    """GraphedConformerStep (the whole training step as one replayed CUDA graph, per-step state in device memory): with the regularisers
+    off, three graphed steps leave exactly the parameters three eager steps leave (same kernels, same order, warm-up / cosine lr from
+    the device-resident schedule); with dropout on and lr = 0, two replays of the same batch give different losses (fresh masks)."""
+    name = "conformer_small"
+    g, sd = _load(name)
+    X, day = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["day"]).to(DEV)
+    X_len, y, y_len = torch.from_numpy(g["X_len"]).to(DEV), torch.from_numpy(g["y"]).to(DEV), torch.from_numpy(g["y_len"]).to(DEV)
+    B, T = X.shape[0], X.shape[1]
+    kw = dict(lr=4e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-3, max_grad_norm=1.0)
+    a, b = _build(name, "bf16", sd), _build(name, "bf16", sd)
+    oa, ob = nsd.FusedAdamW(a.parameters(), **kw), nsd.FusedAdamW(b.parameters(), **kw)
+    oa.attach_shadows(a._shadows); ob.attach_shadows(b._shadows)
+    a.check_day_ids = False
+    for step in range(3):                                                  # eager reference
+        for grp in oa.param_groups:
+            grp["lr"] = 4e-4 * nsd.lr_lambda(step, 2, 10)
+        la = nsd.conformer_train_step(a, oa, X, y, X_len, y_len, day, 0.1, 0.3)
+    gs = nsd.GraphedConformerStep(b, ob, B, T, int(y.shape[1]), label_smoothing=0.1, interctc_weight=0.3, base_lr=4e-4, warmup_steps=2, total_steps=10)
+    for step in range(3):
+        lb = gs.step(X, y, X_len, y_len, day)
+    torch.cuda.synchronize()
+    assert gs.graph is not None and gs.kernels_per_replay > 100 and gs.steps_done == 3
+    assert abs(la.item() - lb.item()) < 1e-6 * abs(la.item())
+    for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(p, q), k
+    gs.close()
+    # fresh masks on every replay
+    cfg = dict(CFG[name]); cfg.update(transformer_dropout=0.3, drop_path_prob=0.1, use_spec_augment=True, spec_augment_freq_mask=20, spec_augment_time_mask=4)
+    c = nsd.NeuralTransformerCTCModel(device="cuda", precision="bf16", **cfg).to(DEV)
+    oc = nsd.FusedAdamW(c.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0)
+    gc = nsd.GraphedConformerStep(c, oc, B, T, int(y.shape[1]), base_lr=0.0, white_noise_sd=0.8, constant_offset_sd=0.2)
+    losses = [gc.step(X, y, X_len, y_len, day).item() for _ in range(4)]
+    gc.close()
+    assert len(set(round(v, 6) for v in losses)) == 4, losses
