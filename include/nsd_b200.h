@@ -289,10 +289,11 @@ size_t nsd_cast_colsum_workspace(int M, int N);
 int nsd_bgemm(const void* A, int a_dtype, int64_t a_rs, int64_t a_cs, int64_t a_b0, int64_t a_b1, const void* B, int b_dtype, int64_t b_rs, int64_t b_cs,
               int64_t b_b0, int64_t b_b1, const int64_t* b_index, void* C, int c_dtype, int64_t c_rs, int64_t c_b0, int64_t c_b1, const float* bias,
               int64_t bias_b0, int M, int N, int K, int nb0, int nb1, float alpha, int tc_mode, void* stream);
-/* Attention weights: S [B*H*T, T] f32 scores, in place -> P = softmax over the keys j < lens[b] (key_padding_mask, transformer_ctc.py:250, 475-477;
+/* Attention weights: S [B*H*T rows of T scores, row stride ld >= T (a multiple of 8 keeps the rows 16-byte aligned for nsd_bgemm;
+ * the padding columns are written as zeros)] f32, in place -> P = softmax over the keys j < lens[b] (key_padding_mask, transformer_ctc.py:250, 475-477;
  * lens == NULL: no mask); Pd (optional, f32 or bf16) = dropout_p(P) (nn.MultiheadAttention(dropout=p), :216).  Backward: dPd (in place) -> dS. */
-int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, int B, int H, int T, float p_drop, uint64_t seed, void* stream);
-int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, float p_drop, uint64_t seed, void* stream);
+int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, int B, int H, int T, int ld, float p_drop, uint64_t seed, void* stream);
+int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, int ld, float p_drop, uint64_t seed, void* stream);
 /* out[d, :] = sum of partial[b, :] over the rows b with index[b] == d, in row order (index_select backward for day_weights / day_bias). */
 int nsd_index_reduce(const float* partial, const int64_t* index, int B, size_t n, int n_out, float* out, void* stream);
 /* y = a*x + b;  *out = (accumulate ? *out : 0) + scale * sum(x) + add (one CTA, fixed order: the KL term of the label-smoothed loss, trainer:235-240);

@@ -68,8 +68,8 @@ SIGNATURES = {
     "nsd_cast_colsum": (i32, [vp, i32, i32, vp, i32, vp, vp, sz, vp]),
     "nsd_cast_colsum_workspace": (sz, [i32, i32]),
     "nsd_bgemm": (i32, [vp, i32, i64, i64, i64, i64, vp, i32, i64, i64, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i32, i32, i32, i32, i32, f32, i32, vp]),
-    "nsd_softmax_mask_fwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, u64, vp]),
-    "nsd_softmax_mask_bwd": (i32, [vp, vp, i32, i32, i32, f32, u64, vp]),
+    "nsd_softmax_mask_fwd": (i32, [vp, vp, i32, vp, i32, i32, i32, i32, f32, u64, vp]),
+    "nsd_softmax_mask_bwd": (i32, [vp, vp, i32, i32, i32, i32, f32, u64, vp]),
     "nsd_index_reduce": (i32, [vp, vp, i32, sz, i32, vp, vp]),
     "nsd_axpb": (i32, [vp, f32, f32, vp, sz, vp]),
     "nsd_sum_f32": (i32, [vp, sz, f32, f32, i32, vp, vp]),

@@ -250,39 +250,40 @@ class _Attention(torch.autograd.Function):
         D = qkv.shape[1] // 3
         dh = D // H
         dev = qkv.device
-        S = torch.empty((B * H * T, T), device=dev, dtype=_f32)
+        Tp = (T + 7) // 8 * 8                      # row stride of the score matrices: rows stay 16-byte aligned for the batched GEMM's vector loads
+        S = torch.empty((B * H * T, Tp), device=dev, dtype=_f32)
         sc = 1.0 / math.sqrt(dh)
-        _bgemm(qkv, (3 * D, 1, T * 3 * D, dh), qkv, (1, 3 * D, T * 3 * D, dh), S, (T, H * T * T, T * T), T, T, dh, B, H, alpha=sc, b_off=D)
+        _bgemm(qkv, (3 * D, 1, T * 3 * D, dh), qkv, (1, 3 * D, T * 3 * D, dh), S, (Tp, H * T * Tp, T * Tp), T, T, dh, B, H, alpha=sc, b_off=D)
         lowp = qkv.dtype == _bf16
-        Pd = torch.empty((B * H * T, T), device=dev, dtype=qkv.dtype) if (p > 0 or lowp) else None
-        call("nsd_softmax_mask_fwd", ptr(S), ptr(Pd), _code(qkv.dtype), ptr(lens), B, H, T, float(p), int(seed), stream())
+        Pd = torch.empty((B * H * T, Tp), device=dev, dtype=qkv.dtype) if (p > 0 or lowp) else None
+        call("nsd_softmax_mask_fwd", ptr(S), ptr(Pd), _code(qkv.dtype), ptr(lens), B, H, T, Tp, float(p), int(seed), stream())
         o = torch.empty((B * T, D), device=dev, dtype=qkv.dtype)
         Pv = Pd if Pd is not None else S
-        _bgemm(Pv, (T, 1, H * T * T, T * T), qkv, (3 * D, 1, T * 3 * D, dh), o, (D, T * D, dh), T, dh, T, B, H, b_off=2 * D)
+        _bgemm(Pv, (Tp, 1, H * T * Tp, T * Tp), qkv, (3 * D, 1, T * 3 * D, dh), o, (D, T * D, dh), T, dh, T, B, H, b_off=2 * D)
         ctx.save_for_backward(qkv, S, Pv)
-        ctx.cfg = (B, T, H, D, dh, p, seed, sc)
+        ctx.cfg = (B, T, Tp, H, D, dh, p, seed, sc)
         return o
 
     @staticmethod
     def backward(ctx, do):
         qkv, P, Pv = ctx.saved_tensors
-        B, T, H, D, dh, p, seed, sc = ctx.cfg
+        B, T, Tp, H, D, dh, p, seed, sc = ctx.cfg
         dev = qkv.device
         do = do.contiguous()
         dqkv = torch.empty_like(qkv)
         # dV = Pd^T dO
-        _bgemm(Pv, (1, T, H * T * T, T * T), do, (D, 1, T * D, dh), dqkv, (3 * D, T * 3 * D, dh), T, dh, T, B, H, c_off=2 * D)
+        _bgemm(Pv, (1, Tp, H * T * Tp, T * Tp), do, (D, 1, T * D, dh), dqkv, (3 * D, T * 3 * D, dh), T, dh, T, B, H, c_off=2 * D)
         # dPd = dO V^T  -> dS (in place)
-        dS = torch.empty((B * H * T, T), device=dev, dtype=_f32)
-        _bgemm(do, (D, 1, T * D, dh), qkv, (1, 3 * D, T * 3 * D, dh), dS, (T, H * T * T, T * T), T, T, dh, B, H, b_off=2 * D)
-        call("nsd_softmax_mask_bwd", ptr(P), ptr(dS), B, H, T, float(p), int(seed), stream())
+        dS = torch.empty((B * H * T, Tp), device=dev, dtype=_f32)
+        _bgemm(do, (D, 1, T * D, dh), qkv, (1, 3 * D, T * 3 * D, dh), dS, (Tp, H * T * Tp, T * Tp), T, T, dh, B, H, b_off=2 * D)
+        call("nsd_softmax_mask_bwd", ptr(P), ptr(dS), B, H, T, Tp, float(p), int(seed), stream())
         dSo = dS
         if qkv.dtype == _bf16:             # bf16 operand for the two products below (tensor-core path)
-            dSo = torch.empty((B * H * T, T), device=dev, dtype=_bf16)
+            dSo = torch.empty((B * H * T, Tp), device=dev, dtype=_bf16)
             call("nsd_cast", ptr(dS), F32, ptr(dSo), BF16, dS.numel(), stream())
         # dQ = sc * dS K ; dK = sc * dS^T Q
-        _bgemm(dSo, (T, 1, H * T * T, T * T), qkv, (3 * D, 1, T * 3 * D, dh), dqkv, (3 * D, T * 3 * D, dh), T, dh, T, B, H, alpha=sc, b_off=D)
-        _bgemm(dSo, (1, T, H * T * T, T * T), qkv, (3 * D, 1, T * 3 * D, dh), dqkv, (3 * D, T * 3 * D, dh), T, dh, T, B, H, alpha=sc, c_off=D)
+        _bgemm(dSo, (Tp, 1, H * T * Tp, T * Tp), qkv, (3 * D, 1, T * 3 * D, dh), dqkv, (3 * D, T * 3 * D, dh), T, dh, T, B, H, alpha=sc, b_off=D)
+        _bgemm(dSo, (1, Tp, H * T * Tp, T * Tp), qkv, (3 * D, 1, T * 3 * D, dh), dqkv, (3 * D, T * 3 * D, dh), T, dh, T, B, H, alpha=sc, c_off=D)
         return dqkv, None, None, None, None, None, None
 
 

@@ -29,24 +29,131 @@ __device__ __forceinline__ float ld_elem(const void* p, int dtype, long long i) 
 
 constexpr int BG_T = 64, BG_K = 32, BG_PAD = 8;
 
-// loads a [64 rows x 32 k] tile of an operand addressed as base[row*rs + k*cs] into smem[row][k] (zero outside), threads
-// walking the contiguous direction of the source
+// loads a [64 rows x 32 k] tile of an operand addressed as base[row*rs + k*cs] into smem[row][k] (zero outside).  Tensor-core path:
+// 16-byte global loads along whichever direction is contiguous in the source (8 bf16 / 4 f32 per load; chunks that straddle the
+// matrix edge or are misaligned fall back to element loads), so Q, K, V, P and dS tiles cost 2-4 load instructions per thread instead
+// of 16.  FFMA (fp32 parity) path: element loads, threads walking the contiguous direction.
+struct BgTileSrc {                       // how one operand's [64 x 32] tiles are fetched (fixed for the kernel)
+    const void* base; long long rs, cs; int dtype, nrows, K, V, nc, no, nc_sh, no_sh, v_sh, per_thread; bool along_k, vec_ok;
+};
+__device__ __forceinline__ BgTileSrc bg_src(const void* base, int dtype, long long rs, long long cs, int row0, int nrows, int K) {
+    BgTileSrc t;
+    t.base = base; t.rs = rs; t.cs = cs; t.dtype = dtype; t.nrows = nrows; t.K = K;
+    t.along_k = (cs == 1) || (rs != 1);
+    t.V = dtype == NSD_F32 ? 4 : 8;
+    const size_t es = dtype == NSD_F32 ? 4 : 2;
+    const long long ostr = t.along_k ? rs : cs;
+    // every tile starts at (row0, multiple of 32): alignment of the first one decides for all
+    t.vec_ok = (t.along_k ? cs == 1 : rs == 1) && (ostr % t.V) == 0 && ((reinterpret_cast<uintptr_t>(base) + (size_t)((long long)row0 * rs) * es) & 15) == 0;
+    t.nc = t.along_k ? BG_K / t.V : BG_T / t.V;
+    t.no = t.along_k ? BG_T : BG_K;
+    t.nc_sh = 31 - __clz(t.nc); t.no_sh = 31 - __clz(t.no); t.v_sh = 31 - __clz(t.V);      // all powers of two: shifts, no divisions
+    t.per_thread = t.nc * t.no / 128;            // 2 (bf16) or 4 (f32)
+    return t;
+}
+__device__ __forceinline__ void bg_chunk_coords(const BgTileSrc& t, int c, int& r, int& k) {
+    // consecutive threads take consecutive positions of the OTHER direction when the chunks run along the rows (their shared-memory stores
+    // then fall into consecutive k: conflict-free), and consecutive chunks of a row when they run along k
+    const int ci = t.along_k ? (c & (t.nc - 1)) : (c >> t.no_sh), oi = t.along_k ? (c >> t.nc_sh) : (c & (t.no - 1));
+    r = t.along_k ? oi : (ci << t.v_sh);
+    k = t.along_k ? (ci << t.v_sh) : oi;
+}
+// Per-thread chunk state, computed once per CTA: where each of the thread's (up to 4) 16-byte chunks of a k-tile comes from and goes to.
+// The k-loop then costs one pointer add + one predicated 16-byte load per chunk (chunks at the matrix edge take the element-wise path).
+struct BgThread {
+    const char* gp[4];        // address of the chunk in the first k-tile
+    int r[4], k[4];           // tile coordinates
+    bool fixed_ok[4];         // fast path possible as far as the row direction is concerned
+};
+__device__ __forceinline__ void bg_thread_init(const BgTileSrc& t, int row0, int tid, BgThread& th) {
+    const size_t es = t.dtype == NSD_F32 ? 4 : 2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        th.gp[q] = nullptr; th.r[q] = th.k[q] = 0; th.fixed_ok[q] = false;
+        if (q < t.per_thread) {
+            bg_chunk_coords(t, tid + 128 * q, th.r[q], th.k[q]);
+            th.gp[q] = reinterpret_cast<const char*>(t.base) + (size_t)((long long)(row0 + th.r[q]) * t.rs + (long long)th.k[q] * t.cs) * es;
+            th.fixed_ok[q] = t.vec_ok && (t.along_k ? row0 + th.r[q] < t.nrows : row0 + th.r[q] + t.V <= t.nrows);
+        }
+    }
+}
+// element-wise fetch of one chunk that touches the matrix edge (or of a misaligned operand); zeros outside
+__device__ __noinline__ uint4 bg_fetch_slow(const BgTileSrc t, int row0, int k0, int r, int k) {
+    const int lim = t.along_k ? t.K - (k0 + k) : t.nrows - (row0 + r);
+    const bool other_ok = t.along_k ? row0 + r < t.nrows : k0 + k < t.K;
+    const int n = other_ok ? max(0, min(t.V, lim)) : 0;
+    const long long e0 = (long long)(row0 + r) * t.rs + (long long)(k0 + k) * t.cs, st = t.along_k ? t.cs : t.rs;
+    if (t.dtype == NSD_F32) {
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < n) f[i] = reinterpret_cast<const float*>(t.base)[e0 + (long long)i * st];
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+    unsigned short h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < n) h[i] = reinterpret_cast<const unsigned short*>(t.base)[e0 + (long long)i * st];
+    return make_uint4(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16), h[4] | ((uint32_t)h[5] << 16), h[6] | ((uint32_t)h[7] << 16));
+}
+// request this thread's chunks of the tile at (row0, k0) into registers (raw 16 bytes per chunk)
+__device__ __forceinline__ void bg_fetch(const BgTileSrc& t, const BgThread& th, int row0, int k0, size_t kbytes, uint4 (&raw)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q < t.per_thread) {
+            const bool k_ok = t.along_k ? k0 + th.k[q] + t.V <= t.K : k0 + th.k[q] < t.K;
+            if (th.fixed_ok[q] && k_ok) raw[q] = *reinterpret_cast<const uint4*>(th.gp[q] + kbytes);
+            else raw[q] = bg_fetch_slow(t, row0, k0, th.r[q], th.k[q]);
+        }
+    }
+}
+// registers -> shared memory [row][k] as bf16 (elements beyond the matrix edge were fetched as zeros)
+__device__ __forceinline__ void bg_commit(const BgTileSrc& t, const BgThread& th, __nv_bfloat16 (*sm)[BG_K + BG_PAD], const uint4 (&raw)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q < t.per_thread) {
+            const int r = th.r[q], k = th.k[q];
+            if (t.dtype == NSD_F32) {
+                const float f[4] = {__uint_as_float(raw[q].x), __uint_as_float(raw[q].y), __uint_as_float(raw[q].z), __uint_as_float(raw[q].w)};
+                if (t.along_k) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+                    *reinterpret_cast<uint2*>(&sm[r][k]) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sm[r + i][k] = __float2bfloat16_rn(f[i]);
+                }
+            } else if (t.along_k) {
+                *reinterpret_cast<uint4*>(&sm[r][k]) = raw[q];
+            } else {
+                const uint32_t w[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned short h = (unsigned short)(w[i >> 1] >> (16 * (i & 1)));
+                    sm[r + i][k] = *reinterpret_cast<const __nv_bfloat16*>(&h);
+                }
+            }
+        }
+    }
+}
+
 template <typename ST>
 __device__ __forceinline__ void bg_load_tile(ST (*sm)[BG_K + BG_PAD], const void* base, int dtype, long long rs, long long cs, int row0, int nrows, int k0,
                                              int K, int tid) {
-    if (cs == 1 || rs != 1) {                 // k contiguous (or no contiguous direction): consecutive threads along k
-        for (int i = tid; i < BG_T * BG_K; i += 128) {
-            const int r = i >> 5, k = i & 31;
-            float v = 0.f;
-            if (row0 + r < nrows && k0 + k < K) v = ld_elem(base, dtype, (long long)(row0 + r) * rs + (long long)(k0 + k) * cs);
-            if constexpr (sizeof(ST) == 2) sm[r][k] = __float2bfloat16_rn(v); else sm[r][k] = v;
-        }
-    } else {                                  // rows contiguous: consecutive threads along the row index
-        for (int i = tid; i < BG_T * BG_K; i += 128) {
-            const int k = i >> 6, r = i & 63;
-            float v = 0.f;
-            if (row0 + r < nrows && k0 + k < K) v = ld_elem(base, dtype, (long long)(row0 + r) + (long long)(k0 + k) * cs);
-            if constexpr (sizeof(ST) == 2) sm[r][k] = __float2bfloat16_rn(v); else sm[r][k] = v;
+    {
+        if (cs == 1 || rs != 1) {                 // k contiguous (or no contiguous direction): consecutive threads along k
+            for (int i = tid; i < BG_T * BG_K; i += 128) {
+                const int r = i >> 5, k = i & 31;
+                float v = 0.f;
+                if (row0 + r < nrows && k0 + k < K) v = ld_elem(base, dtype, (long long)(row0 + r) * rs + (long long)(k0 + k) * cs);
+                if constexpr (sizeof(ST) == 2) sm[r][k] = __float2bfloat16_rn(v); else sm[r][k] = v;
+            }
+        } else {                                  // rows contiguous: consecutive threads along the row index
+            for (int i = tid; i < BG_T * BG_K; i += 128) {
+                const int k = i >> 6, r = i & 63;
+                float v = 0.f;
+                if (row0 + r < nrows && k0 + k < K) v = ld_elem(base, dtype, (long long)(row0 + r) + (long long)(k0 + k) * cs);
+                if constexpr (sizeof(ST) == 2) sm[r][k] = __float2bfloat16_rn(v); else sm[r][k] = v;
+            }
         }
     }
 }
@@ -72,11 +179,37 @@ __global__ void __launch_bounds__(128) bgemm_kernel(const BgemmParams p) {
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    // tensor-core path: the next k-tile of both operands is requested into registers before the MMAs of the current one are issued
+    BgTileSrc ta, tb;
+    BgThread tha, thb;
+    uint4 ra[4], rb[4];
+    size_t ka_bytes = 0, kb_bytes = 0;                        // byte step of one k-tile along each operand
+    if constexpr (TC) {
+        ta = bg_src(A, p.a_dtype, p.a_rs, p.a_cs, m0, p.M, p.K);
+        tb = bg_src(Bm, p.b_dtype, p.b_cs, p.b_rs, n0, p.N, p.K);                         // row of Bs = n: (rs, cs) seen from n are (b_cs, b_rs)
+        bg_thread_init(ta, m0, tid, tha);
+        bg_thread_init(tb, n0, tid, thb);
+        ka_bytes = (size_t)BG_K * p.a_cs * ea; kb_bytes = (size_t)BG_K * p.b_rs * eb;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ra[q] = rb[q] = make_uint4(0u, 0u, 0u, 0u);
+        bg_fetch(ta, tha, m0, 0, 0, ra);
+        bg_fetch(tb, thb, n0, 0, 0, rb);
+    }
     for (int k0 = 0; k0 < p.K; k0 += BG_K) {
-        bg_load_tile<ST>(As, A, p.a_dtype, p.a_rs, p.a_cs, m0, p.M, k0, p.K, tid);
-        bg_load_tile<ST>(Bs, Bm, p.b_dtype, p.b_cs, p.b_rs, n0, p.N, k0, p.K, tid);      // row of Bs = n: (rs, cs) seen from n are (b_cs, b_rs)
+        if constexpr (TC) {
+            bg_commit(ta, tha, As, ra);
+            bg_commit(tb, thb, Bs, rb);
+        } else {
+            bg_load_tile<ST>(As, A, p.a_dtype, p.a_rs, p.a_cs, m0, p.M, k0, p.K, tid);
+            bg_load_tile<ST>(Bs, Bm, p.b_dtype, p.b_cs, p.b_rs, n0, p.N, k0, p.K, tid);
+        }
         __syncthreads();
         if constexpr (TC) {
+            if (k0 + BG_K < p.K) {
+                const size_t it = (size_t)(k0 / BG_K + 1);
+                bg_fetch(ta, tha, m0, k0 + BG_K, it * ka_bytes, ra);
+                bg_fetch(tb, thb, n0, k0 + BG_K, it * kb_bytes, rb);
+            }
 #pragma unroll
             for (int ks = 0; ks < BG_K; ks += 16) {
                 uint32_t a[2][4], b[2][4];
@@ -126,13 +259,22 @@ __global__ void __launch_bounds__(128) bgemm_kernel(const BgemmParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int m = m0 + wm + 16 * i + g + 8 * (e >> 1), n = n0 + wn + 8 * j + 2 * c + (e & 1);
+            for (int h = 0; h < 2; ++h) {
+                const int m = m0 + wm + 16 * i + g + 8 * h, n = n0 + wn + 8 * j + 2 * c;
                 if (m < p.M && n < p.N) {
-                    const float v = fmaf(p.alpha, acc[i][j][e], bias ? bias[n] : 0.f);
+                    const float v0 = fmaf(p.alpha, acc[i][j][2 * h], bias ? bias[n] : 0.f);
+                    const float v1 = n + 1 < p.N ? fmaf(p.alpha, acc[i][j][2 * h + 1], bias ? bias[n + 1] : 0.f) : 0.f;
                     const long long o = cbase + (long long)m * p.c_rs + n;
-                    if (p.c_dtype == NSD_F32) reinterpret_cast<float*>(C)[o] = v;
-                    else reinterpret_cast<__nv_bfloat16*>(C)[o] = __float2bfloat16_rn(v);
+                    const bool pair = n + 1 < p.N && (o & 1) == 0;          // two adjacent outputs in one 8- / 4-byte store when aligned
+                    if (p.c_dtype == NSD_F32) {
+                        float* cp = reinterpret_cast<float*>(C) + o;
+                        if (pair) *reinterpret_cast<float2*>(cp) = make_float2(v0, v1);
+                        else { cp[0] = v0; if (n + 1 < p.N) cp[1] = v1; }
+                    } else {
+                        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(C) + o;
+                        if (pair) *reinterpret_cast<__nv_bfloat162*>(cp) = __floats2bfloat162_rn(v0, v1);
+                        else { cp[0] = __float2bfloat16_rn(v0); if (n + 1 < p.N) cp[1] = __float2bfloat16_rn(v1); }
+                    }
                 }
             }
 }
@@ -141,13 +283,14 @@ __global__ void __launch_bounds__(128) bgemm_kernel(const BgemmParams p) {
 // S [rows = B*H*T, T]; row r belongs to utterance b = r / (H*T); keys j >= lens[b] are padding (-inf): P = softmax_j(S) over the valid keys.
 // Pd (optional, f32 or bf16): dropout(P) with the mask of element r*T + j.
 __global__ void __launch_bounds__(256) softmax_mask_fwd_kernel(float* __restrict__ S, void* __restrict__ Pd, int pd_dtype, const int32_t* __restrict__ lens,
-                                                               long long rows, int HT, int T, float p, uint64_t seed, const unsigned long long* __restrict__ seed_off) {
+                                                               long long rows, int HT, int T, int ld, float p, uint64_t seed,
+                                                               const unsigned long long* __restrict__ seed_off) {
     if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
     const int len = lens ? min(T, max(0, lens[r / HT])) : T;
-    float* s = S + r * T;
+    float* s = S + r * ld;
     float mx = -INFINITY;
     for (int j = lane; j < len; j += 32) mx = fmaxf(mx, s[j]);
     mx = warp_max(mx);
@@ -156,24 +299,24 @@ __global__ void __launch_bounds__(256) softmax_mask_fwd_kernel(float* __restrict
     sum = warp_sum(sum);
     const float inv = len > 0 ? 1.0f / sum : 0.f, inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     const uint32_t th = dropout_threshold(p);
-    for (int j = lane; j < T; j += 32) {
+    for (int j = lane; j < ld; j += 32) {                 // the padding columns [T, ld) are written as zeros
         const float v = j < len ? __expf(s[j] - mx) * inv : 0.f;
         s[j] = v;
         if (Pd) {
             float d = v;
-            if (p > 0.f) {
+            if (p > 0.f && j < T) {
                 const size_t e = (size_t)r * T + j;
                 const uint4 rb = dropout_bits(e >> 2, seed);
                 const uint32_t w = (e & 3) == 0 ? rb.x : ((e & 3) == 1 ? rb.y : ((e & 3) == 2 ? rb.z : rb.w));
                 d = w >= th ? v * inv_keep : 0.f;
             }
-            if (pd_dtype == NSD_F32) reinterpret_cast<float*>(Pd)[(size_t)r * T + j] = d;
-            else reinterpret_cast<__nv_bfloat16*>(Pd)[(size_t)r * T + j] = __float2bfloat16_rn(d);
+            if (pd_dtype == NSD_F32) reinterpret_cast<float*>(Pd)[(size_t)r * ld + j] = d;
+            else reinterpret_cast<__nv_bfloat16*>(Pd)[(size_t)r * ld + j] = __float2bfloat16_rn(d);
         }
     }
 }
 // dS = P * (dP - sum_j dP_j P_j), dP = dropout-backward of dPd (in place over dPd)
-__global__ void __launch_bounds__(256) softmax_mask_bwd_kernel(const float* __restrict__ P, float* __restrict__ dPd, long long rows, int T, float p,
+__global__ void __launch_bounds__(256) softmax_mask_bwd_kernel(const float* __restrict__ P, float* __restrict__ dPd, long long rows, int T, int ld, float p,
                                                                uint64_t seed, const unsigned long long* __restrict__ seed_off) {
     if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31;
@@ -183,18 +326,18 @@ __global__ void __launch_bounds__(256) softmax_mask_bwd_kernel(const float* __re
     const uint32_t th = dropout_threshold(p);
     float dot = 0.f;
     for (int j = lane; j < T; j += 32) {
-        float d = dPd[r * T + j];
+        float d = dPd[r * ld + j];
         if (p > 0.f) {
             const size_t e = (size_t)r * T + j;
             const uint4 rb = dropout_bits(e >> 2, seed);
             const uint32_t w = (e & 3) == 0 ? rb.x : ((e & 3) == 1 ? rb.y : ((e & 3) == 2 ? rb.z : rb.w));
             d = w >= th ? d * inv_keep : 0.f;
-            dPd[r * T + j] = d;
+            dPd[r * ld + j] = d;
         }
-        dot = fmaf(d, P[r * T + j], dot);
+        dot = fmaf(d, P[r * ld + j], dot);
     }
     dot = warp_sum(dot);
-    for (int j = lane; j < T; j += 32) dPd[r * T + j] = P[r * T + j] * (dPd[r * T + j] - dot);
+    for (int j = lane; j < ld; j += 32) dPd[r * ld + j] = j < T ? P[r * ld + j] * (dPd[r * ld + j] - dot) : 0.f;
 }
 
 // ---- sum of squares of a list of tensors (clip_grad_norm_, trainer:255-257): per-CTA partials in a fixed order, then one CTA
@@ -259,19 +402,19 @@ int nsd_bgemm(const void* A, int a_dtype, int64_t a_rs, int64_t a_cs, int64_t a_
     return NSD_OK;
 }
 
-int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, int B, int H, int T, float p_drop, uint64_t seed, void* stream) {
-    NSD_CHECK_ARG(S && B >= 0 && H >= 1 && T >= 1 && p_drop >= 0.f && p_drop < 1.f && (!Pd || pd_dtype == NSD_F32 || pd_dtype == NSD_BF16), "softmax_mask_fwd: bad argument");
+int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, int B, int H, int T, int ld, float p_drop, uint64_t seed, void* stream) {
+    NSD_CHECK_ARG(S && B >= 0 && H >= 1 && T >= 1 && ld >= T && p_drop >= 0.f && p_drop < 1.f && (!Pd || pd_dtype == NSD_F32 || pd_dtype == NSD_BF16), "softmax_mask_fwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
-    softmax_mask_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, Pd, pd_dtype, lens, rows, H * T, T, p_drop, seed, seed_offset_ptr());
+    softmax_mask_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, Pd, pd_dtype, lens, rows, H * T, T, ld, p_drop, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
-int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, float p_drop, uint64_t seed, void* stream) {
-    NSD_CHECK_ARG(P && dPd && B >= 0 && H >= 1 && T >= 1 && p_drop >= 0.f && p_drop < 1.f, "softmax_mask_bwd: bad argument");
+int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, int ld, float p_drop, uint64_t seed, void* stream) {
+    NSD_CHECK_ARG(P && dPd && B >= 0 && H >= 1 && T >= 1 && ld >= T && p_drop >= 0.f && p_drop < 1.f, "softmax_mask_bwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
-    softmax_mask_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, dPd, rows, T, p_drop, seed, seed_offset_ptr());
+    softmax_mask_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, dPd, rows, T, ld, p_drop, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

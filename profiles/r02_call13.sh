@@ -2,4 +2,4 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 O=gpurun_out; mkdir -p $O
 timeout 1200 python -m pytest tests/test_gpu_conformer.py -m gpu -q -s > $O/conformer_tests.log 2>&1; echo "conformer tests rc=$?"; grep -E "passed|failed" $O/conformer_tests.log
-timeout 600 python bench.py --mode conformer --no-cpu-baseline > $O/conformer_bench.json 2> $O/conformer_bench.err; echo "bench rc=$?"; cut -c1-300 $O/conformer_bench.json; timeout 600 python bench.py --mode conformer --graph --no-cpu-baseline > $O/conformer_bench_graph.json 2> $O/conformer_bench_graph.err; echo "graph bench rc=$?"; cut -c1-300 $O/conformer_bench_graph.json; tail -5 $O/conformer_bench_graph.err
+timeout 600 python bench.py --mode conformer --no-cpu-baseline --breakdown > $O/conformer_bench.json 2> $O/conformer_bench.err; echo "bench rc=$?"; cut -c1-300 $O/conformer_bench.json; timeout 600 python bench.py --mode conformer --graph --no-cpu-baseline > $O/conformer_bench_graph.json 2> $O/conformer_bench_graph.err; echo "graph bench rc=$?"; cut -c1-300 $O/conformer_bench_graph.json; tail -5 $O/conformer_bench_graph.err
