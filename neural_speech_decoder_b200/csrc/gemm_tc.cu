@@ -76,6 +76,58 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
     *reinterpret_cast<uint2*>(p) = u;
 }
 
+// One thread's 32 consecutive accumulator columns of row `row` (read from TMEM into r[0..31]) -> C[row, col0 .. col0+31], with the optional bias and
+// beta*C terms.  Full 32-byte sectors per thread where alignment allows (256-bit fp32 / 16 x bf16 stores), element-wise at the matrix edge.
+// Shared by the single-CTA and the cta_group::2 kernels.
+template <typename OutT>
+__device__ __forceinline__ void store_acc_row32(OutT* __restrict__ C, int ldc, int row, int col0, int M, int N, const uint32_t (&r)[32],
+                                                const float* __restrict__ bias, float beta, bool vec_ok, bool vec8_ok) {
+    if (row < M) {
+        OutT* crow = C + (size_t)row * ldc + col0;
+        if (std::is_same<OutT, float>::value && vec8_ok && beta == 0.f && col0 + 32 <= N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
+                if (bias) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i + 4));
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                store8_f32(reinterpret_cast<float*>(crow) + i, v);
+            }
+        } else if (std::is_same<OutT, __nv_bfloat16>::value && vec8_ok && (ldc % 16) == 0 && beta == 0.f && col0 + 32 <= N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 16)
+                store16_bf16(reinterpret_cast<__nv_bfloat16*>(crow) + i, r, i, bias ? bias + col0 + i : nullptr);
+        } else if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
+                if (bias) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+                    v0 += bv.x; v1 += bv.y; v2 += bv.z; v3 += bv.w;
+                }
+                if (beta != 0.f) {
+                    v0 = fmaf(beta, to_f32<OutT>(crow[i]), v0); v1 = fmaf(beta, to_f32<OutT>(crow[i + 1]), v1);
+                    v2 = fmaf(beta, to_f32<OutT>(crow[i + 2]), v2); v3 = fmaf(beta, to_f32<OutT>(crow[i + 3]), v3);
+                }
+                store4<OutT>(crow + i, v0, v1, v2, v3);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (col0 + i < N) {
+                    float v = __uint_as_float(r[i]);
+                    if (bias) v += __ldg(bias + col0 + i);
+                    if (beta != 0.f) v = fmaf(beta, to_f32<OutT>(crow[i]), v);
+                    crow[i] = from_f32<OutT>(v);
+                }
+            }
+        }
+    }
+}
+
 // cluster helpers of the pair form below
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
@@ -195,50 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (col0 >= N) break;                                 // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                if (row < M) {
-                    OutT* crow = C + (size_t)row * ldc + col0;
-                    if (std::is_same<OutT, float>::value && vec8_ok && beta == 0.f && col0 + 32 <= N) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
-                            if (bias) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i + 4));
-                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            }
-                            store8_f32(reinterpret_cast<float*>(crow) + i, v);
-                        }
-                    } else if (std::is_same<OutT, __nv_bfloat16>::value && vec8_ok && (ldc % 16) == 0 && beta == 0.f && col0 + 32 <= N) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 16)
-                            store16_bf16(reinterpret_cast<__nv_bfloat16*>(crow) + i, r, i, bias ? bias + col0 + i : nullptr);
-                    } else if (vec_ok && col0 + 32 <= N) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
-                            if (bias) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
-                                v0 += bv.x; v1 += bv.y; v2 += bv.z; v3 += bv.w;
-                            }
-                            if (beta != 0.f) {
-                                v0 = fmaf(beta, to_f32<OutT>(crow[i]), v0); v1 = fmaf(beta, to_f32<OutT>(crow[i + 1]), v1);
-                                v2 = fmaf(beta, to_f32<OutT>(crow[i + 2]), v2); v3 = fmaf(beta, to_f32<OutT>(crow[i + 3]), v3);
-                            }
-                            store4<OutT>(crow + i, v0, v1, v2, v3);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (col0 + i < N) {
-                                float v = __uint_as_float(r[i]);
-                                if (bias) v += __ldg(bias + col0 + i);
-                                if (beta != 0.f) v = fmaf(beta, to_f32<OutT>(crow[i]), v);
-                                crow[i] = from_f32<OutT>(v);
-                            }
-                        }
-                    }
-                }
+                store_acc_row32<OutT>(C, ldc, row, col0, M, N, r, bias, beta, vec_ok, vec8_ok);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -451,50 +460,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (col0 >= N) break;                                 // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                if (row < M) {
-                    OutT* crow = ((t >= per_prob) ? C2 : C) + (size_t)row * ldc + col0;
-                    if (std::is_same<OutT, float>::value && vec8_ok && beta == 0.f && col0 + 32 <= N) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
-                            if (bias) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i + 4));
-                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            }
-                            store8_f32(reinterpret_cast<float*>(crow) + i, v);
-                        }
-                    } else if (std::is_same<OutT, __nv_bfloat16>::value && vec8_ok && (ldc % 16) == 0 && beta == 0.f && col0 + 32 <= N) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 16)
-                            store16_bf16(reinterpret_cast<__nv_bfloat16*>(crow) + i, r, i, bias ? bias + col0 + i : nullptr);
-                    } else if (vec_ok && col0 + 32 <= N) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
-                            if (bias) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
-                                v0 += bv.x; v1 += bv.y; v2 += bv.z; v3 += bv.w;
-                            }
-                            if (beta != 0.f) {
-                                v0 = fmaf(beta, to_f32<OutT>(crow[i]), v0); v1 = fmaf(beta, to_f32<OutT>(crow[i + 1]), v1);
-                                v2 = fmaf(beta, to_f32<OutT>(crow[i + 2]), v2); v3 = fmaf(beta, to_f32<OutT>(crow[i + 3]), v3);
-                            }
-                            store4<OutT>(crow + i, v0, v1, v2, v3);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (col0 + i < N) {
-                                float v = __uint_as_float(r[i]);
-                                if (bias) v += __ldg(bias + col0 + i);
-                                if (beta != 0.f) v = fmaf(beta, to_f32<OutT>(crow[i]), v);
-                                crow[i] = from_f32<OutT>(v);
-                            }
-                        }
-                    }
-                }
+                store_acc_row32<OutT>((t >= per_prob) ? C2 : C, ldc, row, col0, M, N, r, bias, beta, vec_ok, vec8_ok);
             }
             tcgen05_fence_before();
             __syncwarp();
