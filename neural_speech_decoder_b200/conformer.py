@@ -783,6 +783,8 @@ class GraphedConformerStep:
                  total_steps: int = 1 << 30, eager_warmup: int = 2):
         p0 = next(model.parameters())
         dev = p0.device
+        if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
+            raise NsdError("GraphedConformerStep needs a FusedAdamW with a single parameter group (one device-resident schedule)")
         self.model, self.opt, self.dev = model, optimizer, dev
         N = model.day_linear.dim
         self.X = torch.zeros(B, T, N, device=dev)
