@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--nccl-ctas", type=int, default=int(os.environ.get("NSD_NCCL_CTAS", "0")),
                     help="N > 1 GPUs: cap NCCL at this many CTAs (NCCL_MAX_CTAS) and keep as many SMs free of the persistent GEMMs during the backward; 0 = off")
     ap.add_argument("--graph", action="store_true", help="--mode conformer: replay the whole training step as one captured CUDA graph (GraphedConformerStep)")
+    ap.add_argument("--tail-ctas", type=int, default=int(os.environ.get("NSD_TAIL_CTAS", "0")),
+                    help="N > 1 GPUs: cap NCCL at this many CTAs and let ONLY the layer-0 dgrad GEMM leave as many SMs free, so the last (226 MB) "
+                         "bucket's all-reduce runs under it; 0 = off")
+    ap.add_argument("--timeline", default="", help="N > 1: write rank 0's per-bucket all-reduce timeline of one step (ready / done times relative to the start of the backward) to this JSON file")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
     ap.add_argument("--mode", default="train", choices=["train", "infer", "stream", "conformer"],
                     help="infer: BASELINE configs[3] -- unidirectional GRUDecoder forward + greedy CTC decode latency at B=1 and B=32; "
@@ -248,8 +252,8 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if a.nccl_ctas > 0:
-            os.environ["NCCL_MAX_CTAS"] = str(a.nccl_ctas)
+        if a.nccl_ctas > 0 or a.tail_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(a.nccl_ctas or a.tail_ctas)
         dist.init_process_group("nccl", device_id=dev)
     if a.strong:
         if a.batch % world:
@@ -264,7 +268,7 @@ def run_ours(a):
     torch.manual_seed(0)
     model = nsd.GRUDecoder(device="cuda", bidirectional=not a.uni, **MODEL_KW).to(dev)
     model.train()
-    gs = GradSync(world, reserve_sms=a.nccl_ctas) if world > 1 else None
+    gs = GradSync(world, reserve_sms=a.nccl_ctas, tail_sms=a.tail_ctas) if world > 1 else None
     opt, sched = nsd.make_optimizer(model, dict(lrStart=0.02, lrEnd=0.02, nBatch=10000, l2_decay=1e-5))
     if gs is not None:
         opt.grad_scale = gs.grad_scale
@@ -326,6 +330,20 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms, e2e_ms = tt.tolist()
+    if a.timeline and gs is not None:
+        gs.timeline = []
+        step_resident()
+        torch.cuda.synchronize()
+        buckets, t_end = gs.timeline_ms()
+        gs.timeline = None
+        if rank == 0:
+            names = ["fc_decoder_out"] + [f"gru layer {l}" for l in range(4, -1, -1)] + ["dayWeights/dayBias"]
+            json.dump({"n_gpus": world, "note": "one training step, rank 0; ms relative to the start of loss.backward(); ready = the bucket's last wgrad GEMM has been "
+                       "enqueued on the compute stream and reached, done = its NCCL all-reduce has finished; compute_stream_past_last_wait = when the optimizer may start",
+                       "ms_per_step": round(ms / a.steps, 3),
+                       "buckets": [{"bucket": names[i] if i < len(names) else str(i), "MB": round(b / 1e6, 1), "ready_ms": round(r, 3), "done_ms": round(d, 3),
+                                    "allreduce_ms": round(d - r, 3)} for i, (b, r, d) in enumerate(buckets)],
+                       "compute_stream_past_last_wait_ms": round(t_end, 3)}, open(a.timeline, "w"), indent=1)
     if a.breakdown and rank == 0:
         _lib.profile_begin(None)
         step_resident()

@@ -183,13 +183,19 @@ def decoder_backward_tc(ctx, dlogits):
         # the layer's bucket is final once its wgrads are enqueued.  With SMs reserved for NCCL (GradSync.reserve_sms) the
         # all-reduce starts now and runs under the dgrad GEMM below; without a reserve NCCL's CTAs would displace CTAs of the
         # 148-wide persistent GEMM, so the bucket is released after it (measured: no gain at 8 GPUs)
-        early = gs is not None and getattr(gs, "reserve_sms", 0) > 0
+        tail = gs is not None and l == 0 and getattr(gs, "tail_sms", 0) > 0 and getattr(gs, "world", 1) > 1
+        early = gs is not None and (getattr(gs, "reserve_sms", 0) > 0 or tail)
         if early:
             gs.bucket_ready(v_wih._base)
+        if tail:           # the last big bucket: its all-reduce runs on the SMs this one GEMM leaves free (measured timeline: profiles/r02_allreduce_timeline_*.json)
+            from ._lib import call
+            call("nsd_set_gemm_sm_reserve", gs.tail_sms)
         dinp = None
         if l > 0 or day_w.requires_grad:
             dinp = torch.empty((M, in_l), device=dev, dtype=torch.float32 if l > 0 else torch.bfloat16)
             ops.gemm(False, False, M, in_l, D * 3 * H, dgi, D * 3 * H, w_ih_bf, in_l, dinp, in_l)       # dgrad: dgi W_ih
+        if tail:
+            call("nsd_set_gemm_sm_reserve", 0)
         for d in range(D):
             base = (l * D + d) * 4
             ggru[base:base + 4] = [v_wih[d * 3 * H:(d + 1) * 3 * H], v_whh[d * 3 * H:(d + 1) * 3 * H],

@@ -16,14 +16,20 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, world_size: Optional[int] = None, group=None, reserve_sms: int = 0):
+    def __init__(self, world_size: Optional[int] = None, group=None, reserve_sms: int = 0, tail_sms: int = 0):
         """``reserve_sms``: SMs the persistent GEMMs leave to NCCL between ``begin()`` and ``finish()`` (pair it with
-        ``NCCL_MAX_CTAS=<reserve_sms>`` in the environment before the process group is created); 0 = share all SMs."""
+        ``NCCL_MAX_CTAS=<reserve_sms>`` in the environment before the process group is created); 0 = share all SMs.
+        ``tail_sms``: the targeted form -- only the LAST GRU bucket (layer 0: 226 MB, final when nothing but the layer-0 dgrad GEMM and
+        the front-end backward are left to hide it) is released before its dgrad GEMM, and only that GEMM leaves ``tail_sms`` SMs to
+        NCCL (again with ``NCCL_MAX_CTAS=<tail_sms>``); every other GEMM keeps all SMs."""
         self.group = group
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.handles: List = []
         self.bytes = 0
         self.reserve_sms = int(reserve_sms) if self.world > 1 else 0
+        self.tail_sms = int(tail_sms) if self.world > 1 else 0
+        self.timeline = None           # set to [] to record, per bucket, (bytes, ready event, done event) of the coming step (diagnostics)
+        self._t0 = None
 
     @property
     def grad_scale(self) -> float:
@@ -31,6 +37,10 @@ class GradSync:
 
     def begin(self) -> None:
         self.handles, self.bytes = [], 0
+        if self.timeline is not None:
+            self.timeline.clear()
+            self._t0 = torch.cuda.Event(enable_timing=True)
+            self._t0.record()
         if self.reserve_sms:
             from ._lib import call
             call("nsd_set_gemm_sm_reserve", self.reserve_sms)
@@ -41,12 +51,32 @@ class GradSync:
         if self.world <= 1:
             return
         self.bytes += flat.numel() * flat.element_size()
-        self.handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        ready = None
+        if self.timeline is not None:
+            ready = torch.cuda.Event(enable_timing=True)
+            ready.record()                                  # on the compute stream: the bucket's last wgrad has been enqueued before this point
+        h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.handles.append(h)
+        if self.timeline is not None:
+            side = torch.cuda.Stream(flat.device)           # a stream that waits for THIS collective only: its event is the collective's end
+            done = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(side):
+                h.wait()
+                done.record()
+            self.timeline.append((flat.numel() * flat.element_size(), ready, done))
 
     def finish(self) -> None:
         for h in self.handles:
             h.wait()                      # current stream waits for the collective; no host block on NCCL
         self.handles = []
+        if self.timeline is not None:
+            self._t1 = torch.cuda.Event(enable_timing=True)
+            self._t1.record()                               # compute stream: backward enqueued and every collective waited for
         if self.reserve_sms:
             from ._lib import call
             call("nsd_set_gemm_sm_reserve", 0)
+
+    def timeline_ms(self):
+        """After a synchronize: [(bytes, ready_ms, done_ms)] per bucket relative to begin(), and the time at which the compute stream
+        got past the last wait."""
+        return [(b, self._t0.elapsed_time(r), self._t0.elapsed_time(d)) for b, r, d in self.timeline], self._t0.elapsed_time(self._t1)
