@@ -241,10 +241,11 @@ int nsd_set_seed_offset_ptr(const void* dev_u64);
  * backward.  y_f32 and/or y_bf16.  D % 4 == 0, D <= 2048. */
 int nsd_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed, float* y_f32,
                       void* y_bf16, float* mean, float* rstd, int M, int D, void* stream);
-/* dx, dgamma, dbeta of the above (dgamma/dbeta overwritten; two fixed-order stages: deterministic). */
+/* dx, dgamma, dbeta of the above (dgamma/dbeta overwritten; two fixed-order stages: deterministic).  dx_addend (NULL or f32 [M,D]) is added to
+ * dx: the gradient that reaches x around the LayerNorm in a pre-LN residual block (x + f(LN(x)), transformer_ctc.py:245-257), fused here. */
 int nsd_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
-                      float p_drop, uint64_t seed, float* dx, float* dgamma, float* dbeta, int M, int D, void* workspace, size_t workspace_bytes,
-                      void* stream);
+                      float p_drop, uint64_t seed, const float* dx_addend, float* dx, float* dgamma, float* dbeta, int M, int D, void* workspace,
+                      size_t workspace_bytes, void* stream);
 size_t nsd_layernorm_bwd_workspace(int M, int D);
 /* y = dropout_p(act(x)) over n contiguous elements (n % 4 == 0): SiLU + Dropout of the feed-forward modules (transformer_ctc.py:204-205,
  * 223-224), ReLU of the bottleneck MLP (:140); and its backward dx = dy * mask/(1-p) * act'(x). */

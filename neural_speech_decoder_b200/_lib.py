@@ -50,7 +50,7 @@ SIGNATURES = {
     "nsd_adam_step": (i32, [i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, f32, vp]),
     "nsd_set_gemm_sm_reserve": (i32, [i32]),
     "nsd_layernorm_fwd": (i32, [vp, vp, vp, f32, i32, f32, u64, vp, vp, vp, vp, i32, i32, vp]),
-    "nsd_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, f32, u64, vp, vp, vp, i32, i32, vp, sz, vp]),
+    "nsd_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, f32, u64, vp, vp, vp, vp, i32, i32, vp, sz, vp]),
     "nsd_layernorm_bwd_workspace": (sz, [i32, i32]),
     "nsd_act_fwd": (i32, [vp, i32, f32, u64, vp, vp, sz, vp]),
     "nsd_act_bwd": (i32, [vp, i32, vp, i32, f32, u64, vp, sz, vp]),

@@ -93,10 +93,12 @@ class _Linear(torch.autograd.Function):
 
 
 class _LayerNorm(torch.autograd.Function):
-    """dropout_p(act(LayerNorm(x))) -> (f32 and/or bf16 copies).  Returns the copy(ies) requested by ``want``."""
+    """dropout_p(act(LayerNorm(x))) -> (f32 and/or bf16 copies).  Returns the copy(ies) requested by ``want``.
+    ``fork``: additionally returns x itself (an alias) as the LAST output -- the skip path of a pre-LN residual block.  Its gradient then
+    arrives here together with the branch's and the backward kernel adds it to dx (no separate accumulation pass over [M, D])."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, act, p, seed, want32, want16):
+    def forward(ctx, x, gamma, beta, eps, act, p, seed, want32, want16, fork=False):
         M, D = x.shape
         dev = x.device
         y32 = torch.empty((M, D), device=dev, dtype=_f32) if want32 else None
@@ -105,29 +107,37 @@ class _LayerNorm(torch.autograd.Function):
         call("nsd_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), float(eps), act, float(p), int(seed), ptr(y32), ptr(y16), ptr(mean), ptr(rstd), M, D, stream())
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.set_materialize_grads(False)
-        ctx.cfg = (act, p, seed, want32, want16)
-        if want32 and want16:
-            return y32, y16
-        return y32 if want32 else y16
+        ctx.cfg = (act, p, seed, want32, want16, fork)
+        outs = tuple(t for t in (y32, y16) if t is not None)
+        if fork:
+            outs = outs + (x.view_as(x),)
+        return outs if len(outs) > 1 else outs[0]
 
     @staticmethod
     def backward(ctx, *dys):
         x, gamma, beta, mean, rstd = ctx.saved_tensors
-        act, p, seed, want32, want16 = ctx.cfg
+        act, p, seed, want32, want16, fork = ctx.cfg
         M, D = x.shape
         dev = x.device
+        skip = None
+        if fork:
+            skip, dys = dys[-1], dys[:-1]
         dy = None
         for g in dys:                      # the two copies are the same value: their gradients add
             if g is not None:
                 dy = g if dy is None else dy.float() + g.float()
+        if dy is None:                     # only the skip path carries gradient
+            return (skip,) + (None,) * 9
         dy = dy.contiguous()
+        if skip is not None:
+            skip = skip.contiguous()
         dx = torch.empty((M, D), device=dev, dtype=_f32)
         dg, db = torch.empty(D, device=dev), torch.empty(D, device=dev)
         nb = _lib.lib().nsd_layernorm_bwd_workspace(M, D)
         ws = _ws(nb, dev)
-        call("nsd_layernorm_bwd", ptr(dy), _code(dy.dtype), ptr(x), ptr(gamma), ptr(beta), ptr(mean), ptr(rstd), act, float(p), int(seed), ptr(dx),
-             ptr(dg), ptr(db), M, D, ptr(ws), ws.numel(), stream())
-        return dx, dg, db, None, None, None, None, None, None
+        call("nsd_layernorm_bwd", ptr(dy), _code(dy.dtype), ptr(x), ptr(gamma), ptr(beta), ptr(mean), ptr(rstd), act, float(p), int(seed), ptr(skip),
+             ptr(dx), ptr(dg), ptr(db), M, D, ptr(ws), ws.numel(), stream())
+        return dx, dg, db, None, None, None, None, None, None, None
 
 
 class _Act(torch.autograd.Function):
@@ -544,11 +554,11 @@ class NeuralTransformerCTCModel(nn.Module):
             site[0] += 1
             return (base + site[0] * 0x2545F4914F6CDD1D) & 0x7FFFFFFFFFFFFFFF
 
-        def ln(xx, mod: nn.LayerNorm, act=ACT_NONE, p=0.0, want32=False, want16=None):
+        def ln(xx, mod: nn.LayerNorm, act=ACT_NONE, p=0.0, want32=False, want16=None, fork=False):
             want16 = lowp if want16 is None else want16
             if not want32 and not want16:
                 want32 = True
-            return _LayerNorm.apply(xx, mod.weight, mod.bias, mod.eps, act, p, seed() if p > 0 else 0, want32, want16)
+            return _LayerNorm.apply(xx, mod.weight, mod.bias, mod.eps, act, p, seed() if p > 0 else 0, want32, want16, fork)
 
         day = day_ids.to(device=dev, dtype=torch.int64).contiguous()
         if self.check_day_ids and day.numel() and (int(day.min()) < 0 or int(day.max()) >= self.day_linear.day_weights.shape[0]):
@@ -594,7 +604,7 @@ class NeuralTransformerCTCModel(nn.Module):
             # half-step feed-forward (transformer_ctc.py:245)
             z = self._ff(z, blk.ff1, (i, "ff1"), ln, seed, pd, pp, per_sample, adt)
             # self-attention (transformer_ctc.py:248-251)
-            h = ln(z, blk.ln_attn)
+            h, z = ln(z, blk.ln_attn, fork=True)
             wb = self._shadows.stacked((i, "attn.in"), [blk.attn.in_proj_weight]) if lowp else None
             qkv = _Linear.apply(h, blk.attn.in_proj_weight, blk.attn.in_proj_bias, wb, adt)
             o = _Attention.apply(qkv, lens, B, Tn, self.n_heads, pd, seed() if pd > 0 else 0)
@@ -602,7 +612,7 @@ class NeuralTransformerCTCModel(nn.Module):
             z = _Residual.apply(z, y, 1.0, pd, seed(), pp, seed(), per_sample)
             # convolution module (transformer_ctc.py:170-191)
             cm = blk.conv_module
-            h = ln(z, cm.ln)
+            h, z = ln(z, cm.ln, fork=True)
             u = self._lin(h, cm.pw_conv1, (i, "pw1"))
             g = _GLU.apply(u)
             c = _DwConv.apply(g, cm.dw_conv.weight, cm.dw_conv.bias, B, Tn)
@@ -627,7 +637,7 @@ class NeuralTransformerCTCModel(nn.Module):
         return log_probs, out_lengths, inter_log_probs
 
     def _ff(self, z, ff: nn.Sequential, key, ln, seed, pd, pp, per_sample, adt):
-        h = ln(z, ff[0])
+        h, z = ln(z, ff[0], fork=True)
         u = self._lin(h, ff[1], (key, 1))
         s = _Act.apply(u, ACT_SILU, pd, seed() if pd > 0 else 0, adt)
         y = self._lin(s, ff[4], (key, 4))

@@ -285,33 +285,55 @@ __global__ void __launch_bounds__(128) bgemm_kernel(const BgemmParams p) {
 __global__ void __launch_bounds__(256) softmax_mask_fwd_kernel(float* __restrict__ S, void* __restrict__ Pd, int pd_dtype, const int32_t* __restrict__ lens,
                                                                long long rows, int HT, int T, int ld, float p, uint64_t seed,
                                                                const unsigned long long* __restrict__ seed_off) {
+    // a lane owns groups of 4 consecutive scores (ld % 4 == 0): 16-byte accesses, and ONE Philox block per group for the dropout mask
+    // (element r*ld + j: the padded index, so that a group never straddles two blocks)
     if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
     const int len = lens ? min(T, max(0, lens[r / HT])) : T;
-    float* s = S + r * ld;
+    float4* s4 = reinterpret_cast<float4*>(S + r * ld);
+    const int n4 = ld >> 2;
     float mx = -INFINITY;
-    for (int j = lane; j < len; j += 32) mx = fmaxf(mx, s[j]);
+    for (int q = lane; q < n4; q += 32) {
+        const float4 v = s4[q];
+        const int j = 4 * q;
+        if (j < len) mx = fmaxf(mx, v.x);
+        if (j + 1 < len) mx = fmaxf(mx, v.y);
+        if (j + 2 < len) mx = fmaxf(mx, v.z);
+        if (j + 3 < len) mx = fmaxf(mx, v.w);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int j = lane; j < len; j += 32) sum += __expf(s[j] - mx);
+    for (int q = lane; q < n4; q += 32) {
+        const float4 v = s4[q];
+        const int j = 4 * q;
+        sum += (j < len ? __expf(v.x - mx) : 0.f) + (j + 1 < len ? __expf(v.y - mx) : 0.f) + (j + 2 < len ? __expf(v.z - mx) : 0.f) +
+               (j + 3 < len ? __expf(v.w - mx) : 0.f);
+    }
     sum = warp_sum(sum);
     const float inv = len > 0 ? 1.0f / sum : 0.f, inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     const uint32_t th = dropout_threshold(p);
-    for (int j = lane; j < ld; j += 32) {                 // the padding columns [T, ld) are written as zeros
-        const float v = j < len ? __expf(s[j] - mx) * inv : 0.f;
-        s[j] = v;
+    for (int q = lane; q < n4; q += 32) {                 // the padding columns [T, ld) are written as zeros
+        const float4 v = s4[q];
+        const int j = 4 * q;
+        float4 o;
+        o.x = j < len ? __expf(v.x - mx) * inv : 0.f; o.y = j + 1 < len ? __expf(v.y - mx) * inv : 0.f;
+        o.z = j + 2 < len ? __expf(v.z - mx) * inv : 0.f; o.w = j + 3 < len ? __expf(v.w - mx) * inv : 0.f;
+        s4[q] = o;
         if (Pd) {
-            float d = v;
-            if (p > 0.f && j < T) {
-                const size_t e = (size_t)r * T + j;
-                const uint4 rb = dropout_bits(e >> 2, seed);
-                const uint32_t w = (e & 3) == 0 ? rb.x : ((e & 3) == 1 ? rb.y : ((e & 3) == 2 ? rb.z : rb.w));
-                d = w >= th ? v * inv_keep : 0.f;
+            float4 d = o;
+            if (p > 0.f) {
+                const uint4 rb = dropout_bits(((size_t)r * ld + j) >> 2, seed);
+                d.x = rb.x >= th ? d.x * inv_keep : 0.f; d.y = rb.y >= th ? d.y * inv_keep : 0.f;
+                d.z = rb.z >= th ? d.z * inv_keep : 0.f; d.w = rb.w >= th ? d.w * inv_keep : 0.f;
             }
-            if (pd_dtype == NSD_F32) reinterpret_cast<float*>(Pd)[(size_t)r * ld + j] = d;
-            else reinterpret_cast<__nv_bfloat16*>(Pd)[(size_t)r * ld + j] = __float2bfloat16_rn(d);
+            if (pd_dtype == NSD_F32) reinterpret_cast<float4*>(reinterpret_cast<float*>(Pd) + (size_t)r * ld)[q] = d;
+            else {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+                reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(Pd) + (size_t)r * ld)[q] =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+            }
         }
     }
 }
@@ -324,20 +346,33 @@ __global__ void __launch_bounds__(256) softmax_mask_bwd_kernel(const float* __re
     if (r >= rows) return;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     const uint32_t th = dropout_threshold(p);
+    const float4* p4 = reinterpret_cast<const float4*>(P + r * ld);
+    float4* d4 = reinterpret_cast<float4*>(dPd + r * ld);
+    const int n4 = ld >> 2;
     float dot = 0.f;
-    for (int j = lane; j < T; j += 32) {
-        float d = dPd[r * ld + j];
-        if (p > 0.f) {
-            const size_t e = (size_t)r * T + j;
-            const uint4 rb = dropout_bits(e >> 2, seed);
-            const uint32_t w = (e & 3) == 0 ? rb.x : ((e & 3) == 1 ? rb.y : ((e & 3) == 2 ? rb.z : rb.w));
-            d = w >= th ? d * inv_keep : 0.f;
-            dPd[r * ld + j] = d;
+    for (int q = lane; q < n4; q += 32) {
+        float4 d = d4[q];
+        const float4 pv = p4[q];                           // zero in the padding columns and at masked keys
+        const int j = 4 * q;                               // the padding columns of dPd were never written: keep them out of the sums
+        if (j >= T) d.x = 0.f;
+        if (j + 1 >= T) d.y = 0.f;
+        if (j + 2 >= T) d.z = 0.f;
+        if (j + 3 >= T) d.w = 0.f;
+        if (p > 0.f || j + 3 >= T) {
+            if (p > 0.f) {
+                const uint4 rb = dropout_bits(((size_t)r * ld + j) >> 2, seed);
+                d.x = rb.x >= th ? d.x * inv_keep : 0.f; d.y = rb.y >= th ? d.y * inv_keep : 0.f;
+                d.z = rb.z >= th ? d.z * inv_keep : 0.f; d.w = rb.w >= th ? d.w * inv_keep : 0.f;
+            }
+            d4[q] = d;
         }
-        dot = fmaf(d, P[r * ld + j], dot);
+        dot += (d.x * pv.x + d.y * pv.y) + (d.z * pv.z + d.w * pv.w);
     }
     dot = warp_sum(dot);
-    for (int j = lane; j < ld; j += 32) dPd[r * ld + j] = j < T ? P[r * ld + j] * (dPd[r * ld + j] - dot) : 0.f;
+    for (int q = lane; q < n4; q += 32) {
+        const float4 d = d4[q], pv = p4[q];
+        d4[q] = make_float4(pv.x * (d.x - dot), pv.y * (d.y - dot), pv.z * (d.z - dot), pv.w * (d.w - dot));
+    }
 }
 
 // ---- sum of squares of a list of tensors (clip_grad_norm_, trainer:255-257): per-CTA partials in a fixed order, then one CTA
@@ -403,7 +438,7 @@ int nsd_bgemm(const void* A, int a_dtype, int64_t a_rs, int64_t a_cs, int64_t a_
 }
 
 int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, int B, int H, int T, int ld, float p_drop, uint64_t seed, void* stream) {
-    NSD_CHECK_ARG(S && B >= 0 && H >= 1 && T >= 1 && ld >= T && p_drop >= 0.f && p_drop < 1.f && (!Pd || pd_dtype == NSD_F32 || pd_dtype == NSD_BF16), "softmax_mask_fwd: bad argument");
+    NSD_CHECK_ARG(S && B >= 0 && H >= 1 && T >= 1 && ld >= T && ld % 4 == 0 && p_drop >= 0.f && p_drop < 1.f && (!Pd || pd_dtype == NSD_F32 || pd_dtype == NSD_BF16), "softmax_mask_fwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
     softmax_mask_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, Pd, pd_dtype, lens, rows, H * T, T, ld, p_drop, seed, seed_offset_ptr());
@@ -411,7 +446,7 @@ int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, 
     return NSD_OK;
 }
 int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, int ld, float p_drop, uint64_t seed, void* stream) {
-    NSD_CHECK_ARG(P && dPd && B >= 0 && H >= 1 && T >= 1 && ld >= T && p_drop >= 0.f && p_drop < 1.f, "softmax_mask_bwd: bad argument");
+    NSD_CHECK_ARG(P && dPd && B >= 0 && H >= 1 && T >= 1 && ld >= T && ld % 4 == 0 && p_drop >= 0.f && p_drop < 1.f, "softmax_mask_bwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
     softmax_mask_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, dPd, rows, T, ld, p_drop, seed, seed_offset_ptr());

@@ -99,78 +99,98 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     }
 }
 
-// backward: dx per row (warp per row) + per-CTA partial column sums of dgamma / dbeta over the CTA's rows (fixed order),
-// reduced by layernorm_param_reduce_kernel: deterministic.
-constexpr int LNB_ROWS = 32;    // rows per CTA (8 warps x 4 rows): 236 CTAs at M = 7552
+// backward in two light kernels instead of one heavy one (a fused form that also carried the dgamma / dbeta column sums needed 120 registers
+// and 64 KB of shared memory per CTA: 16 warps per SM, long-scoreboard-bound at 20 % of DRAM peak under ncu):
+//   layernorm_bwd_dx_kernel     warp per row, row in registers, no column state -> 4 CTAs per SM;
+//   layernorm_bwd_param_kernel  thread = 4 columns x every 8th row of a 256-row chunk (re-reads dy and x: +1 pass, coalesced, deep MLP),
+//                               per-chunk partial sums reduced in fixed order by layernorm_param_reduce_kernel: deterministic.
+__device__ __forceinline__ float4 ln_bwd_dterm(float4 d, const float4& xh, const float4& g, const float* __restrict__ beta, int c, int act, const float4& k) {
+    d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w;
+    if (act != ACT_NONE) {
+        const float4 b = reinterpret_cast<const float4*>(beta)[c];
+        d.x *= act_grad(fmaf(xh.x, g.x, b.x), act); d.y *= act_grad(fmaf(xh.y, g.y, b.y), act);
+        d.z *= act_grad(fmaf(xh.z, g.z, b.z), act); d.w *= act_grad(fmaf(xh.w, g.w, b.w), act);
+    }
+    return d;
+}
 
 template <int MAXV>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x,
-                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               const float* __restrict__ mean, const float* __restrict__ rstd, int act, float p,
-                                                               uint64_t seed, const unsigned long long* __restrict__ seed_off, float* __restrict__ dx,
-                                                               float* __restrict__ part, int M, int D) {
+__global__ void __launch_bounds__(256, 3) layernorm_bwd_dx_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd, int act, float p,
+                                                                  uint64_t seed, const unsigned long long* __restrict__ seed_off,
+                                                                  const float* __restrict__ addend, float* __restrict__ dx, int M, int D) {
     if (seed_off) seed += *seed_off;
-    extern __shared__ float sm[];                      // [8 warps][2][D]: each warp's running column sums of dgamma / dbeta terms
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
     const int nv = D >> 2;
-    float4* sg = reinterpret_cast<float4*>(sm + (size_t)(warp * 2 + 0) * D);
-    float4* sb = reinterpret_cast<float4*>(sm + (size_t)(warp * 2 + 1) * D);
+    const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    float4 xh[MAXV], dh[MAXV];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int c = lane + 32 * i;
-        if (c < nv) sg[c] = sb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nv) {
+            const float4 xv = xr[c], g = reinterpret_cast<const float4*>(gamma)[c];
+            xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+            const float4 d = ln_bwd_dterm(load4(dy, dy_dtype, (size_t)row * D + 4 * c), xh[i], g, beta, c, act,
+                                          drop4(((size_t)row * D >> 2) + c, p, inv_keep, seed));
+            dh[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+            s1 += (dh[i].x + dh[i].y) + (dh[i].z + dh[i].w);
+            s2 += (dh[i].x * xh[i].x + dh[i].y * xh[i].y) + (dh[i].z * xh[i].z + dh[i].w * xh[i].w);
+        }
     }
+    s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+            float4 o;
+            o.x = rs * (dh[i].x - s1 - xh[i].x * s2); o.y = rs * (dh[i].y - s1 - xh[i].y * s2);
+            o.z = rs * (dh[i].z - s1 - xh[i].z * s2); o.w = rs * (dh[i].w - s1 - xh[i].w * s2);
+            if (addend) {          // the gradient that reaches x past this LayerNorm (a pre-LN residual branch): summed here, not in an extra pass
+                const float4 a = reinterpret_cast<const float4*>(addend + (size_t)row * D)[c];
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            reinterpret_cast<float4*>(dx + (size_t)row * D)[c] = o;
+        }
+    }
+}
+
+constexpr int LNP_CHUNK_ROWS = 256;
+__global__ void __launch_bounds__(256) layernorm_bwd_param_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd, int act, float p,
+                                                                  uint64_t seed, const unsigned long long* __restrict__ seed_off,
+                                                                  float* __restrict__ part, int M, int D) {
+    if (seed_off) seed += *seed_off;
+    __shared__ float4 red[2][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;                           // float4 column index
+    const int m0 = blockIdx.y * LNP_CHUNK_ROWS, m1 = min(M, m0 + LNP_CHUNK_ROWS);
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
-    for (int rr = warp; rr < LNB_ROWS; rr += 8) {
-        const int row = blockIdx.x * LNB_ROWS + rr;
-        if (row >= M) break;
-        const float mu = mean[row], rs = rstd[row];
-        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
-        float4 xh[MAXV], dh[MAXV];
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = lane + 32 * i;
-            if (c < nv) {
-                const float4 xv = xr[c], g = reinterpret_cast<const float4*>(gamma)[c];
-                float4 d = load4(dy, dy_dtype, (size_t)row * D + 4 * c);
-                const float4 k = drop4(((size_t)row * D >> 2) + c, p, inv_keep, seed);
-                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-                d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w;
-                if (act != ACT_NONE) {
-                    const float4 b = reinterpret_cast<const float4*>(beta)[c];
-                    d.x *= act_grad(fmaf(xh[i].x, g.x, b.x), act); d.y *= act_grad(fmaf(xh[i].y, g.y, b.y), act);
-                    d.z *= act_grad(fmaf(xh[i].z, g.z, b.z), act); d.w *= act_grad(fmaf(xh[i].w, g.w, b.w), act);
-                }
-                // this lane's own shared-memory slots (the same ones for every row of the warp): no conflicts, no atomics
-                float4 ab = sb[c], ag = sg[c];
-                ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
-                ag.x = fmaf(d.x, xh[i].x, ag.x); ag.y = fmaf(d.y, xh[i].y, ag.y); ag.z = fmaf(d.z, xh[i].z, ag.z); ag.w = fmaf(d.w, xh[i].w, ag.w);
-                sb[c] = ab; sg[c] = ag;
-                dh[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-                s1 += (dh[i].x + dh[i].y) + (dh[i].z + dh[i].w);
-                s2 += (dh[i].x * xh[i].x + dh[i].y * xh[i].y) + (dh[i].z * xh[i].z + dh[i].w * xh[i].w);
-            }
-        }
-        s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = lane + 32 * i;
-            if (c < nv) {
-                float4 o;
-                o.x = rs * (dh[i].x - s1 - xh[i].x * s2); o.y = rs * (dh[i].y - s1 - xh[i].y * s2);
-                o.z = rs * (dh[i].z - s1 - xh[i].z * s2); o.w = rs * (dh[i].w - s1 - xh[i].w * s2);
-                reinterpret_cast<float4*>(dx + (size_t)row * D)[c] = o;
-            }
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    if (4 * c < D) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+#pragma unroll 4
+        for (int m = m0 + ty; m < m1; m += 8) {
+            const float mu = mean[m], rs = rstd[m];
+            const float4 xv = reinterpret_cast<const float4*>(x + (size_t)m * D)[c];
+            const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+            const float4 d = ln_bwd_dterm(load4(dy, dy_dtype, (size_t)m * D + 4 * c), xh, g, beta, c, act, drop4(((size_t)m * D >> 2) + c, p, inv_keep, seed));
+            ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+            ag.x = fmaf(d.x, xh.x, ag.x); ag.y = fmaf(d.y, xh.y, ag.y); ag.z = fmaf(d.z, xh.z, ag.z); ag.w = fmaf(d.w, xh.w, ag.w);
         }
     }
+    red[0][ty][tx] = ag; red[1][ty][tx] = ab;
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
-        const int which = i / D, c = i - which * D;
-        float a = 0.f;
+    if (ty < 2 && 4 * c < D) {                                    // ty 0: dgamma terms, ty 1: dbeta terms; fixed order over the 8 row lanes
+        float4 a = red[ty][0][tx];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) a += sm[(size_t)(w * 2 + which) * D + c];
-        part[((size_t)blockIdx.x * 2 + which) * D + c] = a;
+        for (int w = 1; w < 8; ++w) { const float4 b = red[ty][w][tx]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * 2 + ty) * D)[c] = a;
     }
 }
 __global__ void __launch_bounds__(256) layernorm_param_reduce_kernel(const float* __restrict__ part, int nparts, int D, float* __restrict__ dgamma,
@@ -485,23 +505,22 @@ int nsd_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
-size_t nsd_layernorm_bwd_workspace(int M, int D) { return sizeof(float) * 2 * (size_t)D * (size_t)cdiv(std::max(M, 1), LNB_ROWS); }
+size_t nsd_layernorm_bwd_workspace(int M, int D) { return sizeof(float) * 2 * (size_t)D * (size_t)cdiv(std::max(M, 1), LNP_CHUNK_ROWS); }
 int nsd_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
-                      float p_drop, uint64_t seed, float* dx, float* dgamma, float* dbeta, int M, int D, void* workspace, size_t workspace_bytes,
-                      void* stream) {
+                      float p_drop, uint64_t seed, const float* dx_addend, float* dx, float* dgamma, float* dbeta, int M, int D, void* workspace,
+                      size_t workspace_bytes, void* stream) {
     NSD_CHECK_ARG(M >= 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXV, "layernorm_bwd: bad sizes M=%d D=%d", M, D);
     NSD_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && dgamma && dbeta && (dy_dtype == NSD_F32 || dy_dtype == NSD_BF16), "layernorm_bwd: bad argument");
     if (workspace_bytes < nsd_layernorm_bwd_workspace(M, D) || !workspace) { set_error("layernorm_bwd: workspace too small"); return NSD_ERR_WORKSPACE; }
-    const int parts = cdiv(std::max(M, 1), LNB_ROWS);
-    const size_t smem = sizeof(float) * 16 * (size_t)D;
-#define NSD_LN_BWD(V)                                                                                                                      \
-    do {                                                                                                                                   \
-        if (smem > 48 * 1024) NSD_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        layernorm_bwd_kernel<V><<<parts, 256, smem, (cudaStream_t)stream>>>(dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(), dx, \
-                                                                            (float*)workspace, M, D);                                      \
-    } while (0)
+    if (M == 0) return NSD_OK;
+    const int parts = cdiv(M, LNP_CHUNK_ROWS);
+    cudaStream_t st = (cudaStream_t)stream;
+#define NSD_LN_BWD(V) layernorm_bwd_dx_kernel<V><<<cdiv(M, 8), 256, 0, st>>>(dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(), dx_addend, dx, M, D)
     if (D <= 512) NSD_LN_BWD(4); else if (D <= 1024) NSD_LN_BWD(8); else NSD_LN_BWD(16);
 #undef NSD_LN_BWD
+    NSD_LAUNCH_CHECK();
+    layernorm_bwd_param_kernel<<<dim3(cdiv(D, 128), parts), 256, 0, st>>>(dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(),
+                                                                          (float*)workspace, M, D);
     NSD_LAUNCH_CHECK();
     layernorm_param_reduce_kernel<<<cdiv(2 * D, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, parts, D, dgamma, dbeta);
     NSD_LAUNCH_CHECK();
