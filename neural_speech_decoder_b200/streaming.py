@@ -119,6 +119,24 @@ class StreamingDecoder:
         self._day_w = m.dayWeights.detach().contiguous()
         self._day_b = m.dayBias.detach().contiguous()
 
+    def refresh_weights(self) -> None:
+        """Call after the model's parameters changed (optimizer step, ``load_state_dict``): the fast form holds the addresses of the
+        bf16 weight copies it was set up with (and so does its captured graph); this re-derives them and drops the graph.  The per-push
+        path deliberately does not check parameter versions (it would cost a tenth of the push latency)."""
+        if getattr(self, "_rawring", None) is None:
+            return
+        m, L = self.m, self.m.layer_dim
+        gw = m._gru_weights()
+        self._w_ih = [m._shadows.stacked(("ih", l), [gw[4 * l]]) for l in range(L)]
+        self._w_hh = [m._shadows.stacked(("hh", l), [gw[4 * l + 1]]) for l in range(L)]
+        self._b_ih = [gw[4 * l + 2].detach().contiguous() for l in range(L)]
+        self._b_hh = [gw[4 * l + 3].detach().contiguous() for l in range(L)]
+        self._fc_w = m._shadows.stacked(("fc", 0), [m.fc_decoder_out.weight])
+        self._fc_b = m.fc_decoder_out.bias.detach().contiguous()
+        self._day_w = m.dayWeights.detach().contiguous()
+        self._day_b = m.dayBias.detach().contiguous()
+        self._graph = None
+
     def _fast_state(self):
         return [self.hs, self._hbf, self._rawring, self._x0buf, self._nbins_dev]
 
