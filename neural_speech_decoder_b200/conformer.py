@@ -41,6 +41,41 @@ def _ws(nbytes: int, dev) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
 
 
+# Weight-gradient GEMMs are off the critical path of the backward (nothing downstream reads dW before the optimizer): while
+# ``wgrad_overlap()`` is active they are issued on a side stream and run beside the memory-bound element-wise chain of the main stream
+# (a persistent tcgen05 GEMM leaves registers / threads for such kernels on every SM).  ``conformer_train_step`` turns it on around
+# ``loss.backward()`` and joins the side stream before the optimizer reads the gradients.
+class _Overlap:
+    on = False
+    side = {}
+    pending = None
+
+    @classmethod
+    def stream(cls, dev):
+        s = cls.side.get(dev)
+        if s is None:
+            s = cls.side[dev] = torch.cuda.Stream(dev)
+        return s
+
+
+class wgrad_overlap:
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        self.prev = _Overlap.on
+        _Overlap.on = self.enabled
+        _Overlap.pending = None
+        return self
+
+    def __exit__(self, *exc):
+        _Overlap.on = self.prev
+        if _Overlap.pending is not None:                  # join: the current stream waits for the last weight-gradient GEMM
+            torch.cuda.current_stream(_Overlap.pending[0]).wait_event(_Overlap.pending[1])
+            _Overlap.pending = None
+        return False
+
+
 # ----------------------------------------------------------------------------------------------------------------- autograd pieces
 class _Linear(torch.autograd.Function):
     """y = x W^T + b (nn.Linear).  x bf16 [M,K] -> tcgen05 GEMM with the kept bf16 copy of W; x f32 -> CUDA-core fp32 GEMM."""
@@ -78,10 +113,23 @@ class _Linear(torch.autograd.Function):
                 dyb = torch.empty((M, Np), device=dev, dtype=_bf16)
                 ops.cast_transpose_into(dy, dyb[:, :N], None)
                 ops.colsum(dy, M, N, N, db)
+            if _Overlap.on:
+                main, side = torch.cuda.current_stream(dev), _Overlap.stream(dev)
+                ready = torch.cuda.Event()
+                ready.record(main)                         # dyb (and x) are complete on the main stream at this point
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    ops.gemm(True, False, N, K, M, dyb, Np, x, K, dw, K)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                for t in (dyb, x, dw):                     # the caching allocator must not recycle them under the side stream's GEMM
+                    t.record_stream(side)
+                _Overlap.pending = (dev, done)
+            else:
+                ops.gemm(True, False, N, K, M, dyb, Np, x, K, dw, K)
             if ctx.needs_input_grad[0]:
                 dx = torch.empty((M, K), device=dev, dtype=_bf16)
                 ops.gemm(False, False, M, K, N, dyb, Np, ctx.wb, K, dx, K)
-            ops.gemm(True, False, N, K, M, dyb, Np, x, K, dw, K)
         else:
             dyf = dy if dy.dtype == _f32 else dy.float()
             ops.colsum(dyf, M, N, N, db)
@@ -766,16 +814,19 @@ class FusedAdamW(torch.optim.Optimizer):
 
 
 def conformer_train_step(model, optimizer, X, y, X_len, y_len, day_idx, label_smoothing=0.1, interctc_weight=0.3, white_noise_sd=0.0,
-                         constant_offset_sd=0.0, noise_seed=0):
+                         constant_offset_sd=0.0, noise_seed=0, overlap_wgrad=False):
     """One training step of the transformer branch of the trainer (neural_decoder_trainer.py:181-260): noise augmentation, forward,
-    CTC + InterCTC + label smoothing, backward, gradient clipping and AdamW, all on the CUDA kernels.  Returns the loss tensor."""
+    CTC + InterCTC + label smoothing, backward, gradient clipping and AdamW, all on the CUDA kernels.  Returns the loss tensor.
+    ``overlap_wgrad``: issue the weight-gradient GEMMs on a side stream beside the element-wise chain (pays off when the step is replayed as a
+    graph -- GraphedConformerStep switches it on; issued eagerly from Python the extra events cost more host time than the overlap gains)."""
     model.train()
     if white_noise_sd > 0 or constant_offset_sd > 0:
         X = ops.input_noise(X, white_noise_sd, constant_offset_sd, noise_seed)
     log_probs, out_lens, inter = model(X, day_idx, X_len)
     loss = conformer_loss(log_probs, inter, y, out_lens, y_len, label_smoothing, interctc_weight)
     optimizer.zero_grad(set_to_none=True)
-    loss.backward()
+    with wgrad_overlap(overlap_wgrad):
+        loss.backward()
     optimizer.step()
     return loss
 
@@ -847,7 +898,8 @@ class GraphedConformerStep:
 
     def _body(self):
         ls, iw, wsd, csd = self.cfg
-        self.loss = conformer_train_step(self.model, self.opt, self.X, self.y, self.X_len, self.y_len, self.day, ls, iw, wsd, csd, noise_seed=12345)
+        self.loss = conformer_train_step(self.model, self.opt, self.X, self.y, self.X_len, self.y_len, self.day, ls, iw, wsd, csd, noise_seed=12345,
+                                         overlap_wgrad=True)
 
     def _capture(self):
         m, opt = self.model, self.opt
