@@ -19,8 +19,12 @@ class FusedAdam(torch.optim.Optimizer):
         self.shadows = shadows
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, only=None):
+        """``only``: optional collection of parameters -- update just those (each parameter keeps its own step count, so a step
+        may be split into several calls; the data-parallel train_step updates the buckets whose all-reduce has finished while
+        the last one is still on the wire)."""
         loss = None
+        only_ids = None if only is None else {id(p) for p in only}
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
@@ -30,6 +34,8 @@ class FusedAdam(torch.optim.Optimizer):
             touched = []
             for p in group["params"]:
                 if p.grad is None:            # the reference's dead inpLayer* parameters never get one
+                    continue
+                if only_ids is not None and id(p) not in only_ids:
                     continue
                 if not p.is_cuda or p.dtype != torch.float32:
                     raise RuntimeError("FusedAdam (B200) handles CUDA float32 parameters only")

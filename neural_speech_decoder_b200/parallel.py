@@ -25,6 +25,7 @@ class GradSync:
         self.group = group
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.handles: List = []
+        self._storages: List = []
         self.bytes = 0
         self.reserve_sms = int(reserve_sms) if self.world > 1 else 0
         self.tail_sms = int(tail_sms) if self.world > 1 else 0
@@ -37,6 +38,7 @@ class GradSync:
 
     def begin(self) -> None:
         self.handles, self.bytes = [], 0
+        self._storages = []            # per handle: (storage address, bytes) of the bucket -- tells which parameters' gradients it holds
         if self.timeline is not None:
             self.timeline.clear()
             self._t0 = torch.cuda.Event(enable_timing=True)
@@ -57,6 +59,7 @@ class GradSync:
             ready.record()                                  # on the compute stream: the bucket's last wgrad has been enqueued before this point
         h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.handles.append(h)
+        self._storages.append((flat.untyped_storage().data_ptr(), flat.numel() * flat.element_size()))
         if self.timeline is not None:
             side = torch.cuda.Stream(flat.device)           # a stream that waits for THIS collective only: its event is the collective's end
             done = torch.cuda.Event(enable_timing=True)
@@ -65,10 +68,31 @@ class GradSync:
                 done.record()
             self.timeline.append((flat.numel() * flat.element_size(), ready, done))
 
+    def finish_early(self, tail_bytes: int = 32 << 20) -> set:
+        """Make the current stream wait for every collective EXCEPT the tail of the queue: the last bucket of at least
+        ``tail_bytes`` (layer 0's 226 MB, final when only its dgrad GEMM and the front-end backward are left to hide it) and the
+        small ones released after it.  Returns the storage addresses of the buckets still in flight, so that the caller can
+        update the parameters of the finished buckets while the tail is on the wire (trainer.train_step does; measured timeline:
+        profiles/r02_allreduce_timeline_2gpu.json) and then call ``finish()``.  NCCL runs the collectives of one communicator in
+        order, so waiting for handle k covers every earlier one."""
+        n = len(self.handles)
+        cut = n
+        for i in range(n - 1, -1, -1):
+            cut = i
+            if self._storages[i][1] >= tail_bytes:
+                break
+        if n == 0 or self._storages[cut][1] < tail_bytes:
+            cut = n                                          # no big bucket: nothing worth deferring
+        for h in self.handles[:cut]:
+            h.wait()
+        pending = {a for a, _ in self._storages[cut:]}
+        self.handles, self._storages = self.handles[cut:], self._storages[cut:]
+        return pending
+
     def finish(self) -> None:
         for h in self.handles:
             h.wait()                      # current stream waits for the collective; no host block on NCCL
-        self.handles = []
+        self.handles, self._storages = [], []
         if self.timeline is not None:
             self._t1 = torch.cuda.Event(enable_timing=True)
             self._t1.record()                               # compute stream: backward enqueued and every collective waited for

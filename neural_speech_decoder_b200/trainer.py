@@ -51,9 +51,24 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
     if grad_sync is not None:
         grad_sync.begin()
     loss.backward()                                                         # trainer:252
-    if grad_sync is not None:
-        grad_sync.finish()
-    optimizer.step()                                                        # trainer:259
+    if grad_sync is not None and grad_sync.world > 1 and isinstance(optimizer, FusedAdam):
+        # the last big bucket (layer 0) is still being all-reduced when the backward's kernels are done: update the parameters of
+        # every finished bucket under it, then the rest (same arithmetic per parameter; the step is just issued in two launches)
+        pending = grad_sync.finish_early()
+        if pending:
+            live = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+            late = [p for p in live if p.grad.untyped_storage().data_ptr() in pending]
+            late_ids = {id(p) for p in late}
+            optimizer.step(only=[p for p in live if id(p) not in late_ids])
+            grad_sync.finish()
+            optimizer.step(only=late)
+        else:
+            grad_sync.finish()
+            optimizer.step()
+    else:
+        if grad_sync is not None:
+            grad_sync.finish()
+        optimizer.step()                                                    # trainer:259
     if scheduler is not None:
         scheduler.step()                                                    # trainer:260
     return loss.detach()

@@ -277,6 +277,26 @@ def test_fused_adam_matches_torch_adam():
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
 
 
+def test_fused_adam_split_step_is_bit_identical():
+    """step(only=...) in two calls (what the data-parallel train_step does under the last all-reduce) == one step()."""
+    torch.manual_seed(1)
+    shapes = [(300, 77), (5,), (512, 640), (3, 1, 9)]
+    ps = [torch.randn(s, device=DEV) for s in shapes]
+    one = [p.clone().requires_grad_(True) for p in ps]
+    two = [p.clone().requires_grad_(True) for p in ps]
+    kw = dict(lr=0.02, betas=(0.9, 0.999), eps=0.1, weight_decay=1e-5, grad_scale=0.5)
+    o_one, o_two = nsd.adam.FusedAdam(one, **kw), nsd.adam.FusedAdam(two, **kw)
+    for it in range(3):
+        for a, b in zip(one, two):
+            g = torch.randn_like(a)
+            a.grad = g.clone(); b.grad = g.clone()
+        o_one.step()
+        o_two.step(only=two[:2]); o_two.step(only=two[2:])
+    for a, b in zip(one, two):
+        assert torch.equal(a, b)
+        assert o_two.state[b]["step"] == 3
+
+
 def test_input_noise_moments_and_fused_front_end():
     """trainer:194-201: X += randn*whiteNoiseSD; X += randn([B,1,N])*constantOffsetSD.  Distributional parity (own
     counter-based generator): moments of the two components; the copy fused into K1 must equal K1 of the explicitly

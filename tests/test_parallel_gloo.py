@@ -55,7 +55,11 @@ def _worker(rank, world, port, out):
         flat = torch.cat([g.reshape(-1) for g in chunk])
         gs.bucket_ready(flat)
         flats.append((flat, chunk))
+    # the split finish the trainer uses: everything before the last bucket of >= tail_bytes is waited for, the tail stays in flight
+    pending = gs.finish_early(tail_bytes=flats[1][0].numel() * 4)
+    assert pending == {flats[1][0].untyped_storage().data_ptr()} and len(gs.handles) == 1
     gs.finish()
+    assert gs.handles == []
     assert gs.bytes == sum(f.numel() * 4 for f, _ in flats)
     if rank == 0:
         red = []
