@@ -101,6 +101,13 @@ __device__ __forceinline__ void red_release_add(unsigned int* p) {
 constexpr int PUB_THREADS = WG_THREADS + 32;
 __device__ __forceinline__ void pub_arrive(int w, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(3 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
 __device__ __forceinline__ void pub_sync(int w, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(3 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
+// "fence done" hand-back (one chain per warpgroup only): the publisher ARRIVES once its release fence + counter add have been issued, the
+// epilogue threads SYNC on it before they issue their deferred stores.  MEMBAR.GPU waits for every store the SM has in flight, so deferred
+// stores issued between pub_arrive and the publisher's fence (which the early-arriving threads otherwise do) lengthen the critical publish
+// by 0.2-0.3 us per step (profiles/r02_k3_bounds.log).  The epilogue threads have nothing else to do until the next step's accumulator.
+// With two chains per warpgroup (64-row chains) the wait would hold up the other chain: measured slower in the forward (12.0 -> 13.1 us), so not used there.
+__device__ __forceinline__ void done_arrive(int w, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(7 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
+__device__ __forceinline__ void done_sync(int w, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(7 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
 __device__ __forceinline__ void wg_bar_sync(int w) { asm volatile("bar.sync %0, %1;" ::"r"(1 + w), "n"(WG_THREADS) : "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]: A = stationary weights, lane = row, two bf16 of consecutive k per 32-bit column
@@ -127,7 +134,9 @@ struct Common {
     int cs, upz, nzone;                     // CTAs per cluster, units per zone (= per cluster), zones per direction
     unsigned int* counters;                 // [D][nchain][nzone] step counters, CNT_STRIDE apart: cs * WPC arrivals per step
     long long* trace;                       // debug (NSD_GRU_TRACE=1)
-    int dbg;                                // timing experiments only (WRONG RESULTS): bit 0 = skip the zone waits, bit 1 = publish without release fence
+    int dbg;                                // timing experiments only (WRONG RESULTS): bit 0 = skip the zone waits, bit 1 = publish without release fence,
+                                            // bit 2 = no consumer-side proxy fence, bit 3 = skip the deferred (off-critical-path) stores,
+                                            // bit 4 (results stay right) = deferred stores not held back behind the publisher's fence
 };
 // Debug stamps go to shared memory (a global store here would sit in front of the next fence) and are dumped at exit.
 __device__ __forceinline__ void stamp(const Common& c, long long* tsm, int s, int ev) {
@@ -257,12 +266,14 @@ __device__ __forceinline__ void publisher_warp(const Smem& sm, const Common& c, 
             for (int k = 0; k < WPC; ++k) {
                 const int chain = 2 * pr + (WPC == 1 ? w : k);
                 if (chain >= c.nchain) continue;
-                pub_sync(w, n++);
+                pub_sync(w, n);
                 if (lane == 0) {
                     publish(c, zone_counter(c, d, chain, my_zone));
                     if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
                 }
                 __syncwarp();
+                if (WPC == 1 && !(c.dbg & 16)) done_arrive(w, n);
+                ++n;
             }
 }
 
@@ -300,7 +311,7 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                     }
                     __syncwarp();
                     if (lane == 0 && chain == 0) stamp(c, sm.trace, s, 0);
-                    if (lane == 0) asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy writes (acquired above) -> TMA reads
+                    if (lane == 0 && !(c.dbg & 4)) asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy writes (acquired above) -> TMA reads
                     const int row = t_src * c.B + chain * NROW + c.row_off;
                     for (int sub = 0; sub < nsub; ++sub, ++seq) {
                         const uint32_t stage = seq & 1u, use = seq >> 1;
@@ -588,9 +599,11 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                         st4_bf16(p.hseq_bf + (m + c.row_off) * p.ldh + d * H + ub, k_h[k]);
                     }
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
-                    pub_arrive(w, npub++);                       // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
+                    pub_arrive(w, npub);                         // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
+                    if (WPC == 1 && !(c.dbg & 16)) done_sync(w, npub);      // deferred stores only after the publisher's fence has been issued
+                    ++npub;
                     if (WPC > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
-                    if (row_ok) {                                // off the critical path: nobody else reads these during the launch
+                    if (row_ok && !(c.dbg & 8)) {                // off the critical path: nobody else reads these during the launch
                         st4(p.hseq + m * p.ldh + d * H + ub, k_h[k]);
                         if (p.r) {
                             const size_t o = ((size_t)d * c.Tp * B + m) * H + ub;
@@ -760,12 +773,14 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                         }
                     }
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
-                    pub_arrive(w, npub++);                       // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
+                    pub_arrive(w, npub);                         // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
+                    if (WPC == 1 && !(c.dbg & 16)) done_sync(w, npub);      // deferred stores only after the publisher's fence has been issued
+                    ++npub;
                     if (WPC > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {               // off the critical path
                         const int ub = ub0 + 16 * q;
-                        if (b < B && ub < H) {
+                        if (b < B && ub < H && !(c.dbg & 8)) {
                             __nv_bfloat16* gi_row = p.dgi + m * p.ldg + d * 3 * H + ub;
                             st4_bf16(gi_row, drt[q]); st4_bf16(gi_row + H, dzt[q]); st4_bf16(gi_row + 2 * H, dnt[q]);
                             if (p.db_ih) {                       // bias gradients: fp32 sums over (t, b) of dgi and dgh, this thread's cells
