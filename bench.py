@@ -288,9 +288,12 @@ def run_ours(a):
 
     feed = nsd.BatchPrefetcher(host_batches(), dev)         # the copy of step i+1 runs under the kernels of step i
 
+    reader = nsd.LossReader(dev)                            # the step's loss lands in pinned host memory as soon as the forward has produced it
+
     def step_e2e():
         b = next(feed)
-        return nsd.train_step(model, opt, *b, scheduler=sched, grad_sync=gs, **NOISE).item()
+        nsd.train_step(model, opt, *b, scheduler=sched, grad_sync=gs, loss_reader=reader, **NOISE)
+        return reader.item()                                # D2H read of this step's loss, every step (4 bytes)
 
     def barrier():
         if world > 1:

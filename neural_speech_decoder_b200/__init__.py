@@ -13,7 +13,7 @@ from ._lib import NsdError, lib  # noqa: F401
 from .model import GRUDecoder, set_default_precision  # noqa: F401
 from .ctc import (CTCLoss, ctc_loss_from_logits, greedy_decode, decoded_to_lists, edit_distances,  # noqa: F401
                   phoneme_error_rate, out_lens)
-from .trainer import train_step, eval_batch, make_optimizer  # noqa: F401
+from .trainer import train_step, eval_batch, make_optimizer, LossReader  # noqa: F401
 from .ops import input_noise  # noqa: F401   trainer:194-201 as one kernel
 from .streaming import StreamingDecoder  # noqa: F401   stateful incremental inference (no counterpart in the reference)
 from .conformer import (NeuralTransformerCTCModel, conformer_loss, conformer_train_step, FusedAdamW, lr_lambda, GraphedConformerStep)  # noqa: F401   transformer_ctc.py:333-501

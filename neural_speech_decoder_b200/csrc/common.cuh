@@ -36,6 +36,28 @@ void count_launch(int n);   // kernels enqueued by this library (nsd_launch_coun
         NSD_CUDA(cudaGetLastError());   \
     } while (0)
 
+// Programmatic dependent launch.  Every kernel launched through launch_k() carries the programmatic-stream-serialization attribute: it
+// may be scheduled while its predecessor in the stream is still running, and MUST execute pdl_enter() (or pdl_wait()) before it touches
+// global memory -- griddepcontrol.wait returns once every prerequisite grid has completed and its writes are visible.
+// pdl_launch_dependents() at the top of a kernel lets the next launch's CTAs take SM resources as they free up and run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch) under this kernel's tail: it removes the few microseconds of launch latency and
+// ramp between the ~100 (GRU step) / ~750 (Conformer step) short kernels of a training step.  Both instructions are no-ops in a kernel
+// launched without the attribute.  NSD_PDL=0 turns the attribute off (A/B).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface through cudaGetLastError (NSD_LAUNCH_CHECK)
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }
 

@@ -160,6 +160,7 @@ __device__ __forceinline__ void bg_load_tile(ST (*sm)[BG_K + BG_PAD], const void
 
 template <bool TC>
 __global__ void __launch_bounds__(128) bgemm_kernel(const BgemmParams p) {
+    pdl_enter();
     using ST = typename std::conditional<TC, __nv_bfloat16, float>::type;
     __shared__ __align__(16) ST As[BG_T][BG_K + BG_PAD];
     __shared__ __align__(16) ST Bs[BG_T][BG_K + BG_PAD];      // [n][k]
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(128) bgemm_kernel(const BgemmParams p) {
 __global__ void __launch_bounds__(256) softmax_mask_fwd_kernel(float* __restrict__ S, void* __restrict__ Pd, int pd_dtype, const int32_t* __restrict__ lens,
                                                                long long rows, int HT, int T, int ld, float p, uint64_t seed,
                                                                const unsigned long long* __restrict__ seed_off) {
+    pdl_enter();
     // a lane owns groups of 4 consecutive scores (ld % 4 == 0): 16-byte accesses, and ONE Philox block per group for the dropout mask
     // (element r*ld + j: the padded index, so that a group never straddles two blocks)
     if (seed_off) seed += *seed_off;
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(256) softmax_mask_fwd_kernel(float* __restrict
 // dS = P * (dP - sum_j dP_j P_j), dP = dropout-backward of dPd (in place over dPd)
 __global__ void __launch_bounds__(256) softmax_mask_bwd_kernel(const float* __restrict__ P, float* __restrict__ dPd, long long rows, int T, int ld, float p,
                                                                uint64_t seed, const unsigned long long* __restrict__ seed_off) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(256) softmax_mask_bwd_kernel(const float* __re
 constexpr int SQ_MAX_TENSORS = 160, SQ_CHUNK = 32768;
 struct SqTable { const float* g[SQ_MAX_TENSORS]; long long n[SQ_MAX_TENSORS]; int chunk_start[SQ_MAX_TENSORS + 1]; int count; };
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const __grid_constant__ SqTable tab, float* __restrict__ part, int part0) {
+    pdl_enter();
     __shared__ float sm[8];
     int ti = 0;
     while (ti + 1 < tab.count && (int)blockIdx.x >= tab.chunk_start[ti + 1]) ++ti;
@@ -397,6 +401,7 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const __grid_consta
     }
 }
 __global__ void __launch_bounds__(1024) sqnorm_final_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+    pdl_enter();
     __shared__ float sm[32];
     float a = 0.f;
     for (int i = threadIdx.x; i < n; i += 1024) a += part[i];
@@ -431,8 +436,8 @@ int nsd_bgemm(const void* A, int a_dtype, int64_t a_rs, int64_t a_cs, int64_t a_
     const dim3 grid(cdiv(N, BG_T), cdiv(M, BG_T), nb0 * nb1);
     // bf16 anywhere among the operands -> tensor-core path (operands rounded to bf16 in shared memory); all-fp32 -> FFMA parity path
     const bool tc = tc_mode < 0 ? (a_dtype == NSD_BF16 || b_dtype == NSD_BF16) : tc_mode != 0;
-    if (tc) bgemm_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
-    else bgemm_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    if (tc) nsd::launch_k(bgemm_kernel<true>, grid, 128, 0, (cudaStream_t)stream, p);
+    else nsd::launch_k(bgemm_kernel<false>, grid, 128, 0, (cudaStream_t)stream, p);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -441,7 +446,7 @@ int nsd_softmax_mask_fwd(float* S, void* Pd, int pd_dtype, const int32_t* lens, 
     NSD_CHECK_ARG(S && B >= 0 && H >= 1 && T >= 1 && ld >= T && ld % 4 == 0 && p_drop >= 0.f && p_drop < 1.f && (!Pd || pd_dtype == NSD_F32 || pd_dtype == NSD_BF16), "softmax_mask_fwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
-    softmax_mask_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, Pd, pd_dtype, lens, rows, H * T, T, ld, p_drop, seed, seed_offset_ptr());
+    nsd::launch_k(softmax_mask_fwd_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, S, Pd, pd_dtype, lens, rows, H * T, T, ld, p_drop, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -449,7 +454,7 @@ int nsd_softmax_mask_bwd(const float* P, float* dPd, int B, int H, int T, int ld
     NSD_CHECK_ARG(P && dPd && B >= 0 && H >= 1 && T >= 1 && ld >= T && ld % 4 == 0 && p_drop >= 0.f && p_drop < 1.f, "softmax_mask_bwd: bad argument");
     const long long rows = (long long)B * H * T;
     if (rows == 0) return NSD_OK;
-    softmax_mask_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, dPd, rows, T, ld, p_drop, seed, seed_offset_ptr());
+    nsd::launch_k(softmax_mask_bwd_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, P, dPd, rows, T, ld, p_drop, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -476,11 +481,11 @@ int nsd_sqnorm_multi(int n_tensors, const void* const* grads, const int64_t* num
         }
         tab.chunk_start[tab.count] = chunks;
         if (chunks == 0) continue;
-        sqnorm_partial_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(tab, part, total);
+        nsd::launch_k(sqnorm_partial_kernel, chunks, 256, 0, (cudaStream_t)stream, tab, part, total);
         NSD_LAUNCH_CHECK();
         total += chunks;
     }
-    sqnorm_final_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(part, total, out);
+    nsd::launch_k(sqnorm_final_kernel, 1, 1024, 0, (cudaStream_t)stream, part, total, out);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             float eps, int act, float p, uint64_t seed, const unsigned long long* __restrict__ seed_off,
                                                             float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean, float* __restrict__ rstd,
                                                             int M, int D) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_dx_kernel(const void* __
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd, int act, float p,
                                                                   uint64_t seed, const unsigned long long* __restrict__ seed_off,
                                                                   const float* __restrict__ addend, float* __restrict__ dx, int M, int D) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_param_kernel(const void* __
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd, int act, float p,
                                                                   uint64_t seed, const unsigned long long* __restrict__ seed_off,
                                                                   float* __restrict__ part, int M, int D) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     __shared__ float4 red[2][8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_param_kernel(const void* __
 }
 __global__ void __launch_bounds__(256) layernorm_param_reduce_kernel(const float* __restrict__ part, int nparts, int D, float* __restrict__ dgamma,
                                                                      float* __restrict__ dbeta) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * D) return;
     const int which = i / D, c = i - which * D;
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(256) layernorm_param_reduce_kernel(const float
 // ------------------------------------------------------------------------------------------------ activation (+dropout), GLU
 __global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, int act, float p, uint64_t seed, const unsigned long long* __restrict__ seed_off,
                                                       float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, size_t n4) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
@@ -217,6 +222,7 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ 
 }
 __global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const float* __restrict__ x, int act, float p,
                                                       uint64_t seed, const unsigned long long* __restrict__ seed_off, float* __restrict__ dx, size_t n4) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ d
 }
 __device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + __expf(-v)); }
 __global__ void __launch_bounds__(256) glu_fwd_kernel(const float* __restrict__ u, float* __restrict__ g, int M, int D) {
+    pdl_enter();
     const size_t n4 = (size_t)M * D >> 2;
     const int d4 = D >> 2;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(256) glu_fwd_kernel(const float* __restrict__ 
     }
 }
 __global__ void __launch_bounds__(256) glu_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ u, float* __restrict__ du, int M, int D) {
+    pdl_enter();
     const size_t n4 = (size_t)M * D >> 2;
     const int d4 = D >> 2;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
@@ -255,6 +263,7 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__ x, const float* __restrict__ y, float scale, float p, uint64_t seed,
                                                        float p_path, uint64_t path_seed, const unsigned long long* __restrict__ seed_off, size_t elems_per_sample,
                                                        float* __restrict__ out, size_t n4) {
+    pdl_enter();
     if (seed_off) { seed += *seed_off; path_seed += *seed_off; }
     const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.f;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
@@ -272,6 +281,7 @@ __global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__
 constexpr int DW_TT = 16, DW_MAXK = 32;
 __global__ void __launch_bounds__(128) dwconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ y, int T, int D, int k, int flip, int w_shared) {
+    pdl_enter();
     extern __shared__ float ws[];                       // [128][k] as stored (odd k: a thread's taps sit 'k' words apart -> conflict-free)
     const int d = blockIdx.x * 128 + threadIdx.x, b = blockIdx.z, t0 = blockIdx.y * DW_TT, pad = k / 2;
     float win[DW_TT + DW_MAXK - 1], wreg[DW_MAXK];
@@ -303,6 +313,7 @@ __global__ void __launch_bounds__(128) dwconv_fwd_kernel(const float* __restrict
 // reduced in fixed order by dwconv_w_reduce_kernel.
 __global__ void __launch_bounds__(128) dwconv_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part, int B,
                                                            int T, int D, int k, int b_per_cta) {
+    pdl_enter();
     // thread = one channel; per 16-frame tile the gradient rows and the input window live in registers and feed all k tap sums
     const int d = blockIdx.x * 128 + threadIdx.x, pad = k / 2;
     if (d >= D) return;
@@ -338,6 +349,7 @@ __global__ void __launch_bounds__(128) dwconv_bwd_w_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) dwconv_w_reduce_kernel(const float* __restrict__ part, int nparts, int D, int k, float* __restrict__ dw,
                                                               float* __restrict__ db) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D * (k + 1)) return;
     float a = 0.f;
@@ -350,6 +362,7 @@ __global__ void __launch_bounds__(256) dwconv_w_reduce_kernel(const float* __res
 // strided depthwise conv without padding: y[b,j,c] = sum_k w[c][k] x[b, j*S + k, c], j < T' = (T-K)/S + 1
 __global__ void __launch_bounds__(128) strided_dwconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y32,
                                                                  __nv_bfloat16* __restrict__ y16, int T, int N, int K, int S, int Tp) {
+    pdl_enter();
     const int c = blockIdx.x * 128 + threadIdx.x, j = blockIdx.y, b = blockIdx.z;
     if (c >= N) return;
     const float* xb = x + ((size_t)b * T + (size_t)j * S) * N + c;
@@ -363,6 +376,7 @@ __global__ void __launch_bounds__(128) strided_dwconv_fwd_kernel(const float* __
 // dx[b,t,c] = sum_{(j,k): jS+k=t} dy[b,j,c] w[c][k]   (gather form: deterministic)
 __global__ void __launch_bounds__(128) strided_dwconv_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
                                                                    int T, int N, int K, int S, int Tp) {
+    pdl_enter();
     const int c = blockIdx.x * 128 + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
     if (c >= N) return;
     float acc = 0.f;
@@ -373,6 +387,7 @@ __global__ void __launch_bounds__(128) strided_dwconv_bwd_x_kernel(const float* 
 // dw[c][k] partials per utterance chunk: thread = (channel, tap)
 __global__ void __launch_bounds__(256) strided_dwconv_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part,
                                                                    int B, int T, int N, int K, int S, int Tp, int b_per_cta) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, c = blockIdx.x * 32 + lane;
     if (c >= N) return;
     const int b0 = blockIdx.y * b_per_cta, b1 = min(B, b0 + b_per_cta);
@@ -390,6 +405,7 @@ __global__ void __launch_bounds__(256) strided_dwconv_bwd_w_kernel(const float* 
 struct Bands { int v[8]; };
 __global__ void __launch_bounds__(256) posenc_mask_kernel(const float* __restrict__ z, const float* __restrict__ pe, Bands bands,
                                                           const int* __restrict__ bands_dev, float* __restrict__ out, int T, int D, size_t n4) {
+    pdl_enter();
     if (bands_dev) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) bands.v[i] = bands_dev[i];
@@ -415,6 +431,7 @@ __global__ void __launch_bounds__(256) posenc_mask_kernel(const float* __restric
 // out[d] = sum over the rows b with index[b] == d, in row order (dayWeights / dayBias gradients: index_select backward)
 __global__ void __launch_bounds__(256) index_reduce_kernel(const float* __restrict__ part, const int64_t* __restrict__ index, int B, size_t n, int n_out,
                                                            float* __restrict__ out) {
+    pdl_enter();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int d = blockIdx.y;
     if (i >= n) return;
@@ -424,10 +441,12 @@ __global__ void __launch_bounds__(256) index_reduce_kernel(const float* __restri
     out[(size_t)d * n + i] = a;
 }
 __global__ void __launch_bounds__(256) axpb_kernel(const float* __restrict__ x, float a, float b, float* __restrict__ y, size_t n) {
+    pdl_enter();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = fmaf(a, x[i], b);
 }
 // out = a * in + b*out0 ... single-CTA deterministic sum (the KL term of the label-smoothed loss is a plain sum of log-probs)
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, size_t n, float scale, float add, int accumulate, float* __restrict__ out) {
+    pdl_enter();
     __shared__ float sm[32];
     float a = 0.f;
     for (size_t i = threadIdx.x; i < n; i += 1024) a += x[i];
@@ -442,6 +461,7 @@ __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, 
 // dlogits = dlp - softmax * sum_c dlp   (log_softmax backward, rows of C)
 __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ lp, const float* __restrict__ dlp, float* __restrict__ dl,
                                                               int64_t rows, int C) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -457,6 +477,7 @@ __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __res
 constexpr int CC_CHUNK_ROWS = 256;
 __global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ src, int M, int N, __nv_bfloat16* __restrict__ dst, int ld_dst,
                                                           float* __restrict__ part) {
+    pdl_enter();
     __shared__ float4 red[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int n = blockIdx.x * 128 + 4 * tx;
@@ -479,6 +500,7 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restric
     }
 }
 __global__ void __launch_bounds__(256) colsum_chunks_kernel(const float* __restrict__ part, int N, int chunks, float* __restrict__ out) {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float s = 0.f;
@@ -499,7 +521,7 @@ int nsd_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
     NSD_CHECK_ARG(M >= 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXV, "layernorm_fwd: bad sizes M=%d D=%d (D %% 4 == 0, D <= %d)", M, D, 128 * LN_MAXV);
     NSD_CHECK_ARG(x && gamma && beta && mean && rstd && (y_f32 || y_bf16) && act >= 0 && act <= 3 && p_drop >= 0.f && p_drop < 1.f, "layernorm_fwd: bad argument");
     if (M == 0) return NSD_OK;
-#define NSD_LN_FWD(V) layernorm_fwd_kernel<V><<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, act, p_drop, seed, seed_offset_ptr(), y_f32, (__nv_bfloat16*)y_bf16, mean, rstd, M, D)
+#define NSD_LN_FWD(V) nsd::launch_k(layernorm_fwd_kernel<V>, cdiv(M, 8), 256, 0, (cudaStream_t)stream, x, gamma, beta, eps, act, p_drop, seed, seed_offset_ptr(), y_f32, (__nv_bfloat16*)y_bf16, mean, rstd, M, D)
     if (D <= 512) NSD_LN_FWD(4); else if (D <= 1024) NSD_LN_FWD(8); else NSD_LN_FWD(16);
 #undef NSD_LN_FWD
     NSD_LAUNCH_CHECK();
@@ -515,14 +537,14 @@ int nsd_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
     if (M == 0) return NSD_OK;
     const int parts = cdiv(M, LNP_CHUNK_ROWS);
     cudaStream_t st = (cudaStream_t)stream;
-#define NSD_LN_BWD(V) layernorm_bwd_dx_kernel<V><<<cdiv(M, 8), 256, 0, st>>>(dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(), dx_addend, dx, M, D)
+#define NSD_LN_BWD(V) nsd::launch_k(layernorm_bwd_dx_kernel<V>, cdiv(M, 8), 256, 0, st, dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(), dx_addend, dx, M, D)
     if (D <= 512) NSD_LN_BWD(4); else if (D <= 1024) NSD_LN_BWD(8); else NSD_LN_BWD(16);
 #undef NSD_LN_BWD
     NSD_LAUNCH_CHECK();
-    layernorm_bwd_param_kernel<<<dim3(cdiv(D, 128), parts), 256, 0, st>>>(dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(),
+    nsd::launch_k(layernorm_bwd_param_kernel, dim3(cdiv(D, 128), parts), 256, 0, st, dy, dy_dtype, x, gamma, beta, mean, rstd, act, p_drop, seed, seed_offset_ptr(),
                                                                           (float*)workspace, M, D);
     NSD_LAUNCH_CHECK();
-    layernorm_param_reduce_kernel<<<cdiv(2 * D, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, parts, D, dgamma, dbeta);
+    nsd::launch_k(layernorm_param_reduce_kernel, cdiv(2 * D, 256), 256, 0, (cudaStream_t)stream, (const float*)workspace, parts, D, dgamma, dbeta);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -530,28 +552,28 @@ int nsd_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
 int nsd_act_fwd(const float* x, int act, float p_drop, uint64_t seed, float* y_f32, void* y_bf16, size_t n, void* stream) {
     NSD_CHECK_ARG(x && (y_f32 || y_bf16) && n % 4 == 0 && act >= 0 && act <= 3 && p_drop >= 0.f && p_drop < 1.f, "act_fwd: bad argument (n %% 4 == 0)");
     if (n == 0) return NSD_OK;
-    act_fwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, act, p_drop, seed, seed_offset_ptr(), y_f32, (__nv_bfloat16*)y_bf16, n / 4);
+    nsd::launch_k(act_fwd_kernel, ew_blocks(n / 4), 256, 0, (cudaStream_t)stream, x, act, p_drop, seed, seed_offset_ptr(), y_f32, (__nv_bfloat16*)y_bf16, n / 4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_act_bwd(const void* dy, int dy_dtype, const float* x, int act, float p_drop, uint64_t seed, float* dx, size_t n, void* stream) {
     NSD_CHECK_ARG(dy && x && dx && n % 4 == 0 && act >= 0 && act <= 3 && (dy_dtype == NSD_F32 || dy_dtype == NSD_BF16), "act_bwd: bad argument");
     if (n == 0) return NSD_OK;
-    act_bwd_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, x, act, p_drop, seed, seed_offset_ptr(), dx, n / 4);
+    nsd::launch_k(act_bwd_kernel, ew_blocks(n / 4), 256, 0, (cudaStream_t)stream, dy, dy_dtype, x, act, p_drop, seed, seed_offset_ptr(), dx, n / 4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_glu_fwd(const float* u, float* g, int M, int D, void* stream) {
     NSD_CHECK_ARG(u && g && M >= 0 && D > 0 && D % 4 == 0, "glu_fwd: bad argument");
     if (M == 0) return NSD_OK;
-    glu_fwd_kernel<<<ew_blocks((size_t)M * D / 4), 256, 0, (cudaStream_t)stream>>>(u, g, M, D);
+    nsd::launch_k(glu_fwd_kernel, ew_blocks((size_t)M * D / 4), 256, 0, (cudaStream_t)stream, u, g, M, D);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_glu_bwd(const float* dg, const float* u, float* du, int M, int D, void* stream) {
     NSD_CHECK_ARG(dg && u && du && M >= 0 && D > 0 && D % 4 == 0, "glu_bwd: bad argument");
     if (M == 0) return NSD_OK;
-    glu_bwd_kernel<<<ew_blocks((size_t)M * D / 4), 256, 0, (cudaStream_t)stream>>>(dg, u, du, M, D);
+    nsd::launch_k(glu_bwd_kernel, ew_blocks((size_t)M * D / 4), 256, 0, (cudaStream_t)stream, dg, u, du, M, D);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -560,7 +582,7 @@ int nsd_residual(const float* x, const float* y, float scale, float p_drop, uint
     NSD_CHECK_ARG(y && out && n % 4 == 0 && elems_per_sample > 0 && elems_per_sample % 4 == 0 && p_drop >= 0.f && p_drop < 1.f && p_path >= 0.f && p_path < 1.f,
                   "residual: bad argument");
     if (n == 0) return NSD_OK;
-    residual_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, y, scale, p_drop, seed, p_path, path_seed, seed_offset_ptr(), (size_t)elems_per_sample, out, n / 4);
+    nsd::launch_k(residual_kernel, ew_blocks(n / 4), 256, 0, (cudaStream_t)stream, x, y, scale, p_drop, seed, p_path, path_seed, seed_offset_ptr(), (size_t)elems_per_sample, out, n / 4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -568,7 +590,7 @@ int nsd_residual(const float* x, const float* y, float scale, float p_drop, uint
 int nsd_dwconv_fwd(const float* x, const float* w, const float* bias, float* y, int B, int T, int D, int k, int flip, int w_shared, void* stream) {
     NSD_CHECK_ARG(x && w && y && B >= 0 && T > 0 && D > 0 && k >= 1 && k <= DW_MAXK && (k & 1), "dwconv_fwd: bad argument (odd k <= %d)", DW_MAXK);
     if (B == 0) return NSD_OK;
-    dwconv_fwd_kernel<<<dim3(cdiv(D, 128), cdiv(T, DW_TT), B), 128, sizeof(float) * k * 128, (cudaStream_t)stream>>>(x, w, bias, y, T, D, k, flip, w_shared);
+    nsd::launch_k(dwconv_fwd_kernel, dim3(cdiv(D, 128), cdiv(T, DW_TT), B), 128, sizeof(float) * k * 128, (cudaStream_t)stream, x, w, bias, y, T, D, k, flip, w_shared);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -579,9 +601,9 @@ int nsd_dwconv_bwd_w(const float* dy, const float* x, float* dw, float* db, int 
     NSD_CHECK_ARG(dy && x && dw && B >= 1 && T > 0 && D > 0 && k >= 1 && k <= DW_MAXK && (k & 1), "dwconv_bwd_w: bad argument");
     if (!workspace || workspace_bytes < nsd_dwconv_bwd_w_workspace(B, D, k)) { set_error("dwconv_bwd_w: workspace too small"); return NSD_ERR_WORKSPACE; }
     const int parts = dw_parts(B), per = cdiv(B, parts);
-    dwconv_bwd_w_kernel<<<dim3(cdiv(D, 128), cdiv(B, per)), 128, 0, (cudaStream_t)stream>>>(dy, x, (float*)workspace, B, T, D, k, per);
+    nsd::launch_k(dwconv_bwd_w_kernel, dim3(cdiv(D, 128), cdiv(B, per)), 128, 0, (cudaStream_t)stream, dy, x, (float*)workspace, B, T, D, k, per);
     NSD_LAUNCH_CHECK();
-    dwconv_w_reduce_kernel<<<cdiv(D * (k + 1), 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, cdiv(B, per), D, k, dw, db);
+    nsd::launch_k(dwconv_w_reduce_kernel, cdiv(D * (k + 1), 256), 256, 0, (cudaStream_t)stream, (const float*)workspace, cdiv(B, per), D, k, dw, db);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -589,7 +611,7 @@ int nsd_strided_dwconv_fwd(const float* x, const float* w, float* y_f32, void* y
     NSD_CHECK_ARG(x && w && (y_f32 || y_bf16) && B >= 0 && N > 0 && K >= 1 && S >= 1 && T >= K, "strided_dwconv_fwd: bad argument (T >= K)");
     if (B == 0) return NSD_OK;
     const int Tp = (T - K) / S + 1;
-    strided_dwconv_fwd_kernel<<<dim3(cdiv(N, 128), Tp, B), 128, 0, (cudaStream_t)stream>>>(x, w, y_f32, (__nv_bfloat16*)y_bf16, T, N, K, S, Tp);
+    nsd::launch_k(strided_dwconv_fwd_kernel, dim3(cdiv(N, 128), Tp, B), 128, 0, (cudaStream_t)stream, x, w, y_f32, (__nv_bfloat16*)y_bf16, T, N, K, S, Tp);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -599,11 +621,11 @@ int nsd_strided_dwconv_bwd(const float* dy, const float* x, const float* w, floa
     NSD_CHECK_ARG(dy && x && w && dx && dw && B >= 1 && N > 0 && K >= 1 && S >= 1 && T >= K, "strided_dwconv_bwd: bad argument");
     if (!workspace || workspace_bytes < nsd_strided_dwconv_bwd_workspace(B, N, K)) { set_error("strided_dwconv_bwd: workspace too small"); return NSD_ERR_WORKSPACE; }
     const int Tp = (T - K) / S + 1, parts = dw_parts(B), per = cdiv(B, parts);
-    strided_dwconv_bwd_x_kernel<<<dim3(cdiv(N, 128), T, B), 128, 0, (cudaStream_t)stream>>>(dy, w, dx, T, N, K, S, Tp);
+    nsd::launch_k(strided_dwconv_bwd_x_kernel, dim3(cdiv(N, 128), T, B), 128, 0, (cudaStream_t)stream, dy, w, dx, T, N, K, S, Tp);
     NSD_LAUNCH_CHECK();
-    strided_dwconv_bwd_w_kernel<<<dim3(cdiv(N, 32), cdiv(B, per)), 256, 0, (cudaStream_t)stream>>>(dy, x, (float*)workspace, B, T, N, K, S, Tp, per);
+    nsd::launch_k(strided_dwconv_bwd_w_kernel, dim3(cdiv(N, 32), cdiv(B, per)), 256, 0, (cudaStream_t)stream, dy, x, (float*)workspace, B, T, N, K, S, Tp, per);
     NSD_LAUNCH_CHECK();
-    dwconv_w_reduce_kernel<<<cdiv(N * (K + 1), 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, cdiv(B, per), N, K, dw, nullptr);
+    nsd::launch_k(dwconv_w_reduce_kernel, cdiv(N * (K + 1), 256), 256, 0, (cudaStream_t)stream, (const float*)workspace, cdiv(B, per), N, K, dw, nullptr);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -612,9 +634,9 @@ int nsd_cast_colsum(const float* src, int M, int N, void* dst_bf16, int ld_dst, 
     NSD_CHECK_ARG(src && dst_bf16 && colsum && M >= 1 && N >= 4 && N % 4 == 0 && ld_dst >= N && ld_dst % 4 == 0, "cast_colsum: bad argument (N %% 4 == 0)");
     if (!workspace || workspace_bytes < nsd_cast_colsum_workspace(M, N)) { set_error("cast_colsum: workspace too small"); return NSD_ERR_WORKSPACE; }
     const int chunks = cdiv(M, CC_CHUNK_ROWS);
-    cast_colsum_kernel<<<dim3(cdiv(N, 128), chunks), 256, 0, (cudaStream_t)stream>>>(src, M, N, (__nv_bfloat16*)dst_bf16, ld_dst, (float*)workspace);
+    nsd::launch_k(cast_colsum_kernel, dim3(cdiv(N, 128), chunks), 256, 0, (cudaStream_t)stream, src, M, N, (__nv_bfloat16*)dst_bf16, ld_dst, (float*)workspace);
     NSD_LAUNCH_CHECK();
-    colsum_chunks_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, N, chunks, colsum);
+    nsd::launch_k(colsum_chunks_kernel, cdiv(N, 256), 256, 0, (cudaStream_t)stream, (const float*)workspace, N, chunks, colsum);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -624,34 +646,34 @@ int nsd_posenc_mask(const float* z, const float* pe, const int* bands8, const in
     Bands bd;
     for (int i = 0; i < 8; ++i) bd.v[i] = bands8 ? bands8[i] : 0;
     const size_t n4 = (size_t)B * T * D / 4;
-    posenc_mask_kernel<<<ew_blocks(n4), 256, 0, (cudaStream_t)stream>>>(z, pe, bd, bands8_dev, out, T, D, n4);
+    nsd::launch_k(posenc_mask_kernel, ew_blocks(n4), 256, 0, (cudaStream_t)stream, z, pe, bd, bands8_dev, out, T, D, n4);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_index_reduce(const float* partial, const int64_t* index, int B, size_t n, int n_out, float* out, void* stream) {
     NSD_CHECK_ARG(partial && index && out && B >= 0 && n_out >= 1, "index_reduce: bad argument");
     if (n == 0) return NSD_OK;
-    index_reduce_kernel<<<dim3((unsigned)cdivz(n, 256), n_out), 256, 0, (cudaStream_t)stream>>>(partial, index, B, n, n_out, out);
+    nsd::launch_k(index_reduce_kernel, dim3((unsigned)cdivz(n, 256), n_out), 256, 0, (cudaStream_t)stream, partial, index, B, n, n_out, out);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_axpb(const float* x, float a, float b, float* y, size_t n, void* stream) {
     NSD_CHECK_ARG(x && y, "axpb: null pointer");
     if (n == 0) return NSD_OK;
-    axpb_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, a, b, y, n);
+    nsd::launch_k(axpb_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, x, a, b, y, n);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_sum_f32(const float* x, size_t n, float scale, float add, int accumulate, float* out, void* stream) {
     NSD_CHECK_ARG(x && out, "sum_f32: null pointer");
-    sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, scale, add, accumulate, out);
+    nsd::launch_k(sum_kernel, 1, 1024, 0, (cudaStream_t)stream, x, n, scale, add, accumulate, out);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
 int nsd_log_softmax_bwd(const float* lp, const float* dlp, float* dlogits, int64_t rows, int C, void* stream) {
     NSD_CHECK_ARG(lp && dlp && dlogits && rows >= 0 && C > 0, "log_softmax_bwd: bad argument");
     if (rows == 0) return NSD_OK;
-    log_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(lp, dlp, dlogits, rows, C);
+    nsd::launch_k(log_softmax_bwd_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, lp, dlp, dlogits, rows, C);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

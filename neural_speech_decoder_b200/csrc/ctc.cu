@@ -36,6 +36,7 @@ struct CtcParams {
 };
 
 __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(CtcParams p) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = p.T, C = p.C, SP = p.SP;
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(CtcParams p) {
 __global__ void greedy_decode_kernel(const float* __restrict__ act, int64_t st, int64_t sb, int64_t sc,
                                      const int32_t* __restrict__ lens, int T, int B, int C, int blank,
                                      int64_t* __restrict__ out, int32_t* __restrict__ out_len) {
+    pdl_enter();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -259,6 +261,7 @@ __global__ void greedy_decode_kernel(const float* __restrict__ act, int64_t st, 
 
 // Row-wise log-softmax, one warp per row (trainer:210, 301).  Same arithmetic as phase 0 of ctc_kernel.
 __global__ void log_softmax_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C) {
+    pdl_enter();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -277,6 +280,7 @@ __global__ void log_softmax_kernel(const float* __restrict__ in, float* __restri
 __global__ void edit_distance_kernel(const int64_t* __restrict__ dec, int dec_stride, const int32_t* __restrict__ dec_len,
                                      const int32_t* __restrict__ tgt, int tgt_stride, const int32_t* __restrict__ tgt_len,
                                      int B, int W, int32_t* __restrict__ ws, int32_t* __restrict__ dist) {
+    pdl_enter();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -336,7 +340,7 @@ int nsd_ctc_loss(const float* act, int64_t st, int64_t sb, int64_t sc, int is_lo
     const size_t smem = sizeof(int) * 3 * p.SP + sizeof(float) * (4 * (size_t)(p.SP + 2) + CTC_WARPS * (size_t)p.SP + CTC_WARPS * (size_t)C);
     NSD_CHECK_ARG(smem <= 200 * 1024, "ctc_loss: max_tgt=%d C=%d need %zu B shared memory", max_tgt, C, smem);
     if (smem > 48 * 1024) NSD_CUDA(cudaFuncSetAttribute(ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_kernel<<<B, CTC_THREADS, smem, s>>>(p);
+    nsd::launch_k(ctc_kernel, B, CTC_THREADS, smem, s, p);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -345,7 +349,7 @@ int nsd_greedy_decode(const float* act, int64_t st, int64_t sb, int64_t sc, cons
                       int blank, int64_t* out, int32_t* out_len, void* stream) {
     using namespace nsd;
     NSD_CHECK_ARG(T > 0 && B > 0 && C > 0, "greedy_decode: bad sizes");
-    greedy_decode_kernel<<<cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(act, st, sb, sc, lens, T, B, C, blank, out, out_len);
+    nsd::launch_k(greedy_decode_kernel, cdiv(B, 4), 128, 0, (cudaStream_t)stream, act, st, sb, sc, lens, T, B, C, blank, out, out_len);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -354,7 +358,7 @@ int nsd_log_softmax_f32(const float* in, float* out, int64_t rows, int C, void* 
     using namespace nsd;
     NSD_CHECK_ARG(rows >= 0 && C > 0, "log_softmax: bad sizes");
     if (rows == 0) return NSD_OK;
-    log_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(in, out, rows, C);
+    nsd::launch_k(log_softmax_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, in, out, rows, C);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -367,7 +371,7 @@ int nsd_edit_distance(const int64_t* dec, int dec_stride, const int32_t* dec_len
     NSD_CHECK_ARG(B > 0, "edit_distance: bad batch");
     const size_t W = workspace_bytes / (sizeof(int32_t) * 3 * (size_t)B);
     NSD_CHECK_ARG(W >= 1, "edit_distance: workspace too small");
-    edit_distance_kernel<<<cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(dec, dec_stride, dec_len, tgt, tgt_stride, tgt_len, B, (int)W, (int32_t*)workspace, dist);
+    nsd::launch_k(edit_distance_kernel, cdiv(B, 4), 128, 0, (cudaStream_t)stream, dec, dec_stride, dec_len, tgt, tgt_stride, tgt_len, B, (int)W, (int32_t*)workspace, dist);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

@@ -7,6 +7,7 @@ namespace nsd {
 
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, size_t n, float p, float inv_keep, uint64_t seed) {
+    pdl_enter();
     // one Philox call covers 4 consecutive elements; the mask depends only on (seed, element index)
     const size_t nq = (n + 3) / 4;
     const uint32_t thresh = dropout_threshold(p);
@@ -49,6 +50,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tab, float b1, float b2, float wd, float gs,
                                                    float step_size, float inv_sqrt_bc2, float eps, float decay_mul,
                                                    const float* __restrict__ grad_sqnorm, float max_norm, const float* __restrict__ hyper) {
+    pdl_enter();
     if (hyper != nullptr) { step_size = hyper[0]; inv_sqrt_bc2 = hyper[1]; decay_mul = hyper[2]; }   // device-resident schedule (graph replay)
     if (grad_sqnorm != nullptr) {            // clip_grad_norm_(max_norm): coefficient from the device-resident squared norm, no host sync
         const float norm = sqrtf(*grad_sqnorm) * gs;
@@ -100,6 +102,7 @@ struct CopyTable {
     int count;
 };
 __global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ CopyTable tab) {
+    pdl_enter();
     const int ti = blockIdx.y;
     const float* __restrict__ S = tab.src[ti];
     float* __restrict__ D = tab.dst[ti];
@@ -124,7 +127,7 @@ int nsd_multi_copy_f32(int n_tensors, const void* const* src, void* const* dst, 
         }
         if (nmax == 0) continue;
         const dim3 grid((unsigned)std::min<long long>((nmax + 255) / 256, 64), (unsigned)tab.count);
-        multi_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tab);
+        nsd::launch_k(multi_copy_kernel, grid, 256, 0, (cudaStream_t)stream, tab);
         NSD_LAUNCH_CHECK();
     }
     return NSD_OK;
@@ -152,7 +155,7 @@ static int adam_impl(int n_tensors, void* const* params, const void* const* grad
         }
         tab.chunk_start[tab.count] = chunks;
         if (chunks == 0) continue;
-        adam_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(tab, beta1, beta2, wd_l2, grad_scale, step_size, inv_sqrt_bc2, eps, decay_mul, grad_sqnorm,
+        nsd::launch_k(adam_kernel, chunks, 256, 0, (cudaStream_t)stream, tab, beta1, beta2, wd_l2, grad_scale, step_size, inv_sqrt_bc2, eps, decay_mul, grad_sqnorm,
                                                                max_norm, hyper);
         NSD_LAUNCH_CHECK();
     }
@@ -180,8 +183,8 @@ int nsd_dropout(const void* x, void* out, int dtype, size_t n, float p, uint64_t
     const int blocks = (int)std::min<size_t>(cdivz(cdivz(n, 4), 256), (size_t)sm_count() * 16);
     const float inv_keep = 1.0f / (1.0f - p);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == NSD_F32) dropout_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, (float*)out, n, p, inv_keep, seed);
-    else if (dtype == NSD_BF16) dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n, p, inv_keep, seed);
+    if (dtype == NSD_F32) nsd::launch_k(dropout_kernel<float>, blocks, 256, 0, s, (const float*)x, (float*)out, n, p, inv_keep, seed);
+    else if (dtype == NSD_BF16) nsd::launch_k(dropout_kernel<__nv_bfloat16>, blocks, 256, 0, s, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, n, p, inv_keep, seed);
     else { set_error("dropout: bad dtype"); return NSD_ERR_INVALID; }
     NSD_LAUNCH_CHECK();
     return NSD_OK;

@@ -50,6 +50,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 // to hide the shared-memory and HBM latency of the four phases of a block.
 template <typename OutT, int NTW, int NWARPS>
 __global__ void __launch_bounds__(32 * NWARPS, 1) frontend_fwd_kernel(FrontendFwdParams p) {
+    pdl_enter();
     constexpr int FE_THREADS = 32 * NWARPS;
     extern __shared__ __align__(16) float smem[];
     const int N = p.N, K = p.K, S = p.S, T = p.T, ntaps = p.ntaps;
@@ -326,6 +327,7 @@ __device__ __forceinline__ float4 ff_noise(float4 v, const FrontendFwdParams& p,
 
 template <int K8N>      // 16-byte chunks per channel of a patch row = kernelLen / 8
 __global__ void __launch_bounds__(FF_THREADS, 1) frontend_fwd_fast_kernel(FrontendFwdParams p) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     constexpr int N = FF_N, K = 8 * K8N;
     const int S = p.S, T = p.T;
@@ -527,6 +529,7 @@ struct FrontendBwdParams {
 
 template <typename InT>
 __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_kernel(FrontendBwdParams p) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     const int N = p.N, K = p.K, S = p.S, T = p.T, KP = p.KP, B = p.B;
     const int b = blockIdx.x;
@@ -637,6 +640,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_kernel(FrontendBwd
 // [16*MT*w, 16*MT*(w+1)) of dW, all FB_CN = 128 columns of the CTA's column block.
 template <int MT>
 __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_tc_kernel(FrontendBwdParams p) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     constexpr int N = 128 * MT, NYS = N + 8, NDP = FB_CN + 8;
     const int K = p.K, S = p.S, T = p.T, KP = p.KP, B = p.B;
@@ -785,6 +789,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) frontend_bwd_tc_kernel(Frontend
 // tile buffers double-buffered so the mma of one group runs under the staging of the next.
 constexpr int FB2_THREADS = 512;
 __global__ void __launch_bounds__(FB2_THREADS, 1) frontend_bwd_tc2_kernel(FrontendBwdParams p) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     constexpr int N = 256, K = 32, S = 4, NYS = N + 8, NDP = FB_CN + 8, KP = 36, G = 4;
     const int T = p.T, B = p.B, Tp = p.Tp;
@@ -902,6 +907,7 @@ __global__ void __launch_bounds__(FB2_THREADS, 1) frontend_bwd_tc2_kernel(Fronte
 __global__ void day_segment_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb,
                                           const int64_t* __restrict__ day_idx, int B, int NN, int N, int n_days,
                                           float* __restrict__ dw, float* __restrict__ db) {
+    pdl_enter();
     const int d = blockIdx.y;
     const int per = NN + N;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
@@ -917,6 +923,7 @@ __global__ void day_segment_reduce_kernel(const float* __restrict__ pw, const fl
 // stand-alone form of the augmentation (same values as the fused path): out = x + white + offset
 __global__ void input_noise_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int T, int N, float white_sd, float offset_sd,
                                    unsigned long long seed, const unsigned long long* __restrict__ seed_off) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     const size_t total = (size_t)B * T * N;
     if ((N & 3) == 0) {
@@ -979,7 +986,7 @@ int nsd_frontend_fwd(const float* x, const int64_t* day_idx, const float* day_w,
     cudaStream_t s = (cudaStream_t)stream;
     auto go = [&](auto kern, int threads) -> int {
         NSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, s>>>(p);
+        nsd::launch_k(kern, grid, threads, smem, s, p);
         return NSD_OK;
     };
     int rc;
@@ -1008,7 +1015,7 @@ int nsd_input_noise(const float* x, float* out, int B, int T, int N, float white
     if (total == 0) return NSD_OK;
     NSD_CHECK_ARG((N & 3) != 0 || ((((uintptr_t)x | (uintptr_t)out) & 15) == 0), "input_noise: x/out must be 16-byte aligned");
     const int blocks = (int)std::min<size_t>(cdivz(cdivz(total, 4), 256), (size_t)sm_count() * 16);
-    input_noise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, B, T, N, white_noise_sd, constant_offset_sd, seed, seed_offset_ptr());
+    nsd::launch_k(input_noise_kernel, blocks, 256, 0, (cudaStream_t)stream, x, out, B, T, N, white_noise_sd, constant_offset_sd, seed, seed_offset_ptr());
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -1042,7 +1049,7 @@ int nsd_frontend_bwd(const void* dpatches, int dpatches_dtype, const float* ys, 
         const size_t smem = sizeof(float) * (size_t)4 * FB_CN * 36 + sizeof(__nv_bfloat16) * (2 * 16 * (size_t)(N + 8) + 2 * 16 * (size_t)(FB_CN + 8));
         dim3 grid(B, N / FB_CN);
         NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        frontend_bwd_tc2_kernel<<<grid, FB2_THREADS, smem, s>>>(p);
+        nsd::launch_k(frontend_bwd_tc2_kernel, grid, FB2_THREADS, smem, s, p);
     } else if (mt) {
         // bf16 model path: per-utterance ys^T dpre on tensor cores
         size_t smem = sizeof(float) * ((((size_t)p.ring * (FB_CN + 1) + 3) & ~(size_t)3) + (size_t)FB_G * FB_CN * p.KP + FB_CN) +
@@ -1051,10 +1058,10 @@ int nsd_frontend_bwd(const void* dpatches, int dpatches_dtype, const float* ys, 
         dim3 grid(B, N / FB_CN);
         if (mt == 2) {
             NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            frontend_bwd_tc_kernel<2><<<grid, FB_THREADS, smem, s>>>(p);
+            nsd::launch_k(frontend_bwd_tc_kernel<2>, grid, FB_THREADS, smem, s, p);
         } else {
             NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            frontend_bwd_tc_kernel<1><<<grid, FB_THREADS, smem, s>>>(p);
+            nsd::launch_k(frontend_bwd_tc_kernel<1>, grid, FB_THREADS, smem, s, p);
         }
     } else {
     size_t smem = sizeof(float) * ((size_t)p.ring * (FB_CN + 1) + (size_t)FB_RCH * N + (size_t)FB_G * FB_CN * p.KP);
@@ -1062,16 +1069,16 @@ int nsd_frontend_bwd(const void* dpatches, int dpatches_dtype, const float* ys, 
     dim3 grid(B, cdiv(N, FB_CN));
     if (dpatches_dtype == NSD_F32) {
         NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        frontend_bwd_kernel<float><<<grid, FB_THREADS, smem, s>>>(p);
+        nsd::launch_k(frontend_bwd_kernel<float>, grid, FB_THREADS, smem, s, p);
     } else {
         NSD_CUDA(cudaFuncSetAttribute(frontend_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        frontend_bwd_kernel<__nv_bfloat16><<<grid, FB_THREADS, smem, s>>>(p);
+        nsd::launch_k(frontend_bwd_kernel<__nv_bfloat16>, grid, FB_THREADS, smem, s, p);
     }
     }
     NSD_LAUNCH_CHECK();
     const int per = N * N + N;
     dim3 g2(min(cdiv(per, 256), 64), n_days);
-    day_segment_reduce_kernel<<<g2, 256, 0, s>>>(p.partial_w, p.partial_b, day_idx, B, N * N, N, n_days, d_day_w, d_day_b);
+    nsd::launch_k(day_segment_reduce_kernel, g2, 256, 0, s, p.partial_w, p.partial_b, day_idx, B, N * N, N, n_days, d_day_w, d_day_b);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

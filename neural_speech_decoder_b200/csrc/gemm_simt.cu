@@ -62,6 +62,7 @@ template <bool A_KCONTIG, bool B_KCONTIG>
 __global__ void __launch_bounds__(GS_THREADS, 2)
 sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
              float* __restrict__ C, int ldc, const float* __restrict__ bias, float beta) {
+    pdl_enter();
     __shared__ __align__(16) float As[2][GS_BK * (GS_BM + 4)];
     __shared__ __align__(16) float Bs[2][GS_BK * (GS_BN + 4)];
     const int tid = threadIdx.x;
@@ -136,6 +137,7 @@ constexpr int CS_CHUNKS = 64;
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, int M, int N, int lda, int rows_per_chunk,
                                                              float* __restrict__ partial) {
+    pdl_enter();
     __shared__ float red[4][64 * VEC + 1];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int n = (blockIdx.x * 64 + tx) * VEC;
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
     }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int N, int chunks, float* __restrict__ out) {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float s = 0.f;
@@ -176,6 +179,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int N, in
 
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n) {
+    pdl_enter();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) dst[i] = from_f32<D>(to_f32<S>(src[i]));
@@ -189,6 +193,7 @@ template <typename S, bool VEC2>
 __global__ void __launch_bounds__(256) cast_transpose_kernel(const S* __restrict__ src, int R, int Cn, int ld_src,
                                                              __nv_bfloat16* __restrict__ dst, int ld_dst,
                                                              __nv_bfloat16* __restrict__ dstT, int ld_dstT) {
+    pdl_enter();
     __shared__ float tile[64][65];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
@@ -239,6 +244,7 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const S* __restrict
 }
 
 __global__ void swap01_kernel(const float* __restrict__ in, float* __restrict__ out, int D0, int D1, int C) {
+    pdl_enter();
     // out[d1][d0][c] = in[d0][d1][c]
     const size_t total = (size_t)D0 * D1 * C;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -262,10 +268,10 @@ int nsd_gemm_f32(int transa, int transb, int M, int N, int K, const float* A, in
     dim3 grid(cdiv(N, GS_BN), cdiv(M, GS_BM));
     cudaStream_t s = (cudaStream_t)stream;
     // op(A) is k-contiguous when A is stored [M,K]; op(B) is k-contiguous when B is stored [N,K]
-    if (!transa && transb) sgemm_kernel<true, true><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
-    else if (!transa && !transb) sgemm_kernel<true, false><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
-    else if (transa && !transb) sgemm_kernel<false, false><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
-    else sgemm_kernel<false, true><<<grid, GS_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    if (!transa && transb) nsd::launch_k(sgemm_kernel<true, true>, grid, GS_THREADS, 0, s, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    else if (!transa && !transb) nsd::launch_k(sgemm_kernel<true, false>, grid, GS_THREADS, 0, s, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    else if (transa && !transb) nsd::launch_k(sgemm_kernel<false, false>, grid, GS_THREADS, 0, s, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+    else nsd::launch_k(sgemm_kernel<false, true>, grid, GS_THREADS, 0, s, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -283,13 +289,13 @@ int nsd_colsum(const void* a, int a_dtype, int M, int N, int lda, float* out, vo
     const int chunks = std::max(1, cdiv(M, rows_per_chunk));
     if (a_dtype == NSD_BF16) {
         const bool vec = ((lda & 1) == 0) && (((uintptr_t)a & 3) == 0);
-        if (vec) colsum_partial_kernel<__nv_bfloat16, 2><<<dim3(cdiv(N, 128), chunks), 256, 0, s>>>((const __nv_bfloat16*)a, M, N, lda, rows_per_chunk, partial);
-        else colsum_partial_kernel<__nv_bfloat16, 1><<<dim3(cdiv(N, 64), chunks), 256, 0, s>>>((const __nv_bfloat16*)a, M, N, lda, rows_per_chunk, partial);
+        if (vec) nsd::launch_k(colsum_partial_kernel<__nv_bfloat16, 2>, dim3(cdiv(N, 128), chunks), 256, 0, s, (const __nv_bfloat16*)a, M, N, lda, rows_per_chunk, partial);
+        else nsd::launch_k(colsum_partial_kernel<__nv_bfloat16, 1>, dim3(cdiv(N, 64), chunks), 256, 0, s, (const __nv_bfloat16*)a, M, N, lda, rows_per_chunk, partial);
     } else if (a_dtype == NSD_F32) {
-        colsum_partial_kernel<float, 1><<<dim3(cdiv(N, 64), chunks), 256, 0, s>>>((const float*)a, M, N, lda, rows_per_chunk, partial);
+        nsd::launch_k(colsum_partial_kernel<float, 1>, dim3(cdiv(N, 64), chunks), 256, 0, s, (const float*)a, M, N, lda, rows_per_chunk, partial);
     } else { set_error("colsum: bad dtype"); return NSD_ERR_INVALID; }
     NSD_LAUNCH_CHECK();
-    colsum_final_kernel<<<cdiv(N, 256), 256, 0, s>>>(partial, N, chunks, out);
+    nsd::launch_k(colsum_final_kernel, cdiv(N, 256), 256, 0, s, partial, N, chunks, out);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -299,9 +305,9 @@ int nsd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n,
     if (n == 0) return NSD_OK;
     cudaStream_t s = (cudaStream_t)stream;
     int blocks = (int)std::min<size_t>(cdivz(n, 256), (size_t)sm_count() * 16);
-    if (src_dtype == NSD_F32 && dst_dtype == NSD_BF16) cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
-    else if (src_dtype == NSD_BF16 && dst_dtype == NSD_F32) cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
-    else if (src_dtype == NSD_F32 && dst_dtype == NSD_F32) cast_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, n);
+    if (src_dtype == NSD_F32 && dst_dtype == NSD_BF16) nsd::launch_k(cast_kernel<float, __nv_bfloat16>, blocks, 256, 0, s, (const float*)src, (__nv_bfloat16*)dst, n);
+    else if (src_dtype == NSD_BF16 && dst_dtype == NSD_F32) nsd::launch_k(cast_kernel<__nv_bfloat16, float>, blocks, 256, 0, s, (const __nv_bfloat16*)src, (float*)dst, n);
+    else if (src_dtype == NSD_F32 && dst_dtype == NSD_F32) nsd::launch_k(cast_kernel<float, float>, blocks, 256, 0, s, (const float*)src, (float*)dst, n);
     else { set_error("cast: unsupported dtype pair %d->%d", src_dtype, dst_dtype); return NSD_ERR_INVALID; }
     NSD_LAUNCH_CHECK();
     return NSD_OK;
@@ -319,11 +325,11 @@ int nsd_cast_transpose(const void* src, int src_dtype, int R, int Cn, int ld_src
                      (!dst || ((ld_dst % 2 == 0) && (((uintptr_t)dst & 3) == 0))) && (!dstT || ((ld_dstT % 2 == 0) && (((uintptr_t)dstT & 3) == 0)));
     __nv_bfloat16* d0 = (__nv_bfloat16*)dst; __nv_bfloat16* d1 = (__nv_bfloat16*)dstT;
     if (src_dtype == NSD_F32) {
-        if (vec) cast_transpose_kernel<float, true><<<grid, 256, 0, s>>>((const float*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
-        else cast_transpose_kernel<float, false><<<grid, 256, 0, s>>>((const float*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+        if (vec) nsd::launch_k(cast_transpose_kernel<float, true>, grid, 256, 0, s, (const float*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+        else nsd::launch_k(cast_transpose_kernel<float, false>, grid, 256, 0, s, (const float*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
     } else if (src_dtype == NSD_BF16) {
-        if (vec) cast_transpose_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
-        else cast_transpose_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+        if (vec) nsd::launch_k(cast_transpose_kernel<__nv_bfloat16, true>, grid, 256, 0, s, (const __nv_bfloat16*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
+        else nsd::launch_k(cast_transpose_kernel<__nv_bfloat16, false>, grid, 256, 0, s, (const __nv_bfloat16*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
     } else { set_error("cast_transpose: bad dtype"); return NSD_ERR_INVALID; }
     NSD_LAUNCH_CHECK();
     return NSD_OK;
@@ -334,7 +340,7 @@ int nsd_swap01_f32(const float* in, float* out, int D0, int D1, int C, void* str
     const size_t total = (size_t)D0 * D1 * C;
     if (total == 0) return NSD_OK;
     int blocks = (int)std::min<size_t>(cdivz(total, 256), (size_t)sm_count() * 8);
-    swap01_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, D0, D1, C);
+    nsd::launch_k(swap01_kernel, blocks, 256, 0, (cudaStream_t)stream, in, out, D0, D1, C);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }

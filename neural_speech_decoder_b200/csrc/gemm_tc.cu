@@ -140,6 +140,7 @@ template <int BN, typename OutT, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C, int ldc,
                const float* __restrict__ bias, float beta, int M, int N, int K) {
+    pdl_launch_dependents();
     using cfg = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -172,6 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                             // everything above ran under the previous kernel's tail; operands and C are touched below
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, OutT* __restrict__ C, OutT* __restrict__ C2,
                 int ldc, const float* __restrict__ bias, float beta, int M, int N, int K, int nprob) {
+    pdl_launch_dependents();
     using cfg = Cfg2<BN2>;
     constexpr int BN = cfg::BN;
     extern __shared__ uint8_t smem_raw[];
@@ -379,6 +382,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                             // everything above ran under the previous kernel's tail; operands and C are touched below
 
     if (warp == 0) {
         // ===================== TMA producer: my 128 rows of A, my half of B =====================
@@ -535,7 +539,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int ldc
     }
     const int tiles = cdiv(M, BM) * cdiv(N, BN);
     const int grid = std::min(tiles, gemm_sms());
-    kern<<<grid, THREADS, cfg::SMEM, s>>>(ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K);
+    nsd::launch_k(kern, grid, THREADS, cfg::SMEM, s, ta, tb, reinterpret_cast<OutT*>(C), ldc, bias, beta, M, N, K);
     NSD_LAUNCH_CHECK();
     return NSD_OK;
 }
@@ -554,10 +558,12 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     const int grid = std::min(items, gemm_sms() / 2) * 2;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    lc.attrs = attr; lc.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = pdl_enabled() ? 2 : 1;
     NSD_CUDA(cudaLaunchKernelEx(&lc, kern, ta, tb, ta2, tb2, reinterpret_cast<OutT*>(C), reinterpret_cast<OutT*>(C2), ldc, bias, beta, M, N, K, nprob));
     count_launch(1);
     return NSD_OK;

@@ -28,12 +28,39 @@ def make_optimizer(model: torch.nn.Module, args: dict):
     return opt, sched
 
 
+class LossReader:
+    """Host read-back of a step's loss that does not drain the backward behind it.  ``loss.item()`` on the compute stream waits for the
+    whole step (the stream is in order) and the GPU then idles until the host has enqueued the next step's first kernels; the loss itself
+    is final after the forward + CTC kernel, ~40 % into the step.  ``train_step(..., loss_reader=r)`` copies it to a pinned float on a side
+    stream as soon as it exists; ``r.item()`` waits for that copy only, so the host enqueues step i+1 while step i's backward still runs."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.buf = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.stream = torch.cuda.Stream(self.device)
+        self.done = torch.cuda.Event()
+        self._ready = torch.cuda.Event()
+
+    def capture(self, loss: torch.Tensor) -> None:
+        self._ready.record(torch.cuda.current_stream(self.device))
+        self.stream.wait_event(self._ready)
+        with torch.cuda.stream(self.stream):
+            self.buf.copy_(loss.detach().reshape(1), non_blocking=True)
+            self.done.record(self.stream)
+        loss.record_stream(self.stream)
+
+    def item(self) -> float:
+        self.done.synchronize()
+        return float(self.buf[0])
+
+
 def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, grad_sync=None,
-               white_noise_sd: float = 0.0, constant_offset_sd: float = 0.0) -> torch.Tensor:
+               white_noise_sd: float = 0.0, constant_offset_sd: float = 0.0, loss_reader: Optional[LossReader] = None) -> torch.Tensor:
     """One optimisation step; returns the (device) loss scalar.  ``grad_sync`` is the data-parallel hook
     (parallel.GradSync): it all-reduces gradients bucket by bucket while the backward is still running.
     ``white_noise_sd`` / ``constant_offset_sd`` (args["whiteNoiseSD"], args["constantOffsetSD"]): the in-loop
-    augmentation of trainer:194-201, generated inside the front-end kernel instead of in extra passes over X."""
+    augmentation of trainer:194-201, generated inside the front-end kernel instead of in extra passes over X.
+    ``loss_reader`` (LossReader): host read-back of the loss that does not wait for the backward."""
     model.grad_sync = grad_sync
     # the buckets are all-reduced with SUM: the 1/world average is folded into the Adam kernel.  Adam with eps=0.1 and
     # L2-in-gradient is NOT scale-invariant, so the scale must follow the sync object on every step.
@@ -47,6 +74,8 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
     pred = model.forward(X, dayIdx)                                         # trainer:208
     lens = _ctc.out_lens(X_len, model.kernelLen, model.strideLen)           # trainer:209
     loss = _ctc.ctc_loss_from_logits(pred, y, lens, y_len, blank=0, reduction="mean")   # trainer:210-218, 242
+    if loss_reader is not None:
+        loss_reader.capture(loss)
     optimizer.zero_grad(set_to_none=True)                                   # trainer:251
     if grad_sync is not None:
         grad_sync.begin()

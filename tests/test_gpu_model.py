@@ -152,6 +152,11 @@ def test_train_step_reduces_loss_and_eval_batch():
     opt, sched = nsd.make_optimizer(m, dict(lrStart=0.02, lrEnd=0.02, nBatch=100, l2_decay=1e-5))
     losses = [nsd.train_step(m, opt, *batch, scheduler=sched).item() for _ in range(8)]
     assert losses[-1] < losses[0]
+    # LossReader: the loss read on a side stream right after the forward equals the returned device scalar, step after step
+    reader = nsd.LossReader(DEV)
+    for _ in range(3):
+        dev_loss = nsd.train_step(m, opt, *batch, scheduler=sched, loss_reader=reader)
+        assert reader.item() == dev_loss.item()
     m.eval()
     loss, dist, tot = nsd.eval_batch(m, *batch)
     assert tot == int(g["y_len"].sum()) and 0 <= dist <= tot + int(g["out_lens"].sum())
