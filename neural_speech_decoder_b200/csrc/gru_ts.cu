@@ -108,6 +108,16 @@ __device__ __forceinline__ void pub_sync(int w, uint32_t n) { asm volatile("bar.
 // With two chains per warpgroup (64-row chains) the wait would hold up the other chain: measured slower in the forward (12.0 -> 13.1 us), so not used there.
 __device__ __forceinline__ void done_arrive(int w, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(7 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
 __device__ __forceinline__ void done_sync(int w, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(7 + 2 * w + (int)(n & 1u)), "n"(PUB_THREADS) : "memory"); }
+// Chains in flight.  <WPC, NCH>: WPC warpgroups finalise one chain (32 * WPC rows), NCH chains of a chain group are in flight per CTA.
+//   <1, 2>  B <= 64: warpgroup w owns chain w.            <2, 2>: 64-row chains, both warpgroups work on both chains.
+//   <1, 4>  B > 64: four 32-row chains, warpgroup w owns chains w and w + 2 -- the short per-chain critical path of <1, 2> with twice the
+//           rows in flight: the tensor memory (4 accumulators beside the stationary weights) is exactly full.
+template <int WPC, int NCH> struct Chains {
+    static constexpr int CPW = WPC == 2 ? 2 : NCH / 2;                      // chains a warpgroup works on per step
+    static constexpr int NSLOT = WPC == 2 ? 4 : NCH;                        // message slots: one per (warpgroup, chain it works on)
+    __device__ static __forceinline__ int ch(int w, int k) { return WPC == 2 ? k : w + 2 * k; }       // chain within the group
+    __device__ static __forceinline__ int slot(int w, int k) { return WPC == 2 ? 2 * w + k : w + 2 * k; }
+};
 __device__ __forceinline__ void wg_bar_sync(int w) { asm volatile("bar.sync %0, %1;" ::"r"(1 + w), "n"(WG_THREADS) : "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]: A = stationary weights, lane = row, two bf16 of consecutive k per 32-bit column
@@ -173,13 +183,13 @@ __device__ __forceinline__ int rot_bf16(int u) { return (((u >> 1) & 3) ^ ((u >>
 struct Smem {
     uint8_t* ring; uint8_t* inbox; uint8_t* outbox; float* self;
     uint64_t* full; uint64_t* empty;                               // [MAX_STAGES] each
-    uint64_t* tmem_full;                                           // [2] one per chain in flight
+    uint64_t* tmem_full;                                           // [4] one per chain in flight
     uint64_t* inbox_bar;                                           // [4] one per message slot
     uint32_t* tmem_slot;
     long long* trace;
     float* bsum;                                                   // BPTT: [2 warpgroups][32 values][128 threads] bias-gradient partial sums
 };
-constexpr int BAR_WORDS = 2 * MAX_STAGES + 2 + 4 + 2;             // uint64 slots in the barrier block
+constexpr int BAR_WORDS = 2 * MAX_STAGES + 4 + 4 + 2;             // uint64 slots in the barrier block
 __device__ __forceinline__ Smem carve(uint8_t* raw, int ring_bytes, int nslot, int msgs_bytes, int self_bytes) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     Smem s;
@@ -188,8 +198,8 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int ring_bytes, int nslot, i
     s.outbox = s.inbox + nslot * msgs_bytes;
     s.self = reinterpret_cast<float*>(s.outbox + nslot * msgs_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s.self) + 2 * self_bytes);
-    s.full = bars; s.empty = bars + MAX_STAGES; s.tmem_full = bars + 2 * MAX_STAGES; s.inbox_bar = bars + 2 * MAX_STAGES + 2;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+    s.full = bars; s.empty = bars + MAX_STAGES; s.tmem_full = bars + 2 * MAX_STAGES; s.inbox_bar = bars + 2 * MAX_STAGES + 4;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 8);
     s.trace = reinterpret_cast<long long*>(bars + BAR_WORDS);
     s.bsum = reinterpret_cast<float*>(s.trace + (TRACE_STEPS + 1) * 8);
     return s;
@@ -201,7 +211,7 @@ static size_t smem_bytes(int ring_bytes, int nslot, int msgs_bytes, int self_byt
 __device__ __forceinline__ uint32_t setup(const Smem& sm, int warp, int lane) {
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) mbar_init(&sm.tmem_full[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&sm.tmem_full[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&sm.inbox_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -257,14 +267,15 @@ __device__ __forceinline__ void load_a_row(uint32_t taddr_row, const __nv_bfloat
 //     chain's epilogue.
 // Control warps 2 and 3: publisher of warpgroup w = warp - 2.  Walks the (chain pair, step, chain) items in the order the
 // warpgroup finalises them.
-template <int WPC>
+template <int WPC, int NCH>
 __device__ __forceinline__ void publisher_warp(const Smem& sm, const Common& c, int d, int my_zone, int w, int lane) {
-    const int npair = (c.nchain + 1) / 2;
+    using CH = Chains<WPC, NCH>;
+    const int npair = (c.nchain + NCH - 1) / NCH;
     uint32_t n = 0;
     for (int pr = 0; pr < npair; ++pr)
         for (int s = 0; s < c.Tp; ++s)
-            for (int k = 0; k < WPC; ++k) {
-                const int chain = 2 * pr + (WPC == 1 ? w : k);
+            for (int k = 0; k < CH::CPW; ++k) {
+                const int chain = NCH * pr + CH::ch(w, k);
                 if (chain >= c.nchain) continue;
                 pub_sync(w, n);
                 if (lane == 0) {
@@ -272,23 +283,24 @@ __device__ __forceinline__ void publisher_warp(const Smem& sm, const Common& c, 
                     if (chain == 0 && w == 0) stamp(c, sm.trace, s, 7);
                 }
                 __syncwarp();
-                if (WPC == 1 && !(c.dbg & 16)) done_arrive(w, n);
+                if (CH::CPW == 1 && !(c.dbg & 16)) done_arrive(w, n);
                 ++n;
             }
 }
 
-template <int NT, int WPC>
+template <int NT, int WPC, int NCH>
 __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap* tmB, const CUtensorMap* tmB3, int warp, int lane, uint32_t tmem_base,
                                               const Common& c, int d, int my_zone, int k_lo, int k_hi, int nslab, int nbox,
                                               int b_col0, bool bptt) {
     constexpr int NROW = NG * WPC;
     constexpr int BOXB = NROW * 128;
-    constexpr uint32_t A_COL0 = 2 * NT * NROW;
+    constexpr uint32_t A_COL0 = NCH * NT * NROW;
+    constexpr bool HANDSHAKE = NCH > 2;              // the ring stage an item reuses was last read by ANOTHER chain's MMAs: explicit empty wait
     const bool rev = (d == 1) || (c.reverse0 != 0);
     const int kc = c.kper / 2;
     const int bps = c.bps;                           // boxes per ring stage
     const int nsub = nbox > 0 ? (nbox + bps - 1) / bps : 1;      // a CTA without a K share still paces its epilogue with one empty stage
-    const int npair = (c.nchain + 1) / 2;
+    const int npair = (c.nchain + NCH - 1) / NCH;
     if (warp == 0) {
         int z0 = my_zone, z1 = my_zone;
         if (lane < nbox) {
@@ -302,8 +314,8 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                 int t_src;
                 if (!bptt) { const int t = rev ? (c.Tp - 1 - s) : s; t_src = rev ? t + 1 : t - 1; }
                 else { const int t = rev ? s : (c.Tp - 1 - s); t_src = rev ? t - 1 : t + 1; }
-                for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch) {
-                    const int chain = 2 * pr + ch;
+                for (int ch = 0; ch < NCH && NCH * pr + ch < c.nchain; ++ch) {
+                    const int chain = NCH * pr + ch;
                     const unsigned int want = (unsigned int)(s * c.cs * WPC);
                     if (poller && !(c.dbg & 1)) {
                         grid_wait(zone_counter(c, d, chain, z0), want);
@@ -315,7 +327,7 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                     const int row = t_src * c.B + chain * NROW + c.row_off;
                     for (int sub = 0; sub < nsub; ++sub, ++seq) {
                         const uint32_t stage = seq & 1u, use = seq >> 1;
-                        if (nsub > 1) {
+                        if (nsub > 1 || HANDSHAKE) {
                             // a step's operand spans both stages: wait until the MMAs that read this stage last have completed.  (With
                             // one stage per item the own-cluster wait above already implies it: the chain's previous step is finished.)
                             if (lane == 0) mbar_wait(&sm.empty[stage], (use & 1u) ^ 1u);
@@ -348,11 +360,11 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
         uint32_t seq = 0;
         for (int pr = 0; pr < npair; ++pr) {
             for (int s = c.s0; s < c.Tp; ++s) {
-                for (int ch = 0; ch < 2 && 2 * pr + ch < c.nchain; ++ch) {
+                for (int ch = 0; ch < NCH && NCH * pr + ch < c.nchain; ++ch) {
                     for (int sub = 0; sub < nsub; ++sub, ++seq) {
                         const uint32_t stage = seq & 1u, use = seq >> 1;
                         mbar_wait(&sm.full[stage], use & 1u);
-                        if (lane == 0 && 2 * pr + ch == 0 && sub == 0) stamp(c, sm.trace, s, 2);
+                        if (lane == 0 && NCH * pr + ch == 0 && sub == 0) stamp(c, sm.trace, s, 2);
                         tcgen05_fence_after();
                         if (elect_one()) {
                             if (nslab > 0) {
@@ -370,21 +382,21 @@ __device__ __forceinline__ void control_warps(const Smem& sm, const CUtensorMap*
                                         if (ns > 3) umma_ts_bf16(dcol, acol + 24u, bdesc + 6u, idesc, 1u);
                                     }
                                 }
-                                if (nsub > 1) umma_commit(&sm.empty[stage]);
+                                if (nsub > 1 || HANDSHAKE) umma_commit(&sm.empty[stage]);
                                 if (sub == nsub - 1) umma_commit(&sm.tmem_full[ch]);
                             } else {
-                                if (nsub > 1) mbar_arrive(&sm.empty[stage]);
+                                if (nsub > 1 || HANDSHAKE) mbar_arrive(&sm.empty[stage]);
                                 if (sub == nsub - 1) mbar_arrive(&sm.tmem_full[ch]);
                             }
                         }
                         __syncwarp();
                     }
-                    if (lane == 0 && 2 * pr + ch == 0) stamp(c, sm.trace, s, 3);
+                    if (lane == 0 && NCH * pr + ch == 0) stamp(c, sm.trace, s, 3);
                 }
             }
         }
     } else {
-        publisher_warp<WPC>(sm, c, d, my_zone, warp - 2, lane);
+        publisher_warp<WPC, NCH>(sm, c, d, my_zone, warp - 2, lane);
     }
 }
 
@@ -475,12 +487,13 @@ struct FwdParams {
     __nv_bfloat16* hdrop; uint32_t drop_thresh; float inv_keep; uint64_t seed;   // fused inter-layer dropout output (or null)
 };
 
-template <int WPC>
+template <int WPC, int NCH>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmH3, const FwdParams p) {
-    constexpr int CS = 4, NT = 2, NGATE = 3, U = 16, NROW = NG * WPC, NSLOT = 2 * WPC;
+    using CH = Chains<WPC, NCH>;
+    constexpr int CS = 4, NT = 2, NGATE = 3, U = 16, NROW = NG * WPC, NSLOT = CH::NSLOT, CPW = CH::CPW;
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
-    constexpr uint32_t A_COL0 = 2 * NT * NROW;
+    constexpr uint32_t A_COL0 = NCH * NT * NROW;
     extern __shared__ uint8_t smem_raw[];
     const Common& c = p.c;
     const int H = c.H, B = c.B;
@@ -510,7 +523,7 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT, WPC>(sm, &tmH, &tmH3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * H, false);
+        control_warps<NT, WPC, NCH>(sm, &tmH, &tmH3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * H, false);
     } else {
         // ------------------------------------------------------------ epilogue warpgroup w
         // WPC == 1: it owns chain w of every chain pair (32 rows).  WPC == 2: it finalises rows [32w, 32w+32) of BOTH chains.
@@ -521,28 +534,28 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         float bh[3][4];
 #pragma unroll
         for (int g = 0; g < 3; ++g) ld4g(p.b_hh + d * 3 * H + g * H + ub, bh[g]);
-        uint32_t it[WPC], npub = 0;
+        uint32_t it[CPW], npub = 0;
 #pragma unroll
-        for (int k = 0; k < WPC; ++k) it[k] = 0;
-        const int npair = (c.nchain + 1) / 2;
+        for (int k = 0; k < CPW; ++k) it[k] = 0;
+        const int npair = (c.nchain + NCH - 1) / NCH;
         for (int pr = 0; pr < npair; ++pr) {
-            float k_h[WPC][4];                             // h_{t-1} of this thread's (row, 4 units) per chain, fp32, in registers
+            float k_h[CPW][4];                             // h_{t-1} of this thread's (row, 4 units) per chain, fp32, in registers
 #pragma unroll
-            for (int k = 0; k < WPC; ++k) {
-                const int ch = WPC == 1 ? w : k;
-                const int b = (2 * pr + ch) * NROW + (WPC == 1 ? 0 : w * NG) + bl;
+            for (int k = 0; k < CPW; ++k) {
+                const int ch = CH::ch(w, k);
+                const int b = (NCH * pr + ch) * NROW + (WPC == 1 ? 0 : w * NG) + bl;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) k_h[k][i] = 0.f;
-                if (p.h0 != nullptr && 2 * pr + ch < c.nchain && b < B) ld4g(p.h0 + (size_t)b * p.ldh + d * H + ub, k_h[k]);
+                if (p.h0 != nullptr && NCH * pr + ch < c.nchain && b < B) ld4g(p.h0 + (size_t)b * p.ldh + d * H + ub, k_h[k]);
             }
             for (int s = 0; s < c.Tp; ++s) {
                 const int t = rev ? (c.Tp - 1 - s) : s;
 #pragma unroll
-                for (int k = 0; k < WPC; ++k) {
-                    const int ch = WPC == 1 ? w : k;
-                    const int chain = 2 * pr + ch;
+                for (int k = 0; k < CPW; ++k) {
+                    const int ch = CH::ch(w, k);
+                    const int chain = NCH * pr + ch;
                     if (chain >= c.nchain) continue;
-                    const int slot = WPC == 1 ? w : 2 * w + k;
+                    const int slot = CH::slot(w, k);
                     uint8_t* inbox = sm.inbox + slot * MSGS;
                     uint8_t* outbox = sm.outbox + slot * MSGS;
                     const int b = chain * NROW + (WPC == 1 ? 0 : w * NG) + bl;
@@ -600,9 +613,9 @@ gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                     }
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
                     pub_arrive(w, npub);                         // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
-                    if (WPC == 1 && !(c.dbg & 16)) done_sync(w, npub);      // deferred stores only after the publisher's fence has been issued
+                    if (CPW == 1 && !(c.dbg & 16)) done_sync(w, npub);      // deferred stores only after the publisher's fence has been issued
                     ++npub;
-                    if (WPC > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
+                    if (CPW > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
                     if (row_ok && !(c.dbg & 8)) {                // off the critical path: nobody else reads these during the launch
                         st4(p.hseq + m * p.ldh + d * H + ub, k_h[k]);
                         if (p.r) {
@@ -639,12 +652,13 @@ struct BwdParams {
     float* db_ih; float* db_hh;                          // [D*3H] column sums of dgi / dgh over all rows (or null), pre-zeroed
 };
 
-template <int WPC>
+template <int WPC, int NCH>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG3, const BwdParams p) {
-    constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16, NROW = NG * WPC, NSLOT = 2 * WPC;       // NP passes of (batch row, 4 units) per thread
+    using CH = Chains<WPC, NCH>;
+    constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16, NROW = NG * WPC, NSLOT = CH::NSLOT, CPW = CH::CPW;       // NP passes of (batch row, 4 units) per thread
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
-    constexpr uint32_t A_COL0 = 2 * NT * NROW;
+    constexpr uint32_t A_COL0 = NCH * NT * NROW;
     extern __shared__ uint8_t smem_raw[];
     const Common& c = p.c;
     const int H = c.H, B = c.B;
@@ -675,7 +689,7 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     tcgen05_fence_after();
 
     if (warp < 4) {
-        control_warps<NT, WPC>(sm, &tmG, &tmG3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * 3 * H, true);
+        control_warps<NT, WPC, NCH>(sm, &tmG, &tmG3, warp, lane, tmem_base, c, d, my_zone, k_lo, k_hi, nslab, nbox, d * 3 * H, true);
     } else {
         const int e = warp - 4, w4 = e & 3, w = e >> 2, te = w4 * 32 + lane;
         const int bl = te >> 2, uo4 = te & 3;
@@ -684,14 +698,14 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         float* bsum = sm.bsum + (size_t)w * 16 * NP * WG_THREADS + te;
         if (p.db_ih)
             for (int v = 0; v < 16 * NP; ++v) bsum[v * WG_THREADS] = 0.f;
-        uint32_t it[WPC], npub = 0;
+        uint32_t it[CPW], npub = 0;
 #pragma unroll
-        for (int k = 0; k < WPC; ++k) it[k] = 0;
-        const int npair = (c.nchain + 1) / 2;
+        for (int k = 0; k < CPW; ++k) it[k] = 0;
+        const int npair = (c.nchain + NCH - 1) / NCH;
         for (int pr = 0; pr < npair; ++pr) {
-            float cr[WPC][NP][4];                            // dh_t * z_t carried to the next step, in registers
+            float cr[CPW][NP][4];                            // dh_t * z_t carried to the next step, in registers
 #pragma unroll
-            for (int k = 0; k < WPC; ++k)
+            for (int k = 0; k < CPW; ++k)
 #pragma unroll
                 for (int q = 0; q < NP; ++q)
 #pragma unroll
@@ -701,11 +715,11 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 const int tprev = rev ? t + 1 : t - 1;               // forward-time predecessor (source of h_{t-1})
                 const bool has_prev = rev ? (t + 1 < c.Tp) : (t > 0);
 #pragma unroll
-                for (int k = 0; k < WPC; ++k) {
-                    const int ch = WPC == 1 ? w : k;
-                    const int chain = 2 * pr + ch;
+                for (int k = 0; k < CPW; ++k) {
+                    const int ch = CH::ch(w, k);
+                    const int chain = NCH * pr + ch;
                     if (chain >= c.nchain) continue;
-                    const int slot = WPC == 1 ? w : 2 * w + k;
+                    const int slot = CH::slot(w, k);
                     uint8_t* inbox = sm.inbox + slot * MSGS;
                     uint8_t* outbox = sm.outbox + slot * MSGS;
                     const int b = chain * NROW + (WPC == 1 ? 0 : w * NG) + bl;
@@ -774,9 +788,9 @@ gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     }
                     if (te == 0 && chain == 0 && w == 0) stamp(c, sm.trace, s, 6);
                     pub_arrive(w, npub);                         // the publisher warp releases the counter (the consumer fences generic->async proxy after its acquire)
-                    if (WPC == 1 && !(c.dbg & 16)) done_sync(w, npub);      // deferred stores only after the publisher's fence has been issued
+                    if (CPW == 1 && !(c.dbg & 16)) done_sync(w, npub);      // deferred stores only after the publisher's fence has been issued
                     ++npub;
-                    if (WPC > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
+                    if (CPW > 1) wg_bar_sync(w);                 // the other chain's stage_row reuses `self`: every thread's gather must be done
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {               // off the critical path
                         const int ub = ub0 + 16 * q;
@@ -877,11 +891,17 @@ static int debug_flags() {
 }
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // chains of 32 rows (one warpgroup each) up to B = 64, chains of 64 rows (both warpgroups) beyond
-static int wg_per_chain(int B) {
-    static const int forced = [] { const char* e = getenv("NSD_GRU_WPC"); return e ? atoi(e) : 0; }();      // debug: force 1 or 2
-    if (forced == 1 || forced == 2) return forced;
-    return B > 2 * NG ? 2 : 1;
+// B > 64: four 32-row chains in flight (mode <1, 4>); NSD_GRU_WPC=2 selects the 64-row-chain form <2, 2> instead (A/B), =1 forces
+// 32-row chain pairs <1, 2> for any B
+static int forced_mode() {
+    static const int forced = [] { const char* e = getenv("NSD_GRU_WPC"); return e ? atoi(e) : 0; }();
+    return forced;
 }
+static int wg_per_chain(int B) {
+    if (forced_mode() == 1 || forced_mode() == 2) return forced_mode();
+    return 1;
+}
+static int chains_in_flight(int B, int wpc) { return (wpc == 1 && B > 2 * NG && forced_mode() != 1) ? 4 : 2; }
 static int n_chains(int B, int wpc) { return (B + NG * wpc - 1) / (NG * wpc); }
 // boxes per ring stage: the whole K share of a step, or half of it when two such stages would not fit (BPTT, 64-row chains)
 static int boxes_per_stage(int nbox, int wpc) {
@@ -941,9 +961,11 @@ int nsd_gru_fwd_bf16(const float* gi, int ldgi, const void* w_hh_bf16, const flo
     p.gi = gi; p.ldgi = ldgi; p.b_hh = b_hh; p.hseq = hseq; p.hseq_bf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16); p.ldh = ldh;
     p.r = r; p.z = z; p.n = n; p.hn = hn;
     p.hdrop = reinterpret_cast<__nv_bfloat16*>(hdrop_bf16); p.drop_thresh = dropout_threshold(p_drop); p.inv_keep = 1.0f / (1.0f - p_drop); p.seed = seed;
-    const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, 2 * wpc, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
-    rc = wpc == 1 ? launch_cluster_coop(gru_fwd_ts_kernel<1>, D * nper, CS, smem, tmH, tmH3, p, s)
-                  : launch_cluster_coop(gru_fwd_ts_kernel<2>, D * nper, CS, smem, tmH, tmH3, p, s);
+    const int nch = chains_in_flight(B, wpc);
+    const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, wpc == 2 ? 4 : nch, (CS - 1) * 3 * U * NG * 2, 3 * U * NG * 4);
+    rc = wpc == 2 ? launch_cluster_coop(gru_fwd_ts_kernel<2, 2>, D * nper, CS, smem, tmH, tmH3, p, s)
+       : nch == 4 ? launch_cluster_coop(gru_fwd_ts_kernel<1, 4>, D * nper, CS, smem, tmH, tmH3, p, s)
+                  : launch_cluster_coop(gru_fwd_ts_kernel<1, 2>, D * nper, CS, smem, tmH, tmH3, p, s);
     trace_end("gru_fwd_bf16", tr, s, D * nper);
     return rc;
 }
@@ -985,9 +1007,11 @@ int nsd_gru_bwd_bf16(const float* dhseq, int lddh, const float* hseq, int ldh, c
         NSD_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)D * 3 * H, s));
         NSD_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)D * 3 * H, s));
     }
-    const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, 2 * wpc, (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
-    rc = wpc == 1 ? launch_cluster_coop(gru_bwd_ts_kernel<1>, D * nper, CS, smem, tmG, tmG3, p, s)
-                  : launch_cluster_coop(gru_bwd_ts_kernel<2>, D * nper, CS, smem, tmG, tmG3, p, s);
+    const int nch = chains_in_flight(B, wpc);
+    const size_t smem = smem_bytes(2 * bps * NG * wpc * 128, wpc == 2 ? 4 : nch, (CS - 1) * U * NG * 2, U * NG * 4, db_ih ? sizeof(float) * 2 * 16 * (U / 16) * WG_THREADS : 0);
+    rc = wpc == 2 ? launch_cluster_coop(gru_bwd_ts_kernel<2, 2>, D * nper, CS, smem, tmG, tmG3, p, s)
+       : nch == 4 ? launch_cluster_coop(gru_bwd_ts_kernel<1, 4>, D * nper, CS, smem, tmG, tmG3, p, s)
+                  : launch_cluster_coop(gru_bwd_ts_kernel<1, 2>, D * nper, CS, smem, tmG, tmG3, p, s);
     trace_end("gru_bwd_bf16", tr, s, D * nper);
     return rc;
 }

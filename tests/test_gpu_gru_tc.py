@@ -26,7 +26,9 @@ def cu(a, dtype=torch.float32):
 
 
 @pytest.mark.parametrize("B,Tp,H,D,rev0", [(3, 7, 64, 1, 0), (3, 7, 64, 1, 1), (5, 1, 64, 2, 0), (70, 5, 128, 2, 0),
-                                           (64, 6, 1024, 2, 0), (64, 4, 1024, 1, 0), (16, 9, 256, 2, 0)])
+                                           (64, 6, 1024, 2, 0), (64, 4, 1024, 1, 0), (16, 9, 256, 2, 0),
+                                           # B > 64: four 32-row chains in flight; partial last chain, missing chains, two chain groups
+                                           (100, 6, 256, 2, 0), (130, 5, 1024, 2, 0), (200, 4, 128, 1, 1)])
 def test_gru_tc_fwd_bwd(B, Tp, H, D, rev0):
     rng = np.random.default_rng(H + Tp + B)
     M = Tp * B
