@@ -10,7 +10,9 @@ GRUDecoder, dropout 0.4, batch-sharded data parallel (weak scaling: 64 utterance
 
 Our arm prints one JSON line with
   value         utt/s, inputs resident in HBM, CUDA events, max over ranks
-  e2e           utt/s through the public API with HOST (pinned) inputs: H2D copies + a D2H read of the loss per step
+  e2e           utt/s through the public API with HOST (pinned) inputs: H2D copies (BatchPrefetcher) + a D2H read of the step's loss every step
+                (LossReader: the read waits for the forward's loss, not for the backward behind it); wall clock between two barriers, K steps,
+                measured 3 times back to back -- the fastest is reported, every sample is in the line
   roofline      the dominant kernel (K2 GEMM, tensor-bound): algorithmic FLOP / CUDA-event time measured in the timed region
   cpu_baseline  the torch-operator port of the reference (oracle/torch_port.py) on this box's host cores (rank 0, N=1)
 ``--impl reference`` times the reference's CPU path alone on the FULL batch: the reference's own ``GRUDecoder`` module,
@@ -34,6 +36,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "train utterances/sec (GRUDecoder, B=64, T=500)"
 UNIT = "utterances/s"
+E2E_REPEATS = 3                                                # samples of the host-timed end-to-end region (K steps each)
 NOISE = dict(white_noise_sd=0.8, constant_offset_sd=0.2)     # scripts/train_model.py:17-18 (whiteNoiseSD, constantOffsetSD)
 K1_SAVED_TENSORS = 2          # [B,T,N] f32 tensors K1's forward writes for its own backward (ys, z)
 MODEL_KW = dict(neural_dim=256, n_classes=40, hidden_dim=1024, layer_dim=5, nDays=24, dropout=0.4, strideLen=4,
@@ -322,17 +325,23 @@ def run_ours(a):
     prof = _lib.profile_end()
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: host inputs through the public API
+    # The host is in this loop (wall clock, a read-back every step), so a single scheduling hiccup of the box's CPU moves a 10-step sample
+    # by 10-20 %: the region is measured E2E_REPEATS times back to back (K steps each, max over ranks each) and the fastest is reported;
+    # every sample is kept in the line (e2e.samples_ms_per_step).
     step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        lv = step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    tt = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    e2e_samples = []
+    for _ in range(E2E_REPEATS):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            lv = step_e2e()
+        barrier()
+        e2e_samples.append((time.perf_counter() - t0) * 1e3)
+    tt = torch.tensor([ms] + e2e_samples, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = tt.tolist()
+    ms, e2e_samples = tt.tolist()[0], tt.tolist()[1:]
+    e2e_ms = min(e2e_samples)
     if a.timeline and gs is not None:
         gs.timeline = []
         step_resident()
@@ -419,7 +428,8 @@ def run_ours(a):
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "strong" if a.strong else "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic", "config": config_dict(a, world), "clocks": clocks,
-            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "samples_ms_per_step": [round(x / a.steps, 3) for x in e2e_samples], "reported": "fastest of the samples"},
             "gpu_launches": int(launches), "roofline": roofline, "rooflines_other": others, "loss": float(lv)}
     if world == 1 and not a.no_cpu_baseline:
         val, cores, t_step, kind, sample, _, _ = cpu_reference_run(a, 3, 1, budget_s=30.0)     # same protocol as --impl reference, bounded to ~30 s
