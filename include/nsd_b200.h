@@ -108,6 +108,10 @@ int nsd_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n,
  * BPTT kernel's stationary W_hh^T operand is loaded from.) */
 int nsd_cast_transpose(const void* src, int src_dtype, int R, int C, int ld_src, void* dst, int ld_dst, void* dstT,
                        int ld_dstT, void* stream);
+/* dstT[i] [C,R] (ld_dstT) <- transpose of the bf16 matrix src[i] [R,C] (ld_src), i < n, one launch for all of them (host arrays of device
+ * pointers; R, C and the leading dimensions even, bases 4-byte aligned).  The BPTT's W_hh^T operands of every layer and direction per step
+ * (model.py:50-57 keeps W_hh as [3H, H]; autograd's matmul backward reads it transposed). */
+int nsd_transpose_bf16_multi(int n, const void* const* src, void* const* dstT, int R, int C, int ld_src, int ld_dstT, void* stream);
 /* out[B,T,C] <- in[T,B,C] (or the inverse with the roles of T and B swapped by the caller). */
 int nsd_swap01_f32(const float* in, float* out, int D0, int D1, int C, void* stream);
 

@@ -255,6 +255,34 @@ __global__ void swap01_kernel(const float* __restrict__ in, float* __restrict__ 
     }
 }
 
+// Batched bf16 transposes of equally shaped matrices in ONE launch (the W_hh^T operands of every layer and direction for the BPTT:
+// ten 3072 x 1024 transposes of 6 MB each are ~12 us apiece as separate launches -- too small to fill the GPU -- and ~25 us together).
+constexpr int TR_MAX = 64;
+struct TransposeTable { const __nv_bfloat16* src[TR_MAX]; __nv_bfloat16* dstT[TR_MAX]; };
+__global__ void __launch_bounds__(256) transpose_bf16_multi_kernel(const __grid_constant__ TransposeTable tab, int R, int Cn, int ld_src, int ld_dstT) {
+    pdl_enter();
+    __shared__ uint32_t tile[64][33];                    // [row][column pair]
+    const __nv_bfloat16* __restrict__ src = tab.src[blockIdx.z];
+    __nv_bfloat16* __restrict__ dstT = tab.dstT[blockIdx.z];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    for (int i = ty; i < 64; i += 8) {
+        const int r = r0 + i, c = c0 + 2 * tx;
+        uint32_t v = 0u;
+        if (r < R && c < Cn) v = *reinterpret_cast<const uint32_t*>(src + (size_t)r * ld_src + c);      // R, Cn, ld even: c + 1 < Cn too
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i, r = r0 + 2 * tx;
+        if (c < Cn && r < R) {
+            const uint32_t a = tile[2 * tx][i >> 1], b = tile[2 * tx + 1][i >> 1];
+            const uint32_t lo = (i & 1) ? (a >> 16) : (a & 0xffffu), hi = (i & 1) ? (b >> 16) : (b & 0xffffu);
+            *reinterpret_cast<uint32_t*>(dstT + (size_t)c * ld_dstT + r) = lo | (hi << 16);
+        }
+    }
+}
+
 }  // namespace nsd
 
 extern "C" {
@@ -332,6 +360,25 @@ int nsd_cast_transpose(const void* src, int src_dtype, int R, int Cn, int ld_src
         else nsd::launch_k(cast_transpose_kernel<__nv_bfloat16, false>, grid, 256, 0, s, (const __nv_bfloat16*)src, R, Cn, ld_src, d0, ld_dst, d1, ld_dstT);
     } else { set_error("cast_transpose: bad dtype"); return NSD_ERR_INVALID; }
     NSD_LAUNCH_CHECK();
+    return NSD_OK;
+}
+
+int nsd_transpose_bf16_multi(int n, const void* const* src, void* const* dstT, int R, int Cn, int ld_src, int ld_dstT, void* stream) {
+    using namespace nsd;
+    NSD_CHECK_ARG(n >= 0 && R >= 0 && Cn >= 0, "transpose_bf16_multi: bad sizes");
+    if (n == 0 || R == 0 || Cn == 0) return NSD_OK;
+    NSD_CHECK_ARG(R % 2 == 0 && Cn % 2 == 0 && ld_src % 2 == 0 && ld_dstT % 2 == 0 && ld_src >= Cn && ld_dstT >= R,
+                  "transpose_bf16_multi: R=%d C=%d ld_src=%d ld_dstT=%d must be even (and ld >= row length)", R, Cn, ld_src, ld_dstT);
+    for (int t0 = 0; t0 < n; t0 += TR_MAX) {
+        TransposeTable tab;
+        const int cnt = std::min(TR_MAX, n - t0);
+        for (int i = 0; i < cnt; ++i) {
+            NSD_CHECK_ARG(src[t0 + i] && dstT[t0 + i] && (((uintptr_t)src[t0 + i] | (uintptr_t)dstT[t0 + i]) & 3) == 0, "transpose_bf16_multi: matrix %d null or misaligned", t0 + i);
+            tab.src[i] = (const __nv_bfloat16*)src[t0 + i]; tab.dstT[i] = (__nv_bfloat16*)dstT[t0 + i];
+        }
+        nsd::launch_k(transpose_bf16_multi_kernel, dim3(cdiv(Cn, 64), cdiv(R, 64), cnt), 256, 0, (cudaStream_t)stream, tab, R, Cn, ld_src, ld_dstT);
+        NSD_LAUNCH_CHECK();
+    }
     return NSD_OK;
 }
 

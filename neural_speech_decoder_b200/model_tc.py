@@ -93,17 +93,19 @@ def decoder_forward_tc(ctx, cfg, x, day_idx, taps, day_w, day_b, fc_w, fc_b, *gr
         bias_all = torch.empty((L, 2, D * 3 * H), device=dev, dtype=torch.float32)
         ops.multi_copy([gru_w[(l * D + d) * 4 + 2 + k].detach() for l in range(L) for k in range(2) for d in range(D)],
                        [bias_all[l, k, d * 3 * H:(d + 1) * 3 * H] for l in range(L) for k in range(2) for d in range(D)])
+    # gru_w holds the Parameters themselves: their version counters tell whether the kept bf16 copies are current
+    w_hh_all = [sh.stacked(("hh", l), [gru_w[(l * D + d) * 4 + 1] for d in range(D)]) for l in range(L)]      # [D*3H, H] each
+    w_hhT_all = None
+    if need_grad:                                            # BPTT operands [D*H, 3H] of every layer, all transposed in one launch
+        w_hhT_all = torch.empty((L, D * H, 3 * H), device=dev, dtype=torch.bfloat16)
+        ops.transpose_bf16_multi([w_hh_all[l][d * 3 * H:(d + 1) * 3 * H] for l in range(L) for d in range(D)],
+                                 [w_hhT_all[l, d * H:(d + 1) * H] for l in range(L) for d in range(D)])
     for l in range(L):
         in_l = inp.shape[1]
         ws = [[t.detach() for t in gru_w[(l * D + d) * 4:(l * D + d) * 4 + 4]] for d in range(D)]
-        # gru_w holds the Parameters themselves: their version counters tell whether the kept bf16 copies are current
         w_ih_bf = sh.stacked(("ih", l), [gru_w[(l * D + d) * 4] for d in range(D)])          # [D*3H, in_l]
-        w_hh_bf = sh.stacked(("hh", l), [gru_w[(l * D + d) * 4 + 1] for d in range(D)])      # [D*3H, H]
-        w_hhT_bf = None
-        if need_grad:                                                                        # [D*H, 3H] (BPTT operand)
-            w_hhT_bf = torch.empty((D * H, 3 * H), device=dev, dtype=torch.bfloat16)
-            for d in range(D):
-                ops.cast_transpose_into(w_hh_bf[d * 3 * H:(d + 1) * 3 * H], None, w_hhT_bf[d * H:(d + 1) * H])
+        w_hh_bf = w_hh_all[l]
+        w_hhT_bf = w_hhT_all[l] if need_grad else None
         b_ih, b_hh = (bias_all[l, 0], bias_all[l, 1]) if D > 1 else (ws[0][2], ws[0][3])
         gi = torch.empty((M, D * 3 * H), device=dev, dtype=torch.float32)
         ops.gemm(False, True, M, D * 3 * H, in_l, inp, in_l, w_ih_bf, in_l, gi, D * 3 * H, bias=b_ih.contiguous())

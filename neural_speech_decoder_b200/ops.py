@@ -115,6 +115,20 @@ def cast_transpose_into(src, dst, dstT):
          dst.stride(0) if dst is not None else 0, ptr(dstT), dstT.stride(0) if dstT is not None else 0, stream())
 
 
+def transpose_bf16_multi(srcs, dstTs):
+    """dstTs[i] [C,R] <- srcs[i]^T for equally shaped bf16 2-D views with unit inner strides and equal row strides, in one launch."""
+    import ctypes as C
+    n = len(srcs)
+    if n == 0:
+        return
+    R, Cn = srcs[0].shape
+    for s_, d_ in zip(srcs, dstTs):
+        assert s_.dtype == torch.bfloat16 and d_.dtype == torch.bfloat16 and tuple(s_.shape) == (R, Cn) and tuple(d_.shape) == (Cn, R)
+        assert s_.stride(1) == 1 and d_.stride(1) == 1 and s_.stride(0) == srcs[0].stride(0) and d_.stride(0) == dstTs[0].stride(0)
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    call("nsd_transpose_bf16_multi", n, arr(srcs), arr(dstTs), R, Cn, srcs[0].stride(0), dstTs[0].stride(0), stream())
+
+
 def swap01(x):
     """[D0,D1,C] -> contiguous [D1,D0,C]."""
     D0, D1, Cc = x.shape

@@ -277,6 +277,18 @@ def test_fused_adam_matches_torch_adam():
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
 
 
+def test_transpose_bf16_multi_is_exact():
+    """One launch transposes every layer's / direction's W_hh (row-range views of stacked buffers) bit for bit."""
+    torch.manual_seed(3)
+    for R, Cn, n in [(192, 64, 4), (3072, 1024, 10), (70, 130, 3)]:
+        src = torch.randn(n, R + 6, Cn, device=DEV).to(torch.bfloat16)
+        dst = torch.zeros(n, Cn, R + 2, device=DEV, dtype=torch.bfloat16)
+        ops.transpose_bf16_multi([src[i, 2:2 + R] for i in range(n)], [dst[i, :, :R] for i in range(n)])
+        for i in range(n):
+            assert torch.equal(dst[i, :, :R], src[i, 2:2 + R].t())
+        assert float(dst[:, :, R:].abs().max()) == 0.0
+
+
 def test_fused_adam_split_step_is_bit_identical():
     """step(only=...) in two calls (what the data-parallel train_step does under the last all-reduce) == one step()."""
     torch.manual_seed(1)
