@@ -34,7 +34,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "train utterances/sec (GRUDecoder, B=64, T=500)"
+METRIC = "train utterances/sec (GRUDecoder, B=64, T=500)"      # BASELINE.json's metric; metric_name() restates B and T when they are overridden
+
+
+def metric_name(a):
+    return METRIC if (a.batch == 64 and a.T == 500) else f"train utterances/sec (GRUDecoder, B={a.batch}, T={a.T})"
 UNIT = "utterances/s"
 E2E_REPEATS = 3                                                # samples of the host-timed end-to-end region (K steps each)
 NOISE = dict(white_noise_sd=0.8, constant_offset_sd=0.2)     # scripts/train_model.py:17-18 (whiteNoiseSD, constantOffsetSD)
@@ -137,7 +141,7 @@ def run_reference(a):
     if rank != 0:
         return
     val, cores, t_step, kind, sample, n_timed, n_warm = cpu_reference_run(a, a.steps, a.warmup)
-    line = {"metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": n_timed, "warmup": n_warm,
+    line = {"metric": metric_name(a), "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": n_timed, "warmup": n_warm,
             "ms_per_step": round(t_step * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config_dict(a, a.gpus),
             "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
@@ -178,7 +182,7 @@ def run_reference_cuda(a):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
-        print(json.dumps({"metric": METRIC, "value": round(a.batch / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+        print(json.dumps({"metric": metric_name(a), "value": round(a.batch / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": 1, "steps": a.steps,
                           "warmup": max(a.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True, "impl": "reference-cuda",
                           "kind": kind, "dtype": mode, "data": "synthetic", "config": config_dict(a, 1), "loss": float(loss),
                           "note": "secondary: reference module on the GPU through torch/cuDNN/cuBLAS (no repo kernels); not the headline ratio"}),
@@ -425,7 +429,7 @@ def run_ours(a):
             others.append({"kernel": nm, "bound": "latency", "us_per_timestep": round(t_ms * 1e3 / (5 * frames), 3), "ms_per_step": round(t_ms, 3),
                            "note": "both directions, all batch groups; 5 layers x %d sequential timesteps" % frames})
     h2d = sum(t.numel() * t.element_size() for t in host)
-    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+    line = {"metric": metric_name(a), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "strong" if a.strong else "weak", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic", "config": config_dict(a, world), "clocks": clocks,
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
