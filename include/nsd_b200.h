@@ -203,6 +203,10 @@ size_t nsd_edit_distance_workspace(int B, int max_len);
  * numel a HOST array.  One launch per 48 tensors.  shadow_bf16 (NULL, or a HOST array whose entries
  * may be NULL): device pointer of a contiguous bf16 copy of the parameter, rewritten with the
  * updated value in the same pass (the tensor-core operand copy the next forward reads).       */
+/* on != 0: the following nsd_adam_step launches are issued directly behind a recurrence kernel (nsd_gru_bwd_bf16) whose output they do not
+ * need; they run under it on the SMs it leaves free and complete after it (programmatic dependent launch).  Set it back to 0 afterwards.
+ * No counterpart in the reference (trainer:259 steps after the whole backward). */
+int nsd_set_adam_late_wait(int on);
 int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                   void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream);

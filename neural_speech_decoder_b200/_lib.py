@@ -81,6 +81,7 @@ SIGNATURES = {
     "nsd_stream_push": (i32, [vp, vp, i32, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
                               vp, vp, vp, vp, vp, vp, sz, vp]),
     "nsd_multi_copy_f32": (i32, [i32, vp, vp, vp, vp]),
+    "nsd_set_adam_late_wait": (i32, [i32]),
     "nsd_transpose_bf16_multi": (i32, [i32, vp, vp, i32, i32, i32, i32, vp]),
     "nsd_greedy_decode": (i32, [vp, i64, i64, i64, vp, i32, i32, i32, i32, vp, vp, vp]),
     "nsd_edit_distance": (i32, [vp, i32, vp, vp, i32, vp, i32, vp, vp, sz, vp]),

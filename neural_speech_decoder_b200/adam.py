@@ -19,10 +19,11 @@ class FusedAdam(torch.optim.Optimizer):
         self.shadows = shadows
 
     @torch.no_grad()
-    def step(self, closure=None, only=None):
+    def step(self, closure=None, only=None, under_recurrence=False):
         """``only``: optional collection of parameters -- update just those (each parameter keeps its own step count, so a step
         may be split into several calls; the data-parallel train_step updates the buckets whose all-reduce has finished while
-        the last one is still on the wire)."""
+        the last one is still on the wire).  ``under_recurrence``: the call comes from inside the backward, directly behind the launch of a
+        recurrence kernel that does not produce these parameters' gradients: the update runs under that kernel (ops.adam_step)."""
         loss = None
         only_ids = None if only is None else {id(p) for p in only}
         if closure is not None:
@@ -60,7 +61,7 @@ class FusedAdam(torch.optim.Optimizer):
                     raise RuntimeError("FusedAdam (B200): the parameters of one group must live on one device")
                 with torch.cuda.device(ps[0].device):
                     ops.adam_step(ps, gs, ms, vs, group["lr"], *group["betas"], group["eps"], group["weight_decay"], step,
-                                  self.grad_scale, sh)
+                                  self.grad_scale, sh, under_recurrence=under_recurrence and len(ps) <= 48)
             # the kernels write through raw pointers: tell autograd (and the shadow cache) that the parameters changed
             if touched:
                 torch.autograd.graph.increment_version(touched)

@@ -47,10 +47,15 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
     p -= step_size * (m / denom);
 }
 
+// late_wait (the optimizer under the recurrence): the launch sits behind a K3 kernel whose OUTPUT it does not need -- its gradients were
+// final before that kernel started -- so it must not wait for it: the CTAs start as soon as every K3 CTA is resident (they get the SMs
+// the recurrence leaves free) and stream their update under it.  The grid must still not COMPLETE before K3 has, because the next kernel
+// in the stream orders itself after THIS grid only: the last CTA to finish its work (device counter) executes griddepcontrol.wait.
+__device__ unsigned int g_adam_done = 0;
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tab, float b1, float b2, float wd, float gs,
                                                    float step_size, float inv_sqrt_bc2, float eps, float decay_mul,
-                                                   const float* __restrict__ grad_sqnorm, float max_norm, const float* __restrict__ hyper) {
-    pdl_enter();
+                                                   const float* __restrict__ grad_sqnorm, float max_norm, const float* __restrict__ hyper, int late_wait) {
+    if (!late_wait) { pdl_launch_dependents(); pdl_wait(); }   // late_wait: the next kernel's CTAs must not crowd the few SMs this launch runs on
     if (hyper != nullptr) { step_size = hyper[0]; inv_sqrt_bc2 = hyper[1]; decay_mul = hyper[2]; }   // device-resident schedule (graph replay)
     if (grad_sqnorm != nullptr) {            // clip_grad_norm_(max_norm): coefficient from the device-resident squared norm, no host sync
         const float norm = sqrtf(*grad_sqnorm) * gs;
@@ -91,7 +96,18 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
             if (S) S[i] = __float2bfloat16_rn(P[i]);
         }
     }
+    if (late_wait) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&g_adam_done, 1u) == gridDim.x - 1) {
+                g_adam_done = 0;
+                pdl_wait();
+            }
+        }
+    }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // Multi-tensor gather: up to 64 small f32 vectors copied to their destinations in ONE launch (the per-direction GRU
@@ -133,6 +149,8 @@ int nsd_multi_copy_f32(int n_tensors, const void* const* src, void* const* dst, 
     return NSD_OK;
 }
 
+
+static int g_adam_late_wait = 0;
 static int adam_impl(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                      const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps, float wd_l2, float decay_mul,
                      int step, float grad_scale, const float* grad_sqnorm, float max_norm, const float* hyper, void* stream, const char* who) {
@@ -156,11 +174,13 @@ static int adam_impl(int n_tensors, void* const* params, const void* const* grad
         tab.chunk_start[tab.count] = chunks;
         if (chunks == 0) continue;
         nsd::launch_k(adam_kernel, chunks, 256, 0, (cudaStream_t)stream, tab, beta1, beta2, wd_l2, grad_scale, step_size, inv_sqrt_bc2, eps, decay_mul, grad_sqnorm,
-                                                               max_norm, hyper);
+                                                               max_norm, hyper, (g_adam_late_wait && pdl_enabled() && n_tensors <= ADAM_MAX_TENSORS) ? 1 : 0);
         NSD_LAUNCH_CHECK();
     }
     return NSD_OK;
 }
+
+int nsd_set_adam_late_wait(int on) { g_adam_late_wait = on ? 1 : 0; return NSD_OK; }
 
 int nsd_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
                   void* const* exp_avg_sq, const int64_t* numel, void* const* shadow_bf16, float lr, float beta1, float beta2, float eps,

@@ -490,6 +490,9 @@ struct FwdParams {
 template <int WPC, int NCH>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmH3, const FwdParams p) {
+    // a kernel launched behind this one with the programmatic-serialization attribute may take the ~20 SMs the recurrence leaves free
+    // once all of its CTAs are resident (the optimizer of the previous layer's bucket does, elementwise.cu: adam_kernel late_wait)
+    pdl_launch_dependents();
     using CH = Chains<WPC, NCH>;
     constexpr int CS = 4, NT = 2, NGATE = 3, U = 16, NROW = NG * WPC, NSLOT = CH::NSLOT, CPW = CH::CPW;
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;
@@ -655,6 +658,9 @@ struct BwdParams {
 template <int WPC, int NCH>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG3, const BwdParams p) {
+    // a kernel launched behind this one with the programmatic-serialization attribute may take the ~20 SMs the recurrence leaves free
+    // once all of its CTAs are resident (the optimizer of the previous layer's bucket does, elementwise.cu: adam_kernel late_wait)
+    pdl_launch_dependents();
     using CH = Chains<WPC, NCH>;
     constexpr int CS = 4, NT = 1, NGATE = 1, U = 32, NP = U / 16, NROW = NG * WPC, NSLOT = CH::NSLOT, CPW = CH::CPW;       // NP passes of (batch row, 4 units) per thread
     constexpr int MSG = NGATE * U * NG * 2, MSGS = (CS - 1) * MSG, SELF = NGATE * U * NG * 4;

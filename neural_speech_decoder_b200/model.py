@@ -123,6 +123,7 @@ class GRUDecoder(nn.Module):
         self._step = 0
         self._err_flag: Optional[torch.Tensor] = None
         self.grad_sync = None       # parallel.GradSync when training data-parallel (set by trainer.train_step)
+        self.step_hook = None       # callable(list of Parameters): optimizer update of a finished bucket from inside the backward (trainer.train_step)
         # (whiteNoiseSD, constantOffsetSD) of the trainer's in-loop augmentation (trainer:194-201), applied inside K1 while
         # the module is in train mode; None = the caller adds its own noise (or none), as in the reference
         self.input_noise = None
@@ -165,7 +166,7 @@ class GRUDecoder(nn.Module):
         cfg = dict(K=self.kernelLen, S=self.strideLen, H=self.hidden_dim, L=self.layer_dim,
                    D=2 if self.bidirectional else 1, n_days=self.nDays, precision=self.precision,
                    p_drop=float(self.dropout) if self.training else 0.0, seed=0, err_flag=self._err_flag,
-                   grad_sync=self.grad_sync, shadows=self._shadows)
+                   grad_sync=self.grad_sync, shadows=self._shadows, step_hook=self.step_hook)
         noisy = self.training and self.input_noise is not None and any(float(v) != 0.0 for v in self.input_noise)
         if cfg["p_drop"] > 0 or noisy:
             self._step += 1

@@ -146,6 +146,24 @@ def decoder_backward_tc(ctx, dlogits):
     C = fc_w.shape[0]
     f32 = dict(device=dev, dtype=torch.float32)
     gs = cfg.get("grad_sync")
+    # optimizer under the recurrence (single GPU): the bucket whose gradients became final in front of a BPTT launch is updated by a
+    # kernel issued directly BEHIND that launch, which runs on the SMs the recurrence leaves free (trainer.train_step sets the hook)
+    hook = cfg.get("step_hook") if gs is None else None
+    pending, stepped = None, set()
+
+    def flush_pending():
+        nonlocal pending
+        if hook is None or not pending:
+            return
+        ok = [(p_, g_) for p_, g_ in pending if isinstance(p_, torch.Tensor) and p_.requires_grad and p_.grad is None and g_ is not None]
+        pending = None
+        if not ok:
+            return
+        for p_, g_ in ok:
+            p_.grad = g_
+            stepped.add(id(p_))
+        hook([p_ for p_, _ in ok])
+
     dl_tm = ops.swap01(dlogits.contiguous().float()).view(M, C)
     hid = ctx.hid
     d_fc_w, d_fc_b = _flat_views([(C, D * H), (C,)], dev, gs)
@@ -157,6 +175,7 @@ def decoder_backward_tc(ctx, dlogits):
     ops.colsum(dl_tm, M, C, C, d_fc_b)
     if gs is not None:
         gs.bucket_ready(d_fc_w._base)
+    pending = [(ctx.params[2], d_fc_w), (ctx.params[3], d_fc_b)]
     dh = torch.empty((M, D * H), **f32)
     ops.gemm(False, False, M, D * H, C, dl_bf, Cp, ctx.fc_w_bf, D * H, dh, D * H)       # dh = dl fc_w
     ggru: List[Optional[torch.Tensor]] = [None] * len(gru_w)
@@ -171,6 +190,7 @@ def decoder_backward_tc(ctx, dlogits):
         drop = cfg["p_drop"] if (cfg["p_drop"] > 0 and l < L - 1) else 0.0
         # BPTT with the output-dropout mask applied on load and the bias gradients (column sums) accumulated in-kernel
         dgi, dgh = ops.gru_bwd_bf16(dh, hseq, saves, w_hhT_bf, Tp, B, H, D, False, drop, cfg["seed"] + l, v_bih, v_bhh)
+        flush_pending()             # the previous bucket's update: issued right behind the BPTT launch, runs under it
         # wgrad W_ih: dW[D*3H, in_l] = dgi^T inp -- reduction over the T'*B rows, both operands M/N-major as stored
         ops.gemm(True, False, D * 3 * H, in_l, M, dgi, D * 3 * H, inp, in_l, v_wih, in_l)
         if Tp > 1:
@@ -204,6 +224,8 @@ def decoder_backward_tc(ctx, dlogits):
                                    v_bih[d * 3 * H:(d + 1) * 3 * H], v_bhh[d * 3 * H:(d + 1) * 3 * H]]
         if gs is not None and not early:
             gs.bucket_ready(v_wih._base)
+        if l > 0:                   # layer 0's bucket has no recurrence left to hide under: it is updated by the caller's step()
+            pending = [(gru_w[(l * D + d) * 4 + k], ggru[(l * D + d) * 4 + k]) for d in range(D) for k in range(4)]
         ctx.layers[l] = None
         dh = dinp
     ys, z, day_idx = ctx.front
@@ -216,4 +238,6 @@ def decoder_backward_tc(ctx, dlogits):
     grads = (d_day_w, d_day_b, d_fc_w, d_fc_b, *ggru)
     if gs is not None:
         return (None,) * 4 + _assign_grads(ctx.params, grads)
+    if stepped:                     # already assigned (and consumed by the optimizer) inside this backward
+        grads = tuple(None if id(p_) in stepped else g_ for p_, g_ in zip(ctx.params, grads))
     return (None, None, None, None) + grads

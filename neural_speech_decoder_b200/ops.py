@@ -224,7 +224,7 @@ def log_softmax(x):
     return out
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadows=None):
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadows=None, under_recurrence=False):
     """torch.optim.Adam (L2-in-gradient, not AdamW) on a list of f32 tensors in as few launches as possible.
     ``shadows``: optional list (entries may be None) of contiguous bf16 tensors rewritten with the updated parameters."""
     import ctypes as C
@@ -238,8 +238,14 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
         for s_, p_ in zip(shadows, params):
             assert s_ is None or (s_.is_contiguous() and s_.dtype == torch.bfloat16 and s_.numel() == p_.numel())
         sh = (C.c_void_p * n)(*[None if s_ is None else s_.data_ptr() for s_ in shadows])
-    call("nsd_adam_step", n, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq), numel, sh, float(lr), float(beta1),
-         float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), stream())
+    if under_recurrence:       # issued directly behind a K3 launch whose output it does not need: runs under it (nsd_set_adam_late_wait)
+        call("nsd_set_adam_late_wait", 1)
+    try:
+        call("nsd_adam_step", n, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq), numel, sh, float(lr), float(beta1),
+             float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), stream())
+    finally:
+        if under_recurrence:
+            call("nsd_set_adam_late_wait", 0)
 
 
 def stream_push(bins_in, rawring, day, day_w, day_b, taps, x0buf, n_bins, extra, K, S, w_ih_bf, w_hh_bf, b_ih, b_hh, h, hbf, fc_w_bf, fc_b,

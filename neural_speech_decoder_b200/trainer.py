@@ -17,6 +17,11 @@ from . import ctc as _ctc
 from .adam import FusedAdam
 
 
+def _step_in_backward() -> bool:
+    import os
+    return os.environ.get("NSD_STEP_IN_BACKWARD", "1") != "0"
+
+
 def make_optimizer(model: torch.nn.Module, args: dict):
     """trainer:163-175 (the non-AdamW branch, which the GRU configs use)."""
     opt = FusedAdam(model.parameters(), lr=args["lrStart"], betas=(0.9, 0.999), eps=0.1,
@@ -71,6 +76,17 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
         raise RuntimeError("train_step(grad_sync=...) sums gradients over ranks; use FusedAdam (make_optimizer), which folds the "
                            "1/world_size average into its update, or divide the gradients yourself")
     model.input_noise = (white_noise_sd, constant_offset_sd) if (white_noise_sd or constant_offset_sd) else None
+    # single GPU, bf16 path: the update of each finished gradient bucket is issued from inside the backward, directly behind the next
+    # layer's BPTT launch, and runs under it on the SMs the recurrence leaves free (model_tc.decoder_backward_tc); layer 0 and the day
+    # weights -- nothing left to hide under -- are updated after the backward as usual.  Same arithmetic per parameter.
+    stepped = []
+    model.step_hook = None
+    if (grad_sync is None and isinstance(optimizer, FusedAdam) and getattr(model, "precision", None) == "bf16" and _step_in_backward()
+            and len(optimizer.param_groups) == 1):
+        def _hook(ps):
+            optimizer.step(only=ps, under_recurrence=True)
+            stepped.extend(ps)
+        model.step_hook = _hook
     pred = model.forward(X, dayIdx)                                         # trainer:208
     lens = _ctc.out_lens(X_len, model.kernelLen, model.strideLen)           # trainer:209
     loss = _ctc.ctc_loss_from_logits(pred, y, lens, y_len, blank=0, reduction="mean")   # trainer:210-218, 242
@@ -79,7 +95,10 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
     optimizer.zero_grad(set_to_none=True)                                   # trainer:251
     if grad_sync is not None:
         grad_sync.begin()
-    loss.backward()                                                         # trainer:252
+    try:
+        loss.backward()                                                     # trainer:252
+    finally:
+        model.step_hook = None
     if grad_sync is not None and grad_sync.world > 1 and isinstance(optimizer, FusedAdam):
         # the last big bucket (layer 0) is still being all-reduced when the backward's kernels are done: update the parameters of
         # every finished bucket under it, then the rest (same arithmetic per parameter; the step is just issued in two launches)
@@ -94,6 +113,9 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
         else:
             grad_sync.finish()
             optimizer.step()
+    elif stepped:
+        done = {id(p) for p in stepped}
+        optimizer.step(only=[p for g in optimizer.param_groups for p in g["params"] if p.grad is not None and id(p) not in done])
     else:
         if grad_sync is not None:
             grad_sync.finish()

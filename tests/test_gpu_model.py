@@ -162,6 +162,38 @@ def test_train_step_reduces_loss_and_eval_batch():
     assert tot == int(g["y_len"].sum()) and 0 <= dist <= tot + int(g["out_lens"].sum())
 
 
+def test_optimizer_under_the_recurrence_is_bit_identical(monkeypatch):
+    """Single GPU, bf16: train_step updates each finished bucket from inside the backward, behind the next BPTT launch (the update runs under
+    it).  Losses and every parameter after several steps must equal the classic order (whole update after the backward) bit for bit, with
+    and without dropout; and the in-backward path must really have been taken."""
+    from neural_speech_decoder_b200 import _lib
+    kw = dict(neural_dim=32, n_classes=10, hidden_dim=64, layer_dim=3, nDays=4, dropout=0.3, strideLen=4, kernelLen=16,
+              gaussianSmoothWidth=2.0, bidirectional=True)
+    X, y, X_len, y_len, day = make_batch(6, 90, n_feat=32, n_days=4, n_classes=10, seed=7, ragged=True, min_tgt=2, max_tgt=6,
+                                         kernel_len=16, stride_len=4)
+    batch = [t.to(DEV) for t in (X, y, X_len, y_len, day)]
+    runs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NSD_STEP_IN_BACKWARD", flag)
+        nsd.set_default_precision("bf16")
+        try:
+            torch.manual_seed(0)
+            m = nsd.GRUDecoder(device=DEV, **kw)
+        finally:
+            nsd.set_default_precision("fp32")
+        fill_trained_like_(m, seed=3)
+        m = m.to(DEV)
+        m.train()
+        opt, sched = nsd.make_optimizer(m, dict(lrStart=0.02, lrEnd=0.01, nBatch=10, l2_decay=1e-5))
+        _lib.profile_begin({"nsd_adam_step"})
+        losses = [nsd.train_step(m, opt, *batch, scheduler=sched, white_noise_sd=0.3).item() for _ in range(4)]
+        calls = sum(n for n, _ in _lib.profile_end().values())
+        runs.append((losses, [p.detach().clone() for p in m.parameters()], calls))
+    assert runs[0][0] == runs[1][0]
+    assert all(torch.equal(a, b) for a, b in zip(runs[0][1], runs[1][1]))
+    assert runs[1][2] == 4 and runs[0][2] == 4 * (kw["layer_dim"] + 1)      # fc + layers L-1..1 in the backward, layer 0 + day weights after it
+
+
 def test_bf16_weight_shadows_follow_the_parameters():
     """bf16 mode keeps bf16 operand copies of the weights across steps; FusedAdam rewrites them in its update kernel.
     Training with the copies maintained by Adam must be bit-identical to training that re-casts every step, and any
