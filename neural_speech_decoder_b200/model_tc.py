@@ -148,21 +148,49 @@ def decoder_backward_tc(ctx, dlogits):
     gs = cfg.get("grad_sync")
     # optimizer under the recurrence (single GPU): the bucket whose gradients became final in front of a BPTT launch is updated by a
     # kernel issued directly BEHIND that launch, which runs on the SMs the recurrence leaves free (trainer.train_step sets the hook)
-    hook = cfg.get("step_hook") if gs is None else None
+    # Data parallel: the same, one layer later -- a bucket released in front of BPTT(l) is all-reduced under it; the compute stream takes that
+    # collective's event in front of BPTT(l-1) (long finished, no stall) and the update follows BPTT(l-1)'s launch.
+    hook = cfg.get("step_hook")
+    dp = gs is not None
+    if dp and getattr(gs, "world", 1) <= 1:
+        hook = None
     pending, stepped = None, set()
+    queue = []                      # data parallel: [pairs, collective handle, BPTT launches since the release]
 
-    def flush_pending():
-        nonlocal pending
-        if hook is None or not pending:
-            return
-        ok = [(p_, g_) for p_, g_ in pending if isinstance(p_, torch.Tensor) and p_.requires_grad and p_.grad is None and g_ is not None]
-        pending = None
+    def step_pairs(pairs):
+        ok = [(p_, g_) for p_, g_ in pairs if isinstance(p_, torch.Tensor) and p_.requires_grad and p_.grad is None and g_ is not None]
         if not ok:
             return
         for p_, g_ in ok:
             p_.grad = g_
             stepped.add(id(p_))
         hook([p_ for p_, _ in ok])
+
+    def before_bptt():              # data parallel: collectives that had a whole BPTT to finish under -> their events into the compute stream
+        if hook is None or not dp:
+            return []
+        due = [q for q in queue if q[2] >= 1]
+        for q in due:
+            q[1].wait()
+            queue.remove(q)
+        return due
+
+    def flush_pending(due=()):
+        nonlocal pending
+        if hook is None:
+            return
+        if dp:
+            for q in due:
+                step_pairs(q[0])
+            if pending:             # released in front of the BPTT just launched: its all-reduce runs under it
+                queue.append([pending, gs.handles[-1], 0])
+                pending = None
+            for q in queue:
+                q[2] += 1
+            return
+        if pending:
+            pairs, pending = pending, None
+            step_pairs(pairs)
 
     dl_tm = ops.swap01(dlogits.contiguous().float()).view(M, C)
     hid = ctx.hid
@@ -189,8 +217,9 @@ def decoder_backward_tc(ctx, dlogits):
                                                  zero=(Tp == 1))
         drop = cfg["p_drop"] if (cfg["p_drop"] > 0 and l < L - 1) else 0.0
         # BPTT with the output-dropout mask applied on load and the bias gradients (column sums) accumulated in-kernel
+        due = before_bptt()
         dgi, dgh = ops.gru_bwd_bf16(dh, hseq, saves, w_hhT_bf, Tp, B, H, D, False, drop, cfg["seed"] + l, v_bih, v_bhh)
-        flush_pending()             # the previous bucket's update: issued right behind the BPTT launch, runs under it
+        flush_pending(due)          # the previous bucket's update: issued right behind the BPTT launch, runs under it
         # wgrad W_ih: dW[D*3H, in_l] = dgi^T inp -- reduction over the T'*B rows, both operands M/N-major as stored
         ops.gemm(True, False, D * 3 * H, in_l, M, dgi, D * 3 * H, inp, in_l, v_wih, in_l)
         if Tp > 1:
@@ -236,8 +265,8 @@ def decoder_backward_tc(ctx, dlogits):
             gs.bucket_ready(d_day_w._base)
     ctx.layers = ctx.hid = ctx.front = None
     grads = (d_day_w, d_day_b, d_fc_w, d_fc_b, *ggru)
-    if gs is not None:
-        return (None,) * 4 + _assign_grads(ctx.params, grads)
     if stepped:                     # already assigned (and consumed by the optimizer) inside this backward
         grads = tuple(None if id(p_) in stepped else g_ for p_, g_ in zip(ctx.params, grads))
+    if gs is not None:
+        return (None,) * 4 + _assign_grads(ctx.params, grads)
     return (None, None, None, None) + grads

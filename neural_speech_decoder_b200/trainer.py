@@ -76,12 +76,13 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
         raise RuntimeError("train_step(grad_sync=...) sums gradients over ranks; use FusedAdam (make_optimizer), which folds the "
                            "1/world_size average into its update, or divide the gradients yourself")
     model.input_noise = (white_noise_sd, constant_offset_sd) if (white_noise_sd or constant_offset_sd) else None
-    # single GPU, bf16 path: the update of each finished gradient bucket is issued from inside the backward, directly behind the next
-    # layer's BPTT launch, and runs under it on the SMs the recurrence leaves free (model_tc.decoder_backward_tc); layer 0 and the day
-    # weights -- nothing left to hide under -- are updated after the backward as usual.  Same arithmetic per parameter.
+    # bf16 path: the update of each finished gradient bucket is issued from inside the backward, directly behind a BPTT launch, and runs
+    # under it on the SMs the recurrence leaves free (model_tc.decoder_backward_tc): behind the next layer's launch on one GPU, one layer
+    # later (after the bucket's all-reduce) when data parallel.  What has no recurrence left to hide under (layer 0, the day weights; data
+    # parallel also layer 1) is updated after the backward as usual.  Same arithmetic per parameter.
     stepped = []
     model.step_hook = None
-    if (grad_sync is None and isinstance(optimizer, FusedAdam) and getattr(model, "precision", None) == "bf16" and _step_in_backward()
+    if (isinstance(optimizer, FusedAdam) and getattr(model, "precision", None) == "bf16" and _step_in_backward()
             and len(optimizer.param_groups) == 1):
         def _hook(ps):
             optimizer.step(only=ps, under_recurrence=True)
@@ -103,8 +104,9 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
         # the last big bucket (layer 0) is still being all-reduced when the backward's kernels are done: update the parameters of
         # every finished bucket under it, then the rest (same arithmetic per parameter; the step is just issued in two launches)
         pending = grad_sync.finish_early()
+        done = {id(p) for p in stepped}                       # buckets already updated from inside the backward
         if pending:
-            live = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+            live = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None and id(p) not in done]
             late = [p for p in live if p.grad.untyped_storage().data_ptr() in pending]
             late_ids = {id(p) for p in late}
             optimizer.step(only=[p for p in live if id(p) not in late_ids])
@@ -112,7 +114,7 @@ def train_step(model, optimizer, X, y, X_len, y_len, dayIdx, scheduler=None, gra
             optimizer.step(only=late)
         else:
             grad_sync.finish()
-            optimizer.step()
+            optimizer.step(only=[p for g in optimizer.param_groups for p in g["params"] if p.grad is not None and id(p) not in done])
     elif stepped:
         done = {id(p) for p in stepped}
         optimizer.step(only=[p for g in optimizer.param_groups for p in g["params"] if p.grad is not None and id(p) not in done])
