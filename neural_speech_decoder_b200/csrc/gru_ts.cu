@@ -26,8 +26,11 @@
 //     B <= 64 (WPC = 1): a chain is 32 batch rows (UMMA N = 32) and owns one epilogue warpgroup.  B > 64 (WPC = 2): a
 //     chain is 64 rows (N = 64, same MMA cost), both warpgroups finalise 32 rows each and alternate between the chains.
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc_common.cuh"
+
+extern char** environ;      // process environment (POSIX); scanned once for Nsight Compute's injection variables
 
 namespace nsd {
 namespace rts {
@@ -848,7 +851,16 @@ static int launch_cluster_coop(Kern kern, int grid, int cs, size_t smem, const C
     attrs[1].val.cooperative = 1;
     // NSD_GRU_NO_COOP=1 (profiling aid): drop the cooperative attribute, which Nsight Compute's kernel replay cannot combine
     // with clusters.  Co-residency of the whole grid is still checked below; it then holds only while the GPU is otherwise idle.
-    static const bool no_coop = [] { const char* e = getenv("NSD_GRU_NO_COOP"); return e && e[0] == '1'; }();
+    // The same when the process runs under Nsight Compute's injection (its environment variables are present): a profiler pass over any
+    // command of this library then lists the recurrence kernels instead of dying on the first cooperative cluster launch.
+    static const bool no_coop = [] {
+        const char* e = getenv("NSD_GRU_NO_COOP");
+        if (e) return e[0] == '1';
+        if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return true;
+        for (char** v = ::environ; v && *v; ++v)
+            if (strncmp(*v, "NV_NSIGHT_INJECTION", 19) == 0) return true;
+        return false;
+    }();
     cfg.attrs = attrs; cfg.numAttrs = no_coop ? 1 : 2;
     int max_clusters = 0;
     NSD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
