@@ -21,10 +21,14 @@
 //     rejected, profiles/r02_k3_ring_experiment.log: one TMA per 64-column box issued by its own lane as soon as that
 //     box's zone had published -- the zones publish within a few hundred cycles of each other, while a per-lane
 //     fence.proxy.async + per-box barrier hand-offs cost 0.5 us per step forward and 2 us per step in the BPTT.)
-//   * LATENCY HIDING: two independent batch chains are in flight per CTA, each with its own TMEM accumulator and
-//     in/outbox, so the barrier + exchange latency of one chain runs under the MMAs and gate math of the other.
-//     B <= 64 (WPC = 1): a chain is 32 batch rows (UMMA N = 32) and owns one epilogue warpgroup.  B > 64 (WPC = 2): a
-//     chain is 64 rows (N = 64, same MMA cost), both warpgroups finalise 32 rows each and alternate between the chains.
+//   * LATENCY HIDING: independent batch chains are in flight per CTA, each with its own TMEM accumulator and in/outbox, so
+//     the barrier + exchange latency of one chain runs under the MMAs and gate math of the others (struct Chains below).
+//     B <= 64: two chains of 32 batch rows (UMMA N = 32), one epilogue warpgroup each.  B > 64: FOUR 32-row chains, two per
+//     warpgroup (the accumulators beside the stationary weights fill the tensor memory exactly); the earlier form with
+//     two 64-row chains that both warpgroups share (N = 64, same MMA cost) is kept behind NSD_GRU_WPC=2 for A/B.
+//   * The kernels signal griddepcontrol.launch_dependents at their top: a launch placed directly behind them with the
+//     programmatic-serialization attribute gets the ~20 SMs the recurrence leaves free (the optimizer update of the
+//     previous layer's gradient bucket runs there, elementwise.cu: adam_kernel late_wait).
 #include <stdlib.h>
 #include <string.h>
 
